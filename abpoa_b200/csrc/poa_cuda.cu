@@ -1,0 +1,296 @@
+/* poa_cuda.cu -- host side of the CUDA backend: per-stream device context, job staging,
+ * kernel launch, result collection.
+ *
+ * This is the seam the reference fills with its cpuid dispatcher
+ * (src/abpoa_dispatch_simd.c:58-81 -> simd_abpoa_align_sequence_to_subgraph,
+ * prototype src/abpoa_align_simd.h:12).  Here the only implementation is the sm_100a
+ * kernel family in poa_kernels.cu; a missing GPU is a fatal error, never a CPU fallback.
+ *
+ * A "stream context" owns one CUDA stream plus grow-only pinned/HBM buffers and runs a
+ * BATCH of independent alignment jobs per launch (one warp each).  The abpoa.h entry
+ * point uses a batch of one; abpoa_gpu.h drives many contexts from worker threads.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "poa_internal.h"
+#include "poa_device.cuh"
+#include "poa_engine.h"
+
+extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
+                                        const PoaParamsDev *prm, int n_jobs, cudaStream_t st);
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    poa_die("libabpoa_b200/cuda", "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct poa_dev_ctx {
+    int dev;
+    cudaStream_t st;
+    cudaEvent_t ev_k0, ev_k1;
+    uint8_t *h_in, *h_out, *d_in, *d_work, *d_planes;
+    size_t h_in_cap, h_out_cap, d_in_cap, d_work_cap, d_planes_cap;
+    size_t planes_limit;              /* hard cap for the plane slab (bytes); 0 = ask the device */
+    poa_engine_stats stats;
+};
+
+static void require_gpu(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        poa_die("libabpoa_b200", "no CUDA device available (%s). This library has no CPU path: the DP runs only on the GPU.",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+}
+
+poa_dev_ctx *poa_dev_ctx_new(void) {
+    require_gpu();
+    poa_dev_ctx *c = (poa_dev_ctx *)poa_xcalloc(1, sizeof(poa_dev_ctx));
+    const char *env = getenv("ABPOA_GPU_DEVICE");
+    if (env && *env) { c->dev = atoi(env); CK(cudaSetDevice(c->dev)); }
+    else CK(cudaGetDevice(&c->dev));
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev_k0)); CK(cudaEventCreate(&c->ev_k1));
+    return c;
+}
+
+void poa_dev_ctx_free(poa_dev_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->st);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_work) cudaFree(c->d_work);
+    if (c->d_planes) cudaFree(c->d_planes);
+    cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
+    cudaStreamDestroy(c->st);
+    free(c);
+}
+
+void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes) { c->planes_limit = bytes; }
+const poa_engine_stats *poa_dev_ctx_stats(const poa_dev_ctx *c) { return &c->stats; }
+void poa_dev_ctx_reset_stats(poa_dev_ctx *c) { memset(&c->stats, 0, sizeof c->stats); }
+int poa_dev_ctx_device(const poa_dev_ctx *c) { return c->dev; }
+
+static void grow_host(uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap) return;
+    size_t n = al256(need + need / 4);
+    if (*p) CK(cudaFreeHost(*p));
+    CK(cudaHostAlloc((void **)p, n, cudaHostAllocDefault));
+    *cap = n;
+}
+static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
+    if (need <= *cap) return;
+    size_t n = al256(slack ? need + need / 4 : need);
+    if (*p) CK(cudaFree(*p));
+    cudaError_t e = cudaMalloc((void **)p, n);
+    if (e != cudaSuccess && slack) { cudaGetLastError(); n = al256(need); e = cudaMalloc((void **)p, n); }
+    if (e != cudaSuccess) poa_die("libabpoa_b200/cuda", "cudaMalloc of %zu bytes failed: %s", n, cudaGetErrorString(e));
+    *cap = n;
+}
+
+void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
+    memset(p, 0, sizeof *p);
+    if (abpt->m > POA_MAX_M) poa_die("libabpoa_b200", "alphabet size m=%d exceeds the supported maximum %d", abpt->m, POA_MAX_M);
+    p->m = abpt->m; p->align_mode = abpt->align_mode; p->gap_mode = abpt->gap_mode;
+    p->e1 = abpt->gap_ext1; p->o1 = abpt->gap_open1; p->oe1 = abpt->gap_open1 + abpt->gap_ext1;
+    p->e2 = abpt->gap_ext2; p->o2 = abpt->gap_open2; p->oe2 = abpt->gap_open2 + abpt->gap_ext2;
+    p->zdrop = abpt->zdrop;
+    p->put_gap_on_right = abpt->put_gap_on_right; p->put_gap_at_end = abpt->put_gap_at_end;
+    p->ret_cigar = abpt->ret_cigar;
+    p->pn = bits == 16 ? 16 : 8;             /* AVX2: 256-bit vectors of int16 / int32 */
+    memcpy(p->mat, abpt->mat, (size_t)abpt->m * abpt->m * sizeof(int));
+}
+
+static inline int planes_of(int gap_mode) { return gap_mode == ABPOA_LINEAR_GAP ? 1 : (gap_mode == ABPOA_AFFINE_GAP ? 3 : 5); }
+
+/* plane slab (in 8-cell units) a job is given: `generous` = the full rectangle */
+static uint64_t plane_units_for(const poa_job *j, int gap_mode, int generous) {
+    const int P = planes_of(gap_mode);
+    const uint64_t full = (uint64_t)((j->plan.qlen + 1 + 7) / 8 + 1);
+    uint64_t per_row = full;
+    if (!generous && j->plan.w >= 0) {
+        const uint64_t est = (uint64_t)((2 * j->plan.w + 1 + 96 + 7) / 8 + 2);
+        if (est < per_row) per_row = est;
+    }
+    return per_row * (uint64_t)P * (uint64_t)j->plan.n_rows;
+}
+
+/* Run `n` jobs that share parameters and score width.  Results land in pinned host memory
+ * owned by the context (valid until the next run on this context). */
+static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
+    CK(cudaSetDevice(c->dev));
+    const int S = bits / 8;
+    /* ---- layout of the input arena: params | descs | blobs ---- */
+    size_t in_bytes = al256(sizeof(PoaParamsDev)) + al256((size_t)n * sizeof(PoaJobDesc));
+    const size_t off_desc = al256(sizeof(PoaParamsDev));
+    std::vector<size_t> blob_off(n), work_off(n), cig_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    for (int t = 0; t < n; ++t) { blob_off[t] = in_bytes; in_bytes += al256(jobs[idx[t]].plan.bytes); }
+    /* ---- work arena: results | per job (rowinfo, rowoff, cigar) ---- */
+    size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
+    for (int t = 0; t < n; ++t) {
+        const poa_job &j = jobs[idx[t]];
+        work_off[t] = work_bytes;
+        work_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)) + al256((size_t)j.plan.n_rows * 4);
+        cig_off[t] = work_bytes;
+        work_bytes += al256((size_t)(j.plan.qlen + j.plan.n_rows + 8) * 8);
+    }
+    uint64_t tot_units = 0;
+    for (int t = 0; t < n; ++t) {
+        units[t] = plane_units_for(&jobs[idx[t]], abpt->gap_mode, generous);
+        plane_off[t] = tot_units; tot_units += units[t];
+    }
+    const size_t plane_bytes = (size_t)tot_units * POA_GROUP * S;
+    grow_host(&c->h_in, &c->h_in_cap, in_bytes);
+    grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
+    grow_dev(&c->d_work, &c->d_work_cap, work_bytes, 1);
+    grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1);
+
+    poa_fill_params((PoaParamsDev *)c->h_in, abpt, bits);
+    PoaJobDesc *desc = (PoaJobDesc *)(c->h_in + off_desc);
+    for (int t = 0; t < n; ++t) {
+        poa_job &j = jobs[idx[t]];
+        poa_blob_fill(c->h_in + blob_off[t], &j.plan, j.abg, abpt, j.beg_node_id, j.end_node_id, j.query);
+        desc[t].blob = c->d_in + blob_off[t];
+        desc[t].planes = c->d_planes + (size_t)plane_off[t] * POA_GROUP * S;
+        desc[t].plane_cap_units = units[t];
+        desc[t].rowinfo = (PoaRowInfo *)(c->d_work + work_off[t]);
+        desc[t].rowoff = (uint32_t *)(c->d_work + work_off[t] + al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)));
+        desc[t].cigar = (uint64_t *)(c->d_work + cig_off[t]);
+        desc[t].cigar_cap = j.plan.qlen + j.plan.n_rows + 8;
+        desc[t].pad = 0;
+        desc[t].result = (PoaResultDev *)c->d_work + t;
+    }
+    CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CK(cudaEventRecord(c->ev_k0, c->st));
+    CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                        (const PoaParamsDev *)c->d_in, n, c->st));
+    CK(cudaEventRecord(c->ev_k1, c->st));
+    /* ---- results first (they say how many cigar words each job produced) ---- */
+    size_t out_bytes = al256((size_t)n * sizeof(PoaResultDev));
+    grow_host(&c->h_out, &c->h_out_cap, out_bytes);
+    CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
+    c->stats.kernel_ms += ms; c->stats.launches += 1; c->stats.h2d_bytes += in_bytes;
+
+    std::vector<PoaResultDev> resv(n);
+    memcpy(resv.data(), c->h_out, (size_t)n * sizeof(PoaResultDev));
+    std::vector<size_t> out_cig(n), out_band(n);
+    for (int t = 0; t < n; ++t) {
+        const poa_job &j = jobs[idx[t]];
+        out_cig[t] = out_bytes; out_bytes += al256((size_t)(resv[t].status == POA_ST_OK ? resv[t].n_ops : 0) * 8);
+        out_band[t] = out_bytes; if (j.want_bands) out_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo));
+    }
+    grow_host(&c->h_out, &c->h_out_cap, out_bytes);
+    for (int t = 0; t < n; ++t) {
+        const poa_job &j = jobs[idx[t]];
+        if (resv[t].status == POA_ST_OK && resv[t].n_ops > 0)
+            CK(cudaMemcpyAsync(c->h_out + out_cig[t], c->d_work + cig_off[t], (size_t)resv[t].n_ops * 8, cudaMemcpyDeviceToHost, c->st));
+        if (j.want_bands)
+            CK(cudaMemcpyAsync(c->h_out + out_band[t], c->d_work + work_off[t], (size_t)j.plan.n_rows * sizeof(PoaRowInfo), cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    c->stats.d2h_bytes += out_bytes;
+    for (int t = 0; t < n; ++t) {
+        poa_job &j = jobs[idx[t]];
+        j.status = resv[t].status;
+        j.best_score = resv[t].best_score; j.best_i = resv[t].best_i; j.best_j = resv[t].best_j;
+        j.start_i = resv[t].start_i; j.start_j = resv[t].start_j;
+        j.n_aln_bases = resv[t].n_aln_bases; j.n_matched_bases = resv[t].n_matched_bases;
+        j.cells = resv[t].cells; j.max_band = resv[t].max_band; j.bits = bits;
+        j.n_ops = resv[t].status == POA_ST_OK ? resv[t].n_ops : 0;
+        j.ops = (const uint64_t *)(c->h_out + out_cig[t]);
+        j.bands = j.want_bands ? (const int32_t *)(c->h_out + out_band[t]) : NULL;
+        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; }
+    }
+}
+
+/* Public engine entry: plans must be made (poa_blob_plan_make) by the caller.  Jobs whose
+ * band outgrew the estimated slab are re-run alone with the full rectangle.  Because the
+ * pinned output buffer is reused between launches, results are delivered through the
+ * `sink` callback right after the launch that produced them. */
+void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user) {
+    if (n <= 0) return;
+    std::vector<int> w16, w32;
+    for (int t = 0; t < n; ++t) (poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows) == 16 ? w16 : w32).push_back(t);
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<int> &v = pass == 0 ? w16 : w32;
+        const int bits = pass == 0 ? 16 : 32;
+        if (v.empty()) continue;
+        run_same_width(c, abpt, jobs, v.data(), (int)v.size(), bits, 0);
+        std::vector<int> redo;
+        for (int t : v) { if (jobs[t].status == POA_ST_PLANE_OVF) redo.push_back(t); else sink(user, &jobs[t]); }
+        for (int t : redo) {
+            c->stats.retries += 1;
+            run_same_width(c, abpt, jobs, &t, 1, bits, 1);
+            sink(user, &jobs[t]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ abpoa.h single-alignment path */
+struct single_sink_arg { abpoa_t *ab; abpoa_para_t *abpt; abpoa_res_t *res; };
+
+static void fail_job(const poa_job *j) {
+    if (j->status == POA_ST_BT_ERROR) poa_die("poa_backtrack", "Error in %s_backtrack.", "dp");
+    if (j->status == POA_ST_PLANE_OVF) poa_die("libabpoa_b200/cuda", "DP band planes exceed the device slab even at full width");
+    if (j->status != POA_ST_OK) poa_die("libabpoa_b200/cuda", "alignment kernel reported status %d", j->status);
+}
+
+/* translate one finished job into the caller's abpoa_res_t (reference: tail of the
+ * backtrack macros, src/abpoa_align_simd.c:187-192 and friends) */
+void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res) {
+    fail_job(j);
+    res->best_score = j->best_score;
+    if (!abpt->ret_cigar) return;
+    const int n = j->n_ops;
+    abpoa_cigar_t *cg = NULL;
+    if (n > 0) {
+        cg = (abpoa_cigar_t *)poa_xmalloc((size_t)n * sizeof(abpoa_cigar_t));
+        if (abpt->rev_cigar) memcpy(cg, j->ops, (size_t)n * 8);
+        else for (int t = 0; t < n; ++t) cg[t] = j->ops[n - 1 - t];
+    }
+    res->graph_cigar = cg; res->n_cigar = n; res->m_cigar = n;
+    const abpoa_graph_t *g = j->abg;
+    res->node_e = g->index_to_node_id[j->plan.beg_index + j->best_i]; res->query_e = j->best_j - 1;
+    res->node_s = g->index_to_node_id[j->plan.beg_index + j->start_i]; res->query_s = j->start_j - 1;
+    res->n_aln_bases += j->n_aln_bases; res->n_matched_bases += j->n_matched_bases;
+}
+
+static void single_sink(void *user, poa_job *j) {
+    single_sink_arg *a = (single_sink_arg *)user;
+    poa_job_to_res(j, a->abpt, a->res);
+    /* leave the band of every row where the reference leaves it (abpoa.h:139) */
+    abpoa_simd_matrix_t *abm = a->ab->abm;
+    const int nr = j->plan.n_rows;
+    if (nr > abm->rang_m) {
+        int m = poa_roundup32(nr);
+        abm->dp_beg = (int *)poa_xrealloc(abm->dp_beg, (size_t)m * sizeof(int));
+        abm->dp_end = (int *)poa_xrealloc(abm->dp_end, (size_t)m * sizeof(int));
+        abm->dp_beg_sn = (int *)poa_xrealloc(abm->dp_beg_sn, (size_t)m * sizeof(int));
+        abm->dp_end_sn = (int *)poa_xrealloc(abm->dp_end_sn, (size_t)m * sizeof(int));
+        abm->rang_m = m;
+    }
+    const int pn = j->bits == 16 ? 16 : 8;
+    for (int r = 0; r < nr - 1; ++r) {
+        abm->dp_beg[r] = j->bands[4 * r]; abm->dp_end[r] = j->bands[4 * r + 1];
+        abm->dp_beg_sn[r] = abm->dp_beg[r] / pn; abm->dp_end_sn[r] = abm->dp_end[r] / pn;
+    }
+}
+
+int poa_cuda_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id,
+                                        uint8_t *query, int qlen, abpoa_res_t *res) {
+    if (!ab->abm->s_mem) ab->abm->s_mem = poa_dev_ctx_new();
+    poa_dev_ctx *c = (poa_dev_ctx *)ab->abm->s_mem;
+    poa_job j; memset(&j, 0, sizeof j);
+    j.abg = ab->abg; j.beg_node_id = beg_node_id; j.end_node_id = end_node_id; j.query = query; j.want_bands = 1;
+    poa_blob_plan_make(&j.plan, ab->abg, abpt, beg_node_id, end_node_id, qlen);
+    single_sink_arg a = { ab, abpt, res };
+    poa_engine_run(c, abpt, &j, 1, single_sink, &a);
+    return 0;
+}

@@ -1,0 +1,79 @@
+/* poa_device.cuh -- device-side data layout shared by the CUDA kernels and their host
+ * launchers.  Not part of the ABI. */
+#ifndef POA_DEVICE_CUH
+#define POA_DEVICE_CUH
+
+#include <stdint.h>
+
+#define POA_GROUP 8                 /* DP cells handled by one lane per pass (one 16 B int16 vector) */
+#define POA_MAX_M 32                /* largest alphabet held in shared memory                         */
+#define POA_NEG32 (-(1 << 29))      /* "-inf" of the 32-bit register arithmetic                       */
+
+/* status codes written by the kernel */
+#define POA_ST_OK         0
+#define POA_ST_PLANE_OVF  1         /* band planes did not fit the slab handed to the job  */
+#define POA_ST_BT_ERROR   2         /* backtrack found no valid move (reference: fatal)    */
+#define POA_ST_CIGAR_OVF  3
+
+/* Input blob of one alignment job (host builds it in pinned memory, one H2D copy).
+ * All offsets are in bytes from the start of the blob; every section is 16 B aligned. */
+typedef struct PoaJobHeader {
+    int32_t n_rows;         /* DP rows incl. the SINK row (which is never computed)            */
+    int32_t qlen;
+    int32_t w;              /* band half width, < 0: unbanded                                   */
+    int32_t node_n;         /* graph->node_n: initial max_pos_left of every row                 */
+    int32_t off_base;       /* uint8  [n_rows]  residue code of the row's node                  */
+    int32_t off_remain;     /* int32  [n_rows]  band centre term (only if w >= 0)               */
+    int32_t off_predoff;    /* int32  [n_rows+1]                                                */
+    int32_t off_pred;       /* int32  [n_pred]  predecessor rows, reference in_id order          */
+    int32_t off_predscore;  /* int32  [n_pred]  -G path scores, or -1                            */
+    int32_t off_nodeid;     /* int32  [n_rows]                                                   */
+    int32_t off_live;       /* uint8  [n_rows]  sub-graph row mask, or -1 (all rows live)        */
+    int32_t off_qs;         /* uint8  [qlen+1 padded] shifted query: qs[j] = query[j-1], qs[0]=0 */
+    int32_t blob_bytes;
+    int32_t pad[3];
+} PoaJobHeader;
+
+/* one DP row's band and arg-max, 16 B: the adaptive band of a successor row is derived
+ * from (left, right) of its predecessors */
+typedef struct PoaRowInfo { int32_t beg, end, left, right; } PoaRowInfo;
+
+typedef struct PoaResultDev {
+    int32_t status;
+    int32_t best_score, best_i, best_j;
+    int32_t n_ops;                      /* cigar words written (in backtrack order)         */
+    int32_t start_i, start_j;           /* last (row, j) visited by the backtrack           */
+    int32_t n_aln_bases, n_matched_bases;
+    int32_t max_band;                   /* widest row (cells)                               */
+    int64_t cells;                      /* sum over DP rows of (end - beg + 1)              */
+    uint64_t plane_units_used;          /* 8-cell units of plane storage consumed           */
+} PoaResultDev;
+
+/* device pointers of one job */
+typedef struct PoaJobDesc {
+    const uint8_t *blob;
+    void *planes;                       /* score planes slab of this job                    */
+    uint64_t plane_cap_units;           /* capacity in units of POA_GROUP cells             */
+    PoaRowInfo *rowinfo;                /* [n_rows]                                         */
+    uint32_t *rowoff;                   /* [n_rows] start of the row's planes, in units     */
+    uint64_t *cigar;                    /* [cigar_cap]                                      */
+    int32_t cigar_cap;
+    int32_t pad;
+    PoaResultDev *result;
+} PoaJobDesc;
+
+/* alignment parameters, identical for all jobs of a launch */
+typedef struct PoaParamsDev {
+    int32_t m;
+    int32_t align_mode;                 /* ABPOA_GLOBAL/LOCAL/EXTEND_MODE                   */
+    int32_t gap_mode;
+    int32_t e1, o1, oe1, e2, o2, oe2;
+    int32_t zdrop;
+    int32_t put_gap_on_right, put_gap_at_end;
+    int32_t ret_cigar;
+    int32_t pn;                         /* lanes of the reference's AVX2 vector for the chosen
+                                           score width (16 / 8): only used for its beg-clamp rule */
+    int32_t mat[POA_MAX_M * POA_MAX_M];
+} PoaParamsDev;
+
+#endif

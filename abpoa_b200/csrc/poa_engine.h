@@ -1,0 +1,45 @@
+/* poa_engine.h -- private interface between the abpoa.h / abpoa_gpu.h front ends and the
+ * CUDA stream contexts of poa_cuda.cu. */
+#ifndef POA_ENGINE_H
+#define POA_ENGINE_H
+#include "poa_internal.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* one sequence-to-graph alignment handed to a stream context */
+typedef struct {
+    /* in */
+    const abpoa_graph_t *abg; int beg_node_id, end_node_id;
+    const uint8_t *query;
+    poa_blob_plan plan;
+    int want_bands;                 /* copy the per-row (beg,end,left,right) back            */
+    void *tag;                      /* caller's cookie                                        */
+    /* out (valid inside the sink callback only) */
+    int status, bits;
+    int best_score, best_i, best_j, start_i, start_j, n_aln_bases, n_matched_bases, max_band;
+    int64_t cells;
+    int n_ops; const uint64_t *ops; /* graph-CIGAR words in backtrack (reversed) order        */
+    const int32_t *bands;           /* [n_rows][4] when want_bands                            */
+} poa_job;
+
+typedef void (*poa_job_sink)(void *user, poa_job *job);
+
+typedef struct {
+    double kernel_ms;               /* CUDA-event time of the alignment kernels               */
+    int64_t cells, alignments, launches, retries;
+    uint64_t h2d_bytes, d2h_bytes;
+} poa_engine_stats;
+
+void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);
+void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res);
+void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes);
+const poa_engine_stats *poa_dev_ctx_stats(const poa_dev_ctx *c);
+void poa_dev_ctx_reset_stats(poa_dev_ctx *c);
+int poa_dev_ctx_device(const poa_dev_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+/* poa_flat.c -- flatten the host graph into the device job blob.
+ *
+ * Mirrors the set-up half of the reference's DP entry
+ * (src/abpoa_align_simd.c:1257-1269 index_map, :463-560 query profile / pre_index,
+ *  :1293-1303 score width) -- but produces one contiguous, 16 B-aligned byte blob that
+ * is copied to HBM with a single transfer (layout: PoaJobHeader in poa_device.cuh).
+ */
+#include "poa_internal.h"
+#include "poa_device.cuh"
+
+static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+/* w = wb + (int)(wf * qlen) with wf a C float, exactly as the reference evaluates it */
+int poa_band_halfwidth(const abpoa_para_t *abpt, int qlen) {
+    return abpt->wb < 0 ? -1 : abpt->wb + (int)(abpt->wf * qlen);
+}
+
+int poa_score_bits(const abpoa_para_t *abpt, int qlen, int n_rows) {
+    const int len = qlen > n_rows ? qlen : n_rows;
+    const int oe1 = abpt->gap_open1 + abpt->gap_ext1, oe2 = abpt->gap_open2 + abpt->gap_ext2;
+    const int max_score = POA_MAX(qlen * abpt->max_mat, len * abpt->gap_ext1 + abpt->gap_open1);
+    return max_score <= INT16_MAX - abpt->min_mis - oe1 - oe2 ? 16 : 32;
+}
+
+void poa_blob_plan_make(poa_blob_plan *pl, const abpoa_graph_t *abg, const abpoa_para_t *abpt,
+                        int beg_node_id, int end_node_id, int qlen) {
+    const int beg_index = abg->node_id_to_index[beg_node_id], end_index = abg->node_id_to_index[end_node_id];
+    pl->beg_index = beg_index;
+    pl->n_rows = end_index - beg_index + 1;
+    pl->qlen = qlen;
+    pl->whole_graph = (beg_node_id == ABPOA_SRC_NODE_ID && end_node_id == ABPOA_SINK_NODE_ID);
+    pl->w = poa_band_halfwidth(abpt, qlen);
+    pl->with_remain = (abpt->wb >= 0 || abpt->zdrop > 0);
+    pl->with_score = abpt->inc_path_score ? 1 : 0;
+    int n_pred = 0;
+    for (int r = 1; r < pl->n_rows; ++r) n_pred += abg->node[abg->index_to_node_id[beg_index + r]].in_edge_n;
+    pl->n_pred_max = n_pred;
+    const size_t nr = (size_t)pl->n_rows;
+    size_t b = al16(sizeof(struct PoaJobHeader));
+    b += al16(nr);                                   /* base      */
+    if (pl->with_remain) b += al16(nr * 4);          /* remain    */
+    b += al16((nr + 1) * 4);                         /* predoff   */
+    b += al16((size_t)n_pred * 4 + 4);               /* pred      */
+    if (pl->with_score) b += al16((size_t)n_pred * 4 + 4);
+    b += al16(nr * 4);                               /* node ids  */
+    if (!pl->whole_graph) b += al16(nr);             /* live mask */
+    b += al16((size_t)qlen + 1) + 16;                /* shifted query + one spare vector */
+    pl->bytes = b;
+}
+
+void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *abg, const abpoa_para_t *abpt,
+                   int beg_node_id, int end_node_id, const uint8_t *query) {
+    struct PoaJobHeader *h = (struct PoaJobHeader *)dst;
+    const int n_rows = pl->n_rows, beg_index = pl->beg_index, qlen = pl->qlen;
+    const size_t nr = (size_t)n_rows;
+    size_t off = al16(sizeof *h);
+    memset(h, 0, sizeof *h);
+    h->n_rows = n_rows; h->qlen = qlen; h->w = pl->w; h->node_n = abg->node_n;
+    h->off_base = (int32_t)off; off += al16(nr);
+    h->off_remain = -1;
+    if (pl->with_remain) { h->off_remain = (int32_t)off; off += al16(nr * 4); }
+    h->off_predoff = (int32_t)off; off += al16((nr + 1) * 4);
+    h->off_pred = (int32_t)off; off += al16((size_t)pl->n_pred_max * 4 + 4);
+    h->off_predscore = -1;
+    if (pl->with_score) { h->off_predscore = (int32_t)off; off += al16((size_t)pl->n_pred_max * 4 + 4); }
+    h->off_nodeid = (int32_t)off; off += al16(nr * 4);
+    h->off_live = -1;
+    if (!pl->whole_graph) { h->off_live = (int32_t)off; off += al16(nr); }
+    h->off_qs = (int32_t)off; off += al16((size_t)qlen + 1) + 16;
+    h->blob_bytes = (int32_t)off;
+    if (off != pl->bytes) poa_die(__func__, "blob size mismatch (%zu vs %zu)", off, pl->bytes);
+
+    uint8_t *base = dst + h->off_base;
+    int32_t *remain = pl->with_remain ? (int32_t *)(dst + h->off_remain) : NULL;
+    int32_t *predoff = (int32_t *)(dst + h->off_predoff), *pred = (int32_t *)(dst + h->off_pred);
+    int32_t *pscore = pl->with_score ? (int32_t *)(dst + h->off_predscore) : NULL;
+    int32_t *nodeid = (int32_t *)(dst + h->off_nodeid);
+    uint8_t *live = pl->whole_graph ? NULL : dst + h->off_live;
+    uint8_t *qs = dst + h->off_qs;
+
+    /* rows reachable from the begin node inside [beg_index, end_index] */
+    if (live) {
+        memset(live, 0, nr);
+        live[0] = live[n_rows - 1] = 1;
+        for (int r = 0; r < n_rows - 2; ++r) {
+            if (!live[r]) continue;
+            const abpoa_node_t *nd = &abg->node[abg->index_to_node_id[beg_index + r]];
+            for (int e = 0; e < nd->out_edge_n; ++e) {
+                const int t = abg->node_id_to_index[nd->out_id[e]] - beg_index;
+                if (t >= 0 && t < n_rows) live[t] = 1;
+            }
+        }
+    }
+    const int end_remain = remain ? abg->node_id_to_max_remain[end_node_id] : 0;
+    int np = 0;
+    predoff[0] = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const int id = abg->index_to_node_id[beg_index + r];
+        const abpoa_node_t *nd = &abg->node[id];
+        nodeid[r] = id; base[r] = nd->base;
+        if (remain) remain[r] = abg->node_id_to_max_remain[id] - end_remain - 1;
+        if (r > 0) {
+            for (int e = 0; e < nd->in_edge_n; ++e) {
+                const int pr = abg->node_id_to_index[nd->in_id[e]] - beg_index;
+                if (pr < 0 || pr >= n_rows) continue;
+                if (live && !live[pr]) continue;
+                if (pscore) pscore[np] = poa_edge_path_score(abg, id, e);
+                pred[np++] = pr;
+            }
+        }
+        predoff[r + 1] = np;
+    }
+    (void)abpt;
+    qs[0] = 0;
+    memcpy(qs + 1, query, (size_t)qlen);
+    memset(qs + 1 + qlen, 0, (size_t)h->blob_bytes - h->off_qs - 1 - (size_t)qlen);
+}

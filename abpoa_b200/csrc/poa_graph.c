@@ -1,0 +1,534 @@
+/* poa_graph.c -- the partial-order graph on the host.
+ *
+ * The sequence-to-graph DP runs on the GPU; what stays on the host is the (cheap,
+ * strictly sequential) graph bookkeeping between two alignments of a read group:
+ * fusing a graph-CIGAR into the graph, re-deriving the topological order, the edge
+ * order and the `max_remain` band centre.  Those three decide the DP's row order, its
+ * predecessor order and therefore every tie-break, so their behaviour follows the
+ * reference exactly (same observable results for the same call sequence):
+ *
+ *   abpoa_add_graph_edge            reference src/abpoa_graph.c:480-556
+ *   abpoa_add_subgraph_alignment    reference src/abpoa_graph.c:689-774
+ *   abpoa_BFS_set_node_index        reference src/abpoa_graph.c:221-266  (FIFO Kahn, aligned groups)
+ *   edge order (weight, exchange)   reference src/abpoa_graph.c:192-219
+ *   abpoa_BFS_set_node_remain       reference src/abpoa_graph.c:268-309
+ *   abpoa_topological_sort          reference src/abpoa_graph.c:322-357
+ *   MSA column ranks (LIFO Kahn)    reference src/abpoa_graph.c:359-418
+ *   abpoa_reset / init / free       reference src/abpoa_graph.c:99-189, 783-875
+ *
+ * Layout note: abpoa_graph_t / abpoa_node_t are ABI (callers walk them), so nodes keep
+ * their per-node edge arrays.  Scratch that the reference re-mallocs on every sort
+ * (degree counters, BFS queue) lives in a private tail of the graph object instead.
+ */
+#include <math.h>
+#include "poa_internal.h"
+
+typedef struct {
+    abpoa_graph_t pub;          /* must stay first: callers hold &pub */
+    int *deg;                   /* degree counters for the Kahn passes */
+    int *queue;                 /* BFS queue / DFS stack storage        */
+    int scratch_m;
+} poa_graph_x;
+
+static inline poa_graph_x *gx(abpoa_graph_t *abg) { return (poa_graph_x *)abg; }
+
+static void scratch_reserve(abpoa_graph_t *abg, int n) {
+    poa_graph_x *x = gx(abg);
+    if (n <= x->scratch_m) return;
+    int m = poa_roundup32(n);
+    x->deg = (int *)poa_xrealloc(x->deg, (size_t)m * sizeof(int));
+    x->queue = (int *)poa_xrealloc(x->queue, (size_t)m * sizeof(int));
+    x->scratch_m = m;
+}
+
+/* ------------------------------------------------------------------ nodes */
+static void node_blank(abpoa_node_t *nd, int id) {
+    memset(nd, 0, sizeof *nd);
+    nd->node_id = id;
+}
+
+static void node_release(abpoa_node_t *nd) {
+    if (nd->in_edge_m > 0) { free(nd->in_id); free(nd->in_edge_weight); }
+    if (nd->out_edge_m > 0) {
+        free(nd->out_id); free(nd->out_edge_weight);
+        if (nd->read_ids) {
+            if (nd->read_ids_n > 0)
+                for (int j = 0; j < nd->out_edge_m; ++j) free(nd->read_ids[j]);
+            free(nd->read_ids);
+        }
+    }
+    if (nd->m_read > 0) free(nd->read_weight);
+    if (nd->aligned_node_m > 0) free(nd->aligned_node_id);
+}
+
+static void nodes_reserve(abpoa_graph_t *abg, int want) {
+    if (want <= abg->node_m) return;
+    int m = poa_roundup32(want);
+    abg->node = (abpoa_node_t *)poa_xrealloc(abg->node, (size_t)m * sizeof(abpoa_node_t));
+    for (int i = abg->node_m; i < m; ++i) node_blank(&abg->node[i], i);
+    abg->node_m = m;
+}
+
+abpoa_graph_t *poa_graph_new(void) {
+    poa_graph_x *x = (poa_graph_x *)poa_xcalloc(1, sizeof(poa_graph_x));
+    abpoa_graph_t *abg = &x->pub;
+    abg->node_m = 0;
+    nodes_reserve(abg, 2);
+    abg->node_n = 2;                 /* SRC = 0, SINK = 1 always exist */
+    return abg;
+}
+
+void poa_graph_free(abpoa_graph_t *abg) {
+    if (!abg) return;
+    poa_graph_x *x = gx(abg);
+    for (int i = 0; i < abg->node_m; ++i) node_release(&abg->node[i]);
+    free(abg->node);
+    free(abg->index_to_node_id); free(abg->node_id_to_index); free(abg->node_id_to_msa_rank);
+    free(abg->node_id_to_max_pos_left); free(abg->node_id_to_max_pos_right); free(abg->node_id_to_max_remain);
+    free(x->deg); free(x->queue);
+    free(x);
+}
+
+/* per-node index arrays: grow together, allocate the optional ones on first need */
+static void index_arrays_reserve(abpoa_graph_t *abg, const abpoa_para_t *abpt, int n) {
+    int m = abg->index_rank_m;
+    if (n > m) {
+        m = poa_roundup32(n);
+        abg->index_to_node_id = (int *)poa_xrealloc(abg->index_to_node_id, (size_t)m * sizeof(int));
+        abg->node_id_to_index = (int *)poa_xrealloc(abg->node_id_to_index, (size_t)m * sizeof(int));
+        if (abg->node_id_to_msa_rank) abg->node_id_to_msa_rank = (int *)poa_xrealloc(abg->node_id_to_msa_rank, (size_t)m * sizeof(int));
+        if (abg->node_id_to_max_pos_left) {
+            abg->node_id_to_max_pos_left = (int *)poa_xrealloc(abg->node_id_to_max_pos_left, (size_t)m * sizeof(int));
+            abg->node_id_to_max_pos_right = (int *)poa_xrealloc(abg->node_id_to_max_pos_right, (size_t)m * sizeof(int));
+        }
+        if (abg->node_id_to_max_remain) abg->node_id_to_max_remain = (int *)poa_xrealloc(abg->node_id_to_max_remain, (size_t)m * sizeof(int));
+        abg->index_rank_m = m;
+    }
+    if (abpt) {
+        if ((abpt->out_msa || abpt->max_n_cons > 1 || abpt->cons_algrm == ABPOA_MF) && !abg->node_id_to_msa_rank)
+            abg->node_id_to_msa_rank = (int *)poa_xmalloc((size_t)m * sizeof(int));
+        if (abpt->wb >= 0 && !abg->node_id_to_max_pos_left) {
+            abg->node_id_to_max_pos_left = (int *)poa_xmalloc((size_t)m * sizeof(int));
+            abg->node_id_to_max_pos_right = (int *)poa_xmalloc((size_t)m * sizeof(int));
+        }
+        if ((abpt->wb >= 0 || abpt->zdrop > 0) && !abg->node_id_to_max_remain)
+            abg->node_id_to_max_remain = (int *)poa_xmalloc((size_t)m * sizeof(int));
+    }
+}
+
+abpoa_cons_t *poa_cons_new(void) { return (abpoa_cons_t *)poa_xcalloc(1, sizeof(abpoa_cons_t)); }
+
+void poa_cons_clear(abpoa_cons_t *abc) {
+    if (abc->n_cons > 0) {
+        free(abc->clu_n_seq); free(abc->cons_len);
+        for (int i = 0; i < abc->n_cons; ++i) {
+            if (abc->cons_node_ids) free(abc->cons_node_ids[i]);
+            if (abc->cons_base) free(abc->cons_base[i]);
+            if (abc->cons_cov) free(abc->cons_cov[i]);
+            if (abc->clu_read_ids) free(abc->clu_read_ids[i]);
+            if (abc->cons_phred_score) free(abc->cons_phred_score[i]);
+        }
+        free(abc->cons_node_ids); free(abc->cons_base); free(abc->cons_cov);
+        free(abc->clu_read_ids); free(abc->cons_phred_score);
+    }
+    if (abc->msa_len > 0 && abc->msa_base) {
+        for (int i = 0; i < abc->n_seq + abc->n_cons; ++i) free(abc->msa_base[i]);
+        free(abc->msa_base);
+    }
+    memset(abc, 0, sizeof *abc);
+}
+
+void poa_cons_free(abpoa_cons_t *abc) { if (abc) { poa_cons_clear(abc); free(abc); } }
+
+void abpoa_clean_msa_cons(abpoa_t *ab) { poa_cons_clear(ab->abc); }
+
+/* ------------------------------------------------------------------ handle */
+abpoa_t *abpoa_init(void) {
+    abpoa_t *ab = (abpoa_t *)poa_xmalloc(sizeof(abpoa_t));
+    ab->abg = poa_graph_new();
+    ab->abs = poa_seq_new();
+    ab->abm = (abpoa_simd_matrix_t *)poa_xcalloc(1, sizeof(abpoa_simd_matrix_t));
+    ab->abc = poa_cons_new();
+    return ab;
+}
+
+void abpoa_free(abpoa_t *ab) {
+    if (!ab) return;
+    poa_graph_free(ab->abg);
+    poa_seq_free(ab->abs);
+    if (ab->abm) {
+        if (ab->abm->s_mem) poa_dev_ctx_free((poa_dev_ctx *)ab->abm->s_mem);
+        free(ab->abm->dp_beg); free(ab->abm->dp_end); free(ab->abm->dp_beg_sn); free(ab->abm->dp_end_sn);
+        free(ab->abm);
+    }
+    poa_cons_free(ab->abc);
+    free(ab);
+}
+
+/* Empty the graph but keep every allocation for the next read group. */
+void abpoa_reset(abpoa_t *ab, abpoa_para_t *abpt, int qlen) {
+    abpoa_graph_t *abg = ab->abg;
+    abg->is_topological_sorted = abg->is_called_cons = abg->is_set_msa_rank = 0;
+    for (int i = 0; i < abg->node_n; ++i) {
+        abpoa_node_t *nd = &abg->node[i];
+        if (nd->read_ids_n > 0)
+            for (int j = 0; j < nd->out_edge_n; ++j) memset(nd->read_ids[j], 0, (size_t)nd->read_ids_n * sizeof(uint64_t));
+        nd->in_edge_n = nd->out_edge_n = nd->aligned_node_n = 0;
+        nd->n_read = nd->n_span_read = 0;
+    }
+    abg->node_n = 2;
+    nodes_reserve(abg, qlen + 2);
+    index_arrays_reserve(abg, abpt, abg->node_m);
+    ab->abs->n_seq = 0;
+    poa_cons_clear(ab->abc);
+}
+
+/* ------------------------------------------------------------------ edges */
+static void in_edges_reserve(abpoa_node_t *nd, int want) {
+    if (want <= nd->in_edge_m) return;
+    int m = POA_MAX(2, poa_roundup32(want));
+    nd->in_id = (int *)(nd->in_edge_m ? poa_xrealloc(nd->in_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+    nd->in_edge_weight = (int *)(nd->in_edge_m ? poa_xrealloc(nd->in_edge_weight, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+    nd->in_edge_m = m;
+}
+
+static void out_edges_reserve(abpoa_node_t *nd, int want, int want_read_ids) {
+    if (want > nd->out_edge_m) {
+        int old = nd->out_edge_m, m = POA_MAX(2, poa_roundup32(want));
+        nd->out_id = (int *)(old ? poa_xrealloc(nd->out_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+        nd->out_edge_weight = (int *)(old ? poa_xrealloc(nd->out_edge_weight, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+        if (nd->read_ids) {
+            nd->read_ids = (uint64_t **)poa_xrealloc(nd->read_ids, (size_t)m * sizeof(uint64_t *));
+            for (int j = old; j < m; ++j)
+                nd->read_ids[j] = nd->read_ids_n > 0 ? (uint64_t *)poa_xcalloc(nd->read_ids_n, sizeof(uint64_t)) : NULL;
+        }
+        nd->out_edge_m = m;
+    }
+    if (want_read_ids && !nd->read_ids)
+        nd->read_ids = (uint64_t **)poa_xcalloc(nd->out_edge_m, sizeof(uint64_t *));
+}
+
+/* make every out-edge slot of `nd` hold a bitset of at least `words` 64-bit words */
+static void read_ids_widen(abpoa_node_t *nd, int words) {
+    if (nd->read_ids_n >= words) return;
+    for (int j = 0; j < nd->out_edge_m; ++j) {
+        if (nd->read_ids_n == 0) nd->read_ids[j] = (uint64_t *)poa_xcalloc(words, sizeof(uint64_t));
+        else {
+            nd->read_ids[j] = (uint64_t *)poa_xrealloc(nd->read_ids[j], (size_t)words * sizeof(uint64_t));
+            memset(nd->read_ids[j] + nd->read_ids_n, 0, (size_t)(words - nd->read_ids_n) * sizeof(uint64_t));
+        }
+    }
+    nd->read_ids_n = words;
+}
+
+int abpoa_add_graph_node(abpoa_graph_t *abg, uint8_t base) {
+    int id = abg->node_n;
+    nodes_reserve(abg, id + 1);
+    abg->node[id].base = base;
+    abg->node_n = id + 1;
+    return id;
+}
+
+int abpoa_add_graph_edge(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, int w, uint8_t add_read_id,
+                         uint8_t add_read_weight, int read_id, int read_ids_n, int tot_read_n) {
+    if (from_id < 0 || from_id >= abg->node_n || to_id < 0 || to_id >= abg->node_n)
+        poa_die(__func__, "node_n: %d\tfrom_id: %d\tto_id: %d.", abg->node_n, from_id, to_id);
+    abpoa_node_t *from = &abg->node[from_id], *to = &abg->node[to_id];
+    int slot = -1;
+    if (check_edge) {            /* the edge may exist already: bump both copies of its weight */
+        for (int i = 0; i < to->in_edge_n; ++i)
+            if (to->in_id[i] == from_id) { to->in_edge_weight[i] += w; break; }
+        for (int i = 0; i < from->out_edge_n; ++i)
+            if (from->out_id[i] == to_id) { from->out_edge_weight[i] += w; slot = i; break; }
+    }
+    if (slot < 0) {              /* new edge, appended after the existing ones */
+        in_edges_reserve(to, to->in_edge_n + 1);
+        to->in_id[to->in_edge_n] = from_id; to->in_edge_weight[to->in_edge_n] = w; ++to->in_edge_n;
+        out_edges_reserve(from, from->out_edge_n + 1, add_read_id);
+        slot = from->out_edge_n;
+        from->out_id[slot] = to_id; from->out_edge_weight[slot] = w; ++from->out_edge_n;
+    }
+    if (add_read_id) {           /* which reads run through this edge: feeds the RC-MSA */
+        if (read_ids_n <= 0) poa_die(__func__, "Unexpected read_ids_n: %d.", read_ids_n);
+        out_edges_reserve(from, from->out_edge_n, 1);
+        read_ids_widen(from, read_ids_n);
+        from->read_ids[slot][read_id >> 6] |= 1ULL << (read_id & 63);
+    }
+    from->n_read += 1;
+    if (add_read_weight) {
+        if (tot_read_n > from->m_read) {
+            from->read_weight = (int *)poa_xrealloc(from->read_weight, (size_t)tot_read_n * sizeof(int));
+            memset(from->read_weight + from->m_read, 0, (size_t)(tot_read_n - from->m_read) * sizeof(int));
+            from->m_read = tot_read_n;
+        }
+        from->read_weight[read_id] = w;
+    }
+    return 1;
+}
+
+/* nodes that occupy the same MSA column ("aligned" = mismatch alternatives) */
+static void aligned_push(abpoa_node_t *nd, int id) {
+    if (nd->aligned_node_n == nd->aligned_node_m) {
+        int m = nd->aligned_node_m ? nd->aligned_node_m << 1 : 2;
+        nd->aligned_node_id = (int *)(nd->aligned_node_m ? poa_xrealloc(nd->aligned_node_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+        nd->aligned_node_m = m;
+    }
+    nd->aligned_node_id[nd->aligned_node_n++] = id;
+}
+
+static void aligned_join(abpoa_graph_t *abg, int node_id, int new_id) {
+    abpoa_node_t *node = abg->node;
+    for (int i = 0; i < node[node_id].aligned_node_n; ++i) {
+        int sib = node[node_id].aligned_node_id[i];
+        aligned_push(&node[sib], new_id);
+        aligned_push(&node[new_id], sib);
+    }
+    aligned_push(&node[node_id], new_id);
+    aligned_push(&node[new_id], node_id);
+}
+
+static int aligned_with_base(const abpoa_graph_t *abg, int node_id, uint8_t base) {
+    const abpoa_node_t *nd = &abg->node[node_id];
+    for (int i = 0; i < nd->aligned_node_n; ++i)
+        if (abg->node[nd->aligned_node_id[i]].base == base) return nd->aligned_node_id[i];
+    return -1;
+}
+
+/* ------------------------------------------------------------------ orders */
+/* Topological index = dequeue order of a FIFO Kahn traversal in which a node becomes
+ * ready only together with all nodes of its aligned group; the group is enqueued as
+ * (trigger node, then its aligned list in stored order). */
+void abpoa_BFS_set_node_index(abpoa_graph_t *abg, int src_id, int sink_id) {
+    const int n = abg->node_n;
+    scratch_reserve(abg, n);
+    int *deg = gx(abg)->deg, *q = gx(abg)->queue;
+    const abpoa_node_t *node = abg->node;
+    for (int i = 0; i < n; ++i) deg[i] = node[i].in_edge_n;
+    int head = 0, tail = 0, index = 0;
+    q[tail++] = src_id;
+    while (head < tail) {
+        int cur = q[head++];
+        abg->index_to_node_id[index] = cur;
+        abg->node_id_to_index[cur] = index++;
+        if (cur == sink_id) return;
+        for (int e = 0; e < node[cur].out_edge_n; ++e) {
+            int v = node[cur].out_id[e];
+            if (--deg[v] != 0) continue;
+            int ready = 1;
+            for (int a = 0; a < node[v].aligned_node_n; ++a)
+                if (deg[node[v].aligned_node_id[a]] != 0) { ready = 0; break; }
+            if (!ready) continue;
+            q[tail++] = v;
+            for (int a = 0; a < node[v].aligned_node_n; ++a) q[tail++] = node[v].aligned_node_id[a];
+        }
+    }
+    poa_die(__func__, "Failed to set node index.");
+}
+
+/* Edge lists ordered by weight, heaviest first.  This is the DP's predecessor order and
+ * the order every tie is broken in, so the permutation must be the one the reference's
+ * in-place exchange pass produces (swap whenever w[j] < w[k], j < k; not stable). */
+static void order_edges_by_weight(abpoa_graph_t *abg) {
+    for (int i = 0; i < abg->node_n; ++i) {
+        abpoa_node_t *nd = &abg->node[i];
+        for (int j = 0; j + 1 < nd->in_edge_n; ++j)
+            for (int k = j + 1; k < nd->in_edge_n; ++k)
+                if (nd->in_edge_weight[j] < nd->in_edge_weight[k]) {
+                    int t = nd->in_id[j]; nd->in_id[j] = nd->in_id[k]; nd->in_id[k] = t;
+                    t = nd->in_edge_weight[j]; nd->in_edge_weight[j] = nd->in_edge_weight[k]; nd->in_edge_weight[k] = t;
+                }
+        for (int j = 0; j + 1 < nd->out_edge_n; ++j)
+            for (int k = j + 1; k < nd->out_edge_n; ++k)
+                if (nd->out_edge_weight[j] < nd->out_edge_weight[k]) {
+                    int t = nd->out_id[j]; nd->out_id[j] = nd->out_id[k]; nd->out_id[k] = t;
+                    t = nd->out_edge_weight[j]; nd->out_edge_weight[j] = nd->out_edge_weight[k]; nd->out_edge_weight[k] = t;
+                    if (nd->read_ids_n > 0) { uint64_t *r = nd->read_ids[j]; nd->read_ids[j] = nd->read_ids[k]; nd->read_ids[k] = r; }
+                }
+    }
+}
+
+/* max_remain[v] = 1 + max_remain[heaviest out-neighbour, first on ties]; SINK = -1.
+ * Reverse Kahn from the sink; it is the centre line of the adaptive band. */
+void abpoa_BFS_set_node_remain(abpoa_graph_t *abg, int src_id, int sink_id) {
+    const int n = abg->node_n;
+    scratch_reserve(abg, n);
+    int *deg = gx(abg)->deg, *q = gx(abg)->queue, *remain = abg->node_id_to_max_remain;
+    const abpoa_node_t *node = abg->node;
+    for (int i = 0; i < n; ++i) { deg[i] = node[i].out_edge_n; remain[i] = 0; }
+    int head = 0, tail = 0;
+    q[tail++] = sink_id; remain[sink_id] = -1;
+    while (head < tail) {
+        int cur = q[head++];
+        if (cur != sink_id) {
+            int best_w = -1, best = -1;
+            for (int e = 0; e < node[cur].out_edge_n; ++e)
+                if (node[cur].out_edge_weight[e] > best_w) { best_w = node[cur].out_edge_weight[e]; best = node[cur].out_id[e]; }
+            remain[cur] = remain[best] + 1;
+        }
+        if (cur == src_id) return;
+        for (int e = 0; e < node[cur].in_edge_n; ++e) {
+            int u = node[cur].in_id[e];
+            if (--deg[u] == 0) q[tail++] = u;
+        }
+    }
+    poa_die(__func__, "Failed to set node remain.");
+}
+
+void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
+    if (abg->node_n <= 0) { fprintf(stderr, "[%s] Empty graph.\n", __func__); return; }
+    const int n = abg->node_n;
+    index_arrays_reserve(abg, abpt, n);
+    abpoa_BFS_set_node_index(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    order_edges_by_weight(abg);
+    if (abpt->wb >= 0) {
+        for (int i = 0; i < n; ++i) { abg->node_id_to_max_pos_right[i] = 0; abg->node_id_to_max_pos_left[i] = n; }
+        abpoa_BFS_set_node_remain(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    } else if (abpt->zdrop > 0) {
+        abpoa_BFS_set_node_remain(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    }
+    abg->is_topological_sorted = 1;
+}
+
+/* MSA column rank: Kahn traversal with a LIFO; a popped node that has no rank yet
+ * takes the next rank together with its whole aligned group. */
+void poa_set_msa_rank(abpoa_graph_t *abg, int src_id, int sink_id) {
+    if (abg->is_set_msa_rank) return;
+    const int n = abg->node_n;
+    scratch_reserve(abg, n);
+    index_arrays_reserve(abg, NULL, n);
+    if (!abg->node_id_to_msa_rank) abg->node_id_to_msa_rank = (int *)poa_xmalloc((size_t)abg->index_rank_m * sizeof(int));
+    int *deg = gx(abg)->deg, *st = gx(abg)->queue, *rank = abg->node_id_to_msa_rank;
+    const abpoa_node_t *node = abg->node;
+    for (int i = 0; i < n; ++i) deg[i] = node[i].in_edge_n;
+    int top = 0, next_rank = 0;
+    st[top++] = src_id; rank[src_id] = -1;
+    while (top > 0) {
+        int cur = st[--top];
+        if (rank[cur] < 0) {
+            rank[cur] = next_rank;
+            for (int a = 0; a < node[cur].aligned_node_n; ++a) rank[node[cur].aligned_node_id[a]] = next_rank;
+            ++next_rank;
+        }
+        if (cur == sink_id) { abg->is_set_msa_rank = 1; return; }
+        for (int e = 0; e < node[cur].out_edge_n; ++e) {
+            int v = node[cur].out_id[e];
+            if (--deg[v] != 0) continue;
+            int ready = 1;
+            for (int a = 0; a < node[v].aligned_node_n; ++a)
+                if (deg[node[v].aligned_node_id[a]] != 0) { ready = 0; break; }
+            if (!ready) continue;
+            st[top++] = v; rank[v] = -1;
+            for (int a = 0; a < node[v].aligned_node_n; ++a) { st[top++] = node[v].aligned_node_id[a]; rank[node[v].aligned_node_id[a]] = -1; }
+        }
+    }
+    poa_die(__func__, "Error in set_msa_rank.");
+}
+
+/* -G: per-in-edge additive path score max(round(ln(edge_w / node_w)), -20)
+ * (reference src/abpoa_graph.c:421-437) */
+int poa_edge_path_score(const abpoa_graph_t *abg, int node_id, int in_idx) {
+    const abpoa_node_t *nd = &abg->node[node_id];
+    if (in_idx < 0 || in_idx >= nd->in_edge_n) poa_die(__func__, "Unexpected in_id_idx: %d.", in_idx);
+    const abpoa_node_t *pre = &abg->node[nd->in_id[in_idx]];
+    int node_w = 0;
+    for (int e = 0; e < pre->out_edge_n; ++e) node_w += pre->out_edge_weight[e];
+    int edge_w = nd->in_edge_weight[in_idx];
+    if (node_w == 0 || edge_w == 0) return 0;
+    int s = (int)round(log((double)edge_w / (double)node_w));
+    return POA_MAX(s, -20);
+}
+
+/* ------------------------------------------------------------------ fusion */
+static void bump_span_reads(abpoa_graph_t *abg, int src_id, int sink_id, int inc_both_ends) {
+    int lo = abg->node_id_to_index[src_id], hi = abg->node_id_to_index[sink_id];
+    for (int i = lo + 1; i < hi; ++i) abg->node[abg->index_to_node_id[i]].n_span_read += 1;
+    if (inc_both_ends) { abg->node[src_id].n_span_read += 1; abg->node[sink_id].n_span_read += 1; }
+}
+
+/* first read of a group: a simple chain SRC -> b0 -> b1 ... -> SINK */
+static void seed_graph_with_sequence(abpoa_graph_t *abg, abpoa_para_t *abpt, const uint8_t *seq, const int *weight, int seq_l,
+                                     int *qpos_to_node_id, uint8_t add_read_id, uint8_t add_read_weight,
+                                     int read_id, int read_ids_n, int tot_read_n) {
+    if (seq_l <= 0) return;
+    int last = ABPOA_SRC_NODE_ID;
+    for (int i = 0; i < seq_l; ++i) {
+        int cur = abpoa_add_graph_node(abg, seq[i]);
+        if (qpos_to_node_id) qpos_to_node_id[i] = cur;
+        abpoa_add_graph_edge(abg, last, cur, 0, weight[i], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+        abg->node[cur].n_span_read = abg->node[last].n_span_read;
+        last = cur;
+    }
+    abpoa_add_graph_edge(abg, last, ABPOA_SINK_NODE_ID, 0, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+    abg->is_called_cons = abg->is_set_msa_rank = abg->is_topological_sorted = 0;
+    abpoa_topological_sort(abg, abpt);
+    bump_span_reads(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, 1);
+}
+
+/* Thread one aligned read through the graph:
+ *   M on an equal base     -> reuse the node (edge weight += w)
+ *   M on a different base  -> reuse the aligned sibling with that base, else new node
+ *                             registered as aligned with the whole sibling set
+ *   I                      -> one new node per inserted base
+ *   D                      -> nothing
+ * then close with an edge to end_node_id and re-sort. */
+int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *_weight,
+                                 int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends) {
+    abpoa_graph_t *abg = ab->abg;
+    const int read_ids_n = 1 + ((tot_read_n - 1) >> 6);
+    const uint8_t add_read_id = abpt->use_read_ids, add_read_weight = abpt->use_qv & (abpt->max_n_cons > 1);
+    int *weight = _weight;
+    if (!weight) {
+        weight = (int *)poa_xmalloc((size_t)POA_MAX(seq_l, 1) * sizeof(int));
+        for (int i = 0; i < seq_l; ++i) weight[i] = 1;
+    }
+    if (abg->node_n < 2) poa_die(__func__, "Graph node: %d.", abg->node_n);
+    if (abg->node_n == 2) {
+        seed_graph_with_sequence(abg, abpt, seq, weight, seq_l, qpos_to_node_id, add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+    } else if (res.n_cigar > 0) {
+        int qi = -1, last_id = beg_node_id, last_is_new = 0;
+        for (int c = 0; c < res.n_cigar; ++c) {
+            const abpoa_cigar_t cg = res.graph_cigar[c];
+            const int op = (int)(cg & 0xf);
+            if (op == ABPOA_CMATCH) {
+                const int node_id = (int)((cg >> 34) & 0x3fffffff);
+                ++qi;
+                const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
+                int target, target_is_new = 0;
+                if (abg->node[node_id].base == seq[qi]) target = node_id;
+                else if ((target = aligned_with_base(abg, node_id, seq[qi])) < 0) {
+                    target = abpoa_add_graph_node(abg, seq[qi]); target_is_new = 1;
+                }
+                abpoa_add_graph_edge(abg, last_id, target, target_is_new ? 0 : 1 - last_is_new, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
+                if (target_is_new) abg->node[target].n_span_read = abg->node[last_id].n_span_read;
+                if (!add) abg->node[last_id].n_read--;
+                if (target_is_new) aligned_join(abg, node_id, target);
+                last_id = target; last_is_new = target_is_new;
+                if (qpos_to_node_id) qpos_to_node_id[qi] = last_id;
+            } else if (op == ABPOA_CINS || op == ABPOA_CSOFT_CLIP || op == ABPOA_CHARD_CLIP) {
+                const int len = (int)((cg >> 4) & 0x3fffffff);
+                for (int k = 0; k < len; ++k) {
+                    ++qi;
+                    const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
+                    int nid = abpoa_add_graph_node(abg, seq[qi]);
+                    abpoa_add_graph_edge(abg, last_id, nid, 0, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
+                    abg->node[nid].n_span_read = abg->node[last_id].n_span_read;
+                    if (!add) abg->node[last_id].n_read--;
+                    last_id = nid; last_is_new = 1;
+                    if (qpos_to_node_id) qpos_to_node_id[qi] = last_id;
+                }
+            } /* ABPOA_CDEL: the read skips this node */
+        }
+        abpoa_add_graph_edge(abg, last_id, end_node_id, 1 - last_is_new, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+        abg->is_called_cons = abg->is_set_msa_rank = abg->is_topological_sorted = 0;
+        abpoa_topological_sort(abg, abpt);
+        bump_span_reads(abg, beg_node_id, end_node_id, inc_both_ends);
+    }
+    if (!_weight) free(weight);
+    return 0;
+}
+
+int abpoa_add_graph_alignment(abpoa_t *ab, abpoa_para_t *abpt, uint8_t *seq, int *weight, int seq_l, int *qpos_to_node_id,
+                              abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends) {
+    return abpoa_add_subgraph_alignment(ab, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, seq, weight, seq_l, qpos_to_node_id,
+                                        res, read_id, tot_read_n, inc_both_ends);
+}

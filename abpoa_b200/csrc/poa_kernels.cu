@@ -1,0 +1,593 @@
+/* poa_kernels.cu -- sm_100a kernels for the adaptive-banded sequence-to-POA-graph DP
+ * and its backtrace.
+ *
+ * What is computed (the specification, validated cell-for-cell against the reference):
+ *   band + recurrences  reference src/abpoa_align_simd.c:727-815 (linear), :817-933 (affine),
+ *                       :935-1074 (convex); first row :582-688; band macros src/abpoa_align.h:34-35
+ *   row arg-max / band hints   reference src/abpoa_align_simd.c:1107-1130
+ *   end cell                   reference src/abpoa_align_simd.c:1092-1105
+ *   backtrace state machine    reference src/abpoa_align_simd.c:116-458
+ *
+ * How it is mapped to the GPU (nothing of this exists in the reference):
+ *   - ONE WARP PER ALIGNMENT, one CTA = one warp, thousands of independent alignments
+ *     (one per read group) resident at once.  Rows (graph nodes in topological order) are
+ *     sequentially dependent; the cells of a row's band are the parallel axis.
+ *   - A lane owns POA_GROUP = 8 consecutive cells (one 16 B int16 vector); a warp covers 256
+ *     cells per pass and loops for wider bands.  Rows are stored on an absolute 8-cell grid,
+ *     so the predecessor's cells for the same columns are one aligned vector load and the
+ *     "j-1" neighbour is one warp shuffle.
+ *   - The horizontal gap dependency F[j] = max(T[j-1]-oe, F[j-1]-e) is rewritten as an
+ *     exclusive prefix-max of A[k] = T[k]-oe+e*k, resolved by an in-lane chain plus one
+ *     5-step warp-shuffle max-scan per plane.
+ *   - Row maximum + first/last arg-max use the redux unit and ballots; the adaptive band of
+ *     row i is pulled from its predecessors' (left,right) instead of being pushed to
+ *     successors (same values, no scattered writes).
+ *   - Arithmetic is done in 32-bit registers with the DPX add-max instructions; planes are
+ *     stored as int16 when the reference would use int16 (same criterion), else int32.
+ *   - The backtrace runs in the same warp right after the forward pass, lanes evaluating the
+ *     predecessors of the current cell in parallel and electing the first hit in reference order.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "poa_device.cuh"
+
+#define FULL 0xffffffffu
+#define NEG POA_NEG32
+
+enum { LG = 0, AG = 1, CG = 2 };
+enum { GLOBAL = 0, LOCAL = 1, EXTEND = 2 };
+
+#define OP_M   0x1
+#define OP_E1  0x2
+#define OP_E2  0x4
+#define OP_E   0x6
+#define OP_F1  0x8
+#define OP_F2  0x10
+#define OP_F   0x18
+#define OP_ALL 0x1f
+
+/* ------------------------------------------------------------------ plane vectors */
+__device__ __forceinline__ void ld8(const int16_t *p, int v[8]) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    v[0] = (int)(short)(u.x & 0xffff); v[1] = ((int)u.x) >> 16;
+    v[2] = (int)(short)(u.y & 0xffff); v[3] = ((int)u.y) >> 16;
+    v[4] = (int)(short)(u.z & 0xffff); v[5] = ((int)u.z) >> 16;
+    v[6] = (int)(short)(u.w & 0xffff); v[7] = ((int)u.w) >> 16;
+}
+__device__ __forceinline__ void ld8(const int32_t *p, int v[8]) {
+    const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ unsigned pack16(int lo, int hi) {
+    lo = max(lo, -32768); hi = max(hi, -32768);
+    return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+}
+__device__ __forceinline__ void st8(int16_t *p, const int v[8]) {
+    uint4 u;
+    u.x = pack16(v[0], v[1]); u.y = pack16(v[2], v[3]); u.z = pack16(v[4], v[5]); u.w = pack16(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+__device__ __forceinline__ void st8(int32_t *p, const int v[8]) {
+    int4 a, b;
+    a.x = max(v[0], NEG); a.y = max(v[1], NEG); a.z = max(v[2], NEG); a.w = max(v[3], NEG);
+    b.x = max(v[4], NEG); b.y = max(v[5], NEG); b.z = max(v[6], NEG); b.w = max(v[7], NEG);
+    reinterpret_cast<int4 *>(p)[0] = a; reinterpret_cast<int4 *>(p)[1] = b;
+}
+__device__ __forceinline__ void fill8(int v[8], int x) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = x;
+}
+/* exclusive max-scan across the warp of one value per lane; returns the exclusive prefix and
+ * the warp total (lane 31's inclusive value) */
+__device__ __forceinline__ int warp_excl_max(int v, int lane, int &total) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v = max(v, t);
+    }
+    total = __shfl_sync(FULL, v, 31);
+    int e = __shfl_up_sync(FULL, v, 1);
+    return lane == 0 ? 2 * NEG : e;
+}
+
+template <int GAP> struct Planes {
+    static constexpr int N = GAP == LG ? 1 : (GAP == AG ? 3 : 5);
+    static constexpr int H = 0, E1 = 1, E2 = 2, F1 = (GAP == AG ? 2 : 3), F2 = 4;
+};
+
+/* ------------------------------------------------------------------ job view */
+struct JobView {
+    const uint8_t *base; const int32_t *remain, *predoff, *pred, *predscore, *nodeid; const uint8_t *live, *qs;
+    int n_rows, qlen, w, node_n;
+};
+__device__ __forceinline__ JobView open_job(const uint8_t *blob) {
+    const PoaJobHeader *h = reinterpret_cast<const PoaJobHeader *>(blob);
+    JobView v;
+    v.n_rows = h->n_rows; v.qlen = h->qlen; v.w = h->w; v.node_n = h->node_n;
+    v.base = blob + h->off_base;
+    v.remain = reinterpret_cast<const int32_t *>(blob + h->off_remain);
+    v.predoff = reinterpret_cast<const int32_t *>(blob + h->off_predoff);
+    v.pred = reinterpret_cast<const int32_t *>(blob + h->off_pred);
+    v.predscore = h->off_predscore >= 0 ? reinterpret_cast<const int32_t *>(blob + h->off_predscore) : nullptr;
+    v.nodeid = reinterpret_cast<const int32_t *>(blob + h->off_nodeid);
+    v.live = h->off_live >= 0 ? blob + h->off_live : nullptr;
+    v.qs = blob + h->off_qs;
+    return v;
+}
+
+/* ================================================================== backtrace */
+struct BtPred {            /* what lane k knows about predecessor k of the current row */
+    int row;               /* predecessor row, -1 if lane has none                       */
+    int h_jm1, h_j, e1_j, e2_j, ps;
+    bool in_m, in_e;       /* j-1 / j inside the predecessor's band                      */
+};
+
+template <int GAP, typename ST>
+__device__ __forceinline__ BtPred bt_load_pred(const JobView &jv, const PoaRowInfo *rowinfo, const uint32_t *rowoff,
+                                               const ST *planes, int pb, int np, int k, int j) {
+    BtPred r; r.row = -1; r.h_jm1 = r.h_j = r.e1_j = r.e2_j = NEG; r.ps = 0; r.in_m = r.in_e = false;
+    if (k < np) {
+        r.row = jv.pred[pb + k];
+        if (jv.predscore) r.ps = jv.predscore[pb + k];
+        const PoaRowInfo pi = rowinfo[r.row];
+        const int g0 = pi.beg >> 3, ng = (pi.end >> 3) - g0 + 1;
+        const ST *rp = planes + (size_t)rowoff[r.row] * POA_GROUP - (size_t)g0 * POA_GROUP;
+        r.in_m = (j - 1 >= pi.beg && j - 1 <= pi.end);
+        r.in_e = (j >= pi.beg && j <= pi.end);
+        if (r.in_m) r.h_jm1 = (int)rp[j - 1];
+        if (r.in_e) {
+            r.h_j = (int)rp[j];
+            if (GAP != LG) r.e1_j = (int)rp[(size_t)ng * POA_GROUP + j];
+            if (GAP == CG) r.e2_j = (int)rp[(size_t)2 * ng * POA_GROUP + j];
+        }
+    }
+    return r;
+}
+
+struct CigarSink {
+    uint64_t *out; int cap; int n; uint64_t pending; int lane; int ovf;
+    __device__ __forceinline__ void emit(uint64_t w) {
+        if (n < cap) { if (lane == 0) out[n] = w; } else ovf = 1;
+        ++n;
+    }
+    __device__ __forceinline__ void flush() { if (pending) { emit(pending); pending = 0; } }
+    __device__ __forceinline__ void ins(int len, int qpos) {           /* consecutive insertions merge */
+        if (pending) pending += (uint64_t)len << 4;
+        else pending = ((uint64_t)(uint32_t)qpos << 34) | ((uint64_t)len << 4) | 1u;
+    }
+    __device__ __forceinline__ void match(int node_id, int qpos) { flush(); emit(((uint64_t)node_id << 34) | ((uint64_t)qpos << 4)); }
+    __device__ __forceinline__ void del(int node_id) { flush(); emit(((uint64_t)node_id << 34) | (1ull << 4) | 2u); }
+};
+
+template <int GAP, typename ST, int MODE>
+__device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const PoaParamsDev *prm, const int *mat_s,
+                              int lane, int best_i, int best_j, PoaResultDev &res) {
+    typedef Planes<GAP> PL;
+    const ST *planes = reinterpret_cast<const ST *>(jd.planes);
+    const PoaRowInfo *rowinfo = jd.rowinfo; const uint32_t *rowoff = jd.rowoff;
+    const int m = prm->m, e1 = prm->e1, oe1 = prm->oe1, e2 = prm->e2, oe2 = prm->oe2;
+    const int qlen = jv.qlen;
+    CigarSink cg; cg.out = jd.cigar; cg.cap = jd.cigar_cap; cg.n = 0; cg.pending = 0; cg.lane = lane; cg.ovf = 0;
+
+    int i = best_i, j = best_j, start_i = best_i, start_j = best_j, cur = OP_ALL;
+    int n_aln = 0, n_match = 0, err = 0;
+    int gap_at_end = prm->put_gap_at_end; const int gap_on_right = prm->put_gap_on_right;
+    if (best_j < qlen) cg.ins(qlen - best_j, qlen - 1);
+
+    while (i > 0 && j > 0) {
+        const PoaRowInfo ri = rowinfo[i];
+        const int gi0 = ri.beg >> 3, ngi = (ri.end >> 3) - gi0 + 1;
+        const ST *rp = planes + (size_t)rowoff[i] * POA_GROUP - (size_t)gi0 * POA_GROUP;
+        const bool in_j = (j >= ri.beg && j <= ri.end), in_jm1 = (j - 1 >= ri.beg && j - 1 <= ri.end);
+        const int h_ij = in_j ? (int)rp[j] : NEG;
+        if (MODE == LOCAL && h_ij == 0) break;
+        start_i = i; start_j = j;
+        const int id = jv.nodeid[i];
+        const int rb = jv.base[i], qc = jv.qs[j];
+        const int s = mat_s[rb * m + qc];
+        const int pb = jv.predoff[i], np = jv.predoff[i + 1] - pb;
+        const BtPred pc0 = bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, lane, j);
+        int hit = 0;
+
+        /* first predecessor (reference order) whose diagonal cell explains H[i][j] */
+        auto try_match = [&]() {
+            for (int kb = 0; kb < np; kb += 32) {
+                const BtPred pc = kb == 0 ? pc0 : bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, kb + lane, j);
+                const bool ok = pc.row >= 0 && pc.in_m && (pc.h_jm1 + s + pc.ps == h_ij);
+                const unsigned b = __ballot_sync(FULL, ok);
+                if (b) {
+                    const int sel = __ffs(b) - 1;
+                    const int prow = __shfl_sync(FULL, pc.row, sel);
+                    cg.match(id, j - 1);
+                    i = prow; --j; cur = OP_ALL; hit = 1;
+                    ++n_aln; n_match += (rb == qc);
+                    return;
+                }
+            }
+        };
+
+        if (!gap_on_right && !gap_at_end && (GAP == LG || (cur & OP_M))) try_match();
+
+        if (!hit && (GAP == LG || (cur & OP_E))) {                      /* deletion: come from (p, j) */
+            int e1_ij = NEG, e2_ij = NEG;
+            if (GAP != LG && in_j) {
+                e1_ij = (int)rp[(size_t)PL::E1 * ngi * POA_GROUP + j];
+                if (GAP == CG) e2_ij = (int)rp[(size_t)PL::E2 * ngi * POA_GROUP + j];
+            }
+            for (int kb = 0; kb < np && !hit; kb += 32) {
+                const BtPred pc = kb == 0 ? pc0 : bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, kb + lane, j);
+                int code = 0;                                           /* 1: via E1, 2: via E2; +4: gap opened at p */
+                if (pc.row >= 0 && pc.in_e) {
+                    if (GAP == LG) {
+                        if (pc.h_j - e1 + pc.ps == h_ij) code = 1;
+                    } else {
+                        if (cur & OP_E1) {
+                            const bool ok = (cur & OP_M) ? (h_ij == pc.e1_j + pc.ps) : (e1_ij == pc.e1_j - e1 + pc.ps);
+                            if (ok) code = 1 | ((pc.h_j - oe1 == pc.e1_j) ? 4 : 0);
+                        }
+                        if (GAP == CG && code == 0 && (cur & OP_E2)) {
+                            const bool ok = (cur & OP_M) ? (h_ij == pc.e2_j + pc.ps) : (e2_ij == pc.e2_j - e2 + pc.ps);
+                            if (ok) code = 2 | ((pc.h_j - oe2 == pc.e2_j) ? 4 : 0);
+                        }
+                    }
+                }
+                const unsigned b = __ballot_sync(FULL, code != 0);
+                if (b) {
+                    const int sel = __ffs(b) - 1;
+                    const int prow = __shfl_sync(FULL, pc.row, sel);
+                    const int c = __shfl_sync(FULL, code, sel);
+                    if (GAP != LG) cur = (c & 4) ? (OP_M | OP_F) : ((c & 3) == 1 ? OP_E1 : OP_E2);
+                    cg.del(id);
+                    i = prow; hit = 1; gap_at_end = 0;
+                }
+            }
+        }
+
+        if (!hit && (GAP == LG || (cur & OP_F))) {                      /* insertion: come from (i, j-1) */
+            const int h_jm1 = in_jm1 ? (int)rp[j - 1] : NEG;
+            if (GAP == LG) {
+                if (h_jm1 - e1 == h_ij) hit = 1;
+            } else {
+                if (GAP == AG || (cur & OP_F1)) {
+                    const int f_ij = in_j ? (int)rp[(size_t)PL::F1 * ngi * POA_GROUP + j] : NEG;
+                    const int f_jm1 = in_jm1 ? (int)rp[(size_t)PL::F1 * ngi * POA_GROUP + j - 1] : NEG;
+                    if (!(cur & OP_M) || h_ij == f_ij) {
+                        if (h_jm1 - oe1 == f_ij) { cur = OP_M | OP_E; hit = 1; }
+                        else if (f_jm1 - e1 == f_ij) { cur = OP_F1; hit = 1; }
+                    }
+                }
+                if (GAP == CG && !hit && (cur & OP_F2)) {
+                    const int f_ij = in_j ? (int)rp[(size_t)PL::F2 * ngi * POA_GROUP + j] : NEG;
+                    const int f_jm1 = in_jm1 ? (int)rp[(size_t)PL::F2 * ngi * POA_GROUP + j - 1] : NEG;
+                    if (!(cur & OP_M) || h_ij == f_ij) {
+                        if (h_jm1 - oe2 == f_ij) { cur = OP_M | OP_E; hit = 1; }
+                        else if (f_jm1 - e2 == f_ij) { cur = OP_F2; hit = 1; }
+                    }
+                }
+            }
+            if (hit) { cg.ins(1, j - 1); --j; gap_at_end = 0; ++n_aln; }
+        }
+
+        if (!hit && (GAP == LG || (cur & OP_M))) { try_match(); if (hit) gap_at_end = 0; }
+        if (!hit) { err = 1; break; }
+    }
+    if (!err && j > 0) cg.ins(j, j - 1);
+    cg.flush();
+    if (lane == 0) {
+        res.n_ops = cg.n; res.start_i = start_i; res.start_j = start_j;
+        res.n_aln_bases = n_aln; res.n_matched_bases = n_match;
+        if (err) res.status = POA_ST_BT_ERROR; else if (cg.ovf) res.status = POA_ST_CIGAR_OVF;
+    }
+}
+
+/* ================================================================== forward DP + backtrace */
+template <int GAP, typename ST, int MODE>
+__global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm, int n_jobs) {
+    typedef Planes<GAP> PL;
+    __shared__ int mat_s[POA_MAX_M * POA_MAX_M];
+    const int lane = threadIdx.x;
+    const int job = blockIdx.x;
+    if (job >= n_jobs) return;
+    const int m = prm->m;
+    for (int t = lane; t < m * m; t += 32) mat_s[t] = prm->mat[t];
+    __syncwarp();
+
+    const PoaJobDesc jd = jobs[job];
+    const JobView jv = open_job(jd.blob);
+    ST *planes = reinterpret_cast<ST *>(jd.planes);
+    PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
+    const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
+    const bool banded = w >= 0;
+    const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
+    const int pnv = prm->pn;
+
+    PoaResultDev res;
+    res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
+    res.start_i = res.start_j = 0; res.n_aln_bases = res.n_matched_bases = 0; res.max_band = 0; res.cells = 0; res.plane_units_used = 0;
+
+    uint64_t cursor = 0;                 /* bump allocator over the job's plane slab, in 8-cell units */
+    int64_t cells = 0; int max_band = 0;
+    int best_score = NEG, best_i = 0, best_j = 0, best_row = 0;
+    bool stop = false;
+
+    /* ---------------- row 0 (the begin node): reference first_dp, :582-688 ---------------- */
+    {
+        int end0 = qlen;
+        if (banded) end0 = min(qlen, max(0, qlen - jv.remain[0]) + w);
+        const int g1 = end0 >> 3, ngrp = g1 + 1;
+        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; } return; }
+        for (int gp = 0; gp <= g1; gp += 32) {
+            const int g = gp + lane;
+            if (g <= g1) {
+                int h[8], ea[8], eb[8], fa[8], fb[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = g * 8 + c;
+                    if (MODE == LOCAL) { h[c] = ea[c] = eb[c] = fa[c] = fb[c] = (j <= end0) ? 0 : NEG; }
+                    else if (j > end0) { h[c] = ea[c] = eb[c] = fa[c] = fb[c] = NEG; }
+                    else if (GAP == LG) { h[c] = -e1 * j; }
+                    else if (j == 0) { h[c] = 0; ea[c] = -oe1; eb[c] = -oe2; fa[c] = fb[c] = NEG; }
+                    else {
+                        fa[c] = -o1 - e1 * j; fb[c] = -o2 - e2 * j; ea[c] = eb[c] = NEG;
+                        h[c] = (GAP == CG) ? max(fa[c], fb[c]) : fa[c];
+                    }
+                }
+                ST *rp = planes + (size_t)g * POA_GROUP;
+                st8(rp, h);
+                if (GAP != LG) { st8(rp + (size_t)PL::E1 * ngrp * POA_GROUP, ea); st8(rp + (size_t)PL::F1 * ngrp * POA_GROUP, fa); }
+                if (GAP == CG) { st8(rp + (size_t)PL::E2 * ngrp * POA_GROUP, eb); st8(rp + (size_t)PL::F2 * ngrp * POA_GROUP, fb); }
+            }
+        }
+        if (lane == 0) { PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0; rowinfo[0] = r0; rowoff[0] = 0; }
+        cursor = (uint64_t)ngrp * PL::N;
+        cells += end0 + 1; max_band = end0 + 1;
+        __syncwarp();
+    }
+
+    /* ---------------- rows 1 .. n_rows-2 in topological order ---------------- */
+    for (int i = 1; i < n_rows - 1 && !stop; ++i) {
+        if (jv.live && !jv.live[i]) continue;
+        const int pb = jv.predoff[i], np = jv.predoff[i + 1] - pb;
+        const int rbase = jv.base[i];
+
+        /* lane k holds predecessor k (chunk 0); band hints are reductions over all of them */
+        int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
+        int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
+        for (int kb = 0; kb < np; kb += 32) {
+            const int k = kb + lane;
+            int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
+            if (k < np) {
+                const int prow = jv.pred[pb + k];
+                const PoaRowInfo pi = rowinfo[prow];
+                l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
+                if (kb == 0) { pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_off = rowoff[prow]; pk_ps = jv.predscore ? jv.predscore[pb + k] : 0; }
+            }
+            if (banded) {
+                ml = min(ml, __reduce_min_sync(FULL, l1));
+                mr = max(mr, __reduce_max_sync(FULL, r1));
+                min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b1));
+            }
+        }
+        int beg = 0, end = qlen;
+        if (banded) {
+            const int r = qlen - jv.remain[i];
+            beg = max(0, min(ml, r) - w);
+            end = min(qlen, max(mr, r) + w);
+            if (np > 0 && beg / pnv < min_pre_beg / pnv) beg = min_pre_beg;      /* reference's vector-granular clamp */
+        }
+        const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
+        if (cursor + (uint64_t)ngrp * PL::N > jd.plane_cap_units || cursor + (uint64_t)ngrp * PL::N > 0xffffffffull) {
+            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; }
+            return;
+        }
+        const uint32_t my_off = (uint32_t)cursor;
+        cursor += (uint64_t)ngrp * PL::N;
+        ST *rowp = planes + (size_t)my_off * POA_GROUP;
+        cells += (end >= beg) ? (end - beg + 1) : 0;
+        max_band = max(max_band, end - beg + 1);
+
+        int carry1 = 2 * NEG, carry2 = 2 * NEG;            /* prefix-max of A over finished passes */
+        int row_max = NEG, row_left = -1, row_right = -1;
+        const int jbase = g0 * 8;
+
+        for (int gp = g0; gp <= g1; gp += 32) {
+            const int g = gp + lane;
+            const bool active = g <= g1;
+            int M[8], X1[8], X2[8];                         /* M: diagonal term; X1/X2: E1/E2 inputs (LG: X1 = vertical term) */
+            fill8(M, NEG); fill8(X1, NEG); if (GAP == CG) fill8(X2, NEG);
+
+            for (int kb = 0; kb < np; kb += 32) {
+                int c_row = pk_row, c_beg = pk_beg, c_end = pk_end, c_ps = pk_ps; uint32_t c_off = pk_off;
+                if (kb > 0) {                               /* rare: more than 32 predecessors */
+                    const int k = kb + lane; c_row = -1;
+                    if (k < np) {
+                        c_row = jv.pred[pb + k]; const PoaRowInfo pi = rowinfo[c_row];
+                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? jv.predscore[pb + k] : 0;
+                    }
+                }
+                const int nk = min(32, np - kb);
+                for (int k = 0; k < nk; ++k) {
+                    const int p_beg = __shfl_sync(FULL, c_beg, k), p_end = __shfl_sync(FULL, c_end, k);
+                    const uint32_t p_off = __shfl_sync(FULL, c_off, k);
+                    const int ps = jv.predscore ? __shfl_sync(FULL, c_ps, k) : 0;
+                    const int pg0 = p_beg >> 3, pg1 = p_end >> 3, png = pg1 - pg0 + 1;
+                    const ST *ph = planes + (size_t)p_off * POA_GROUP;
+                    int hp[8], ep1[8], ep2[8];
+                    const bool inr = active && g >= pg0 && g <= pg1;
+                    if (inr) {
+                        const ST *q = ph + (size_t)(g - pg0) * POA_GROUP;
+                        ld8(q, hp);
+                        if (GAP != LG) ld8(q + (size_t)PL::E1 * png * POA_GROUP, ep1);
+                        if (GAP == CG) ld8(q + (size_t)PL::E2 * png * POA_GROUP, ep2);
+                    } else { fill8(hp, NEG); if (GAP != LG) fill8(ep1, NEG); if (GAP == CG) fill8(ep2, NEG); }
+                    int hm1 = __shfl_up_sync(FULL, hp[7], 1);
+                    if (lane == 0) {
+                        const int gm = g - 1;
+                        hm1 = (gm >= pg0 && gm <= pg1) ? (int)ph[(size_t)(gm - pg0) * POA_GROUP + 7] : NEG;
+                        if (MODE == LOCAL && g == 0) hm1 = 0;
+                    }
+                    M[0] = max(M[0], hm1 + ps);
+#pragma unroll
+                    for (int c = 1; c < 8; ++c) M[c] = max(M[c], hp[c - 1] + ps);
+                    if (GAP == LG) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) X1[c] = max(X1[c], hp[c] - e1 + ps);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) X1[c] = max(X1[c], ep1[c] + ps);
+                        if (GAP == CG) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) X2[c] = max(X2[c], ep2[c] + ps);
+                        }
+                    }
+                }
+            }
+
+            /* substitution scores of this row's residue against the lane's 8 query bases */
+            uint2 qv = make_uint2(0u, 0u);
+            if (active) qv = *reinterpret_cast<const uint2 *>(jv.qs + (size_t)g * 8);
+            const int *mrow = mat_s + rbase * m;
+            int T[8], H[8], Fa[8], Fb[8];
+            bool inb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = g * 8 + c;
+                inb[c] = active && j >= beg && j <= end;
+                const unsigned code = ((c < 4 ? qv.x : qv.y) >> (8 * (c & 3))) & 0xffu;
+                int s = mrow[code];
+                if (j == 0) s = 0;
+                const int hm = inb[c] ? M[c] + s : NEG;
+                if (!inb[c]) { X1[c] = NEG; if (GAP == CG) X2[c] = NEG; }
+                M[c] = hm;
+                if (GAP == LG) T[c] = max(hm, X1[c]);
+                else if (GAP == AG) T[c] = hm;               /* affine: F opens from the M-only value (reference :916) */
+                else T[c] = max(hm, max(X1[c], X2[c]));
+            }
+
+            /* horizontal dependency as prefix-max of A[k] = T[k] - oe + e*jr */
+            int a1[8], a2[8], l1 = 2 * NEG, l2 = 2 * NEG;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int jr = g * 8 + c - jbase;
+                a1[c] = T[c] + ((GAP == LG ? 0 : -oe1) + e1 * jr);
+                l1 = max(l1, a1[c]);
+                if (GAP == CG) { a2[c] = T[c] + (-oe2 + e2 * jr); l2 = max(l2, a2[c]); }
+            }
+            int tot1, tot2 = 0;
+            int x1 = max(warp_excl_max(l1, lane, tot1), carry1);
+            carry1 = max(carry1, tot1);
+            int x2 = 2 * NEG;
+            if (GAP == CG) { x2 = max(warp_excl_max(l2, lane, tot2), carry2); carry2 = max(carry2, tot2); }
+
+            int E1o[8], E2o[8];
+            int lmax = NEG, lfirst = -1, llast = -1;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = g * 8 + c, jr = j - jbase;
+                if (GAP == LG) {
+                    x1 = max(x1, a1[c]);                    /* inclusive: H[j] = max(H0[j], H[j-1]-e) */
+                    int h = max(x1 - e1 * jr, NEG);
+                    if (MODE == LOCAL) h = max(h, 0);
+                    H[c] = inb[c] ? h : NEG;
+                } else {
+                    const int f1 = max(x1 - e1 * (jr - 1), NEG);
+                    x1 = max(x1, a1[c]);
+                    Fa[c] = f1;
+                    if (GAP == AG) {
+                        const int t = max(M[c], X1[c]);
+                        int h = max(t, f1);
+                        if (MODE == LOCAL) h = max(h, 0);
+                        E1o[c] = (h == t) ? max(X1[c] - e1, h - oe1) : (MODE == LOCAL ? 0 : NEG);
+                        H[c] = h;
+                    } else {
+                        const int f2 = max(x2 - e2 * (jr - 1), NEG);
+                        x2 = max(x2, a2[c]);
+                        Fb[c] = f2;
+                        int h = max(T[c], max(f1, f2));
+                        if (MODE == LOCAL) h = max(h, 0);
+                        int eo1 = max(X1[c] - e1, h - oe1), eo2 = max(X2[c] - e2, h - oe2);
+                        if (MODE == LOCAL) { eo1 = max(eo1, 0); eo2 = max(eo2, 0); }
+                        E1o[c] = eo1; E2o[c] = eo2; H[c] = h;
+                    }
+                    if (!inb[c]) { H[c] = NEG; E1o[c] = NEG; if (GAP == CG) E2o[c] = NEG; }
+                }
+                if (inb[c]) {
+                    if (H[c] > lmax) { lmax = H[c]; lfirst = llast = j; }
+                    else if (H[c] == lmax) llast = j;
+                }
+            }
+
+            if (active) {
+                ST *q = rowp + (size_t)(g - g0) * POA_GROUP;
+                st8(q, H);
+                if (GAP != LG) { st8(q + (size_t)PL::E1 * ngrp * POA_GROUP, E1o); st8(q + (size_t)PL::F1 * ngrp * POA_GROUP, Fa); }
+                if (GAP == CG) { st8(q + (size_t)PL::E2 * ngrp * POA_GROUP, E2o); st8(q + (size_t)PL::F2 * ngrp * POA_GROUP, Fb); }
+            }
+
+            /* row maximum with first / last arg-max (reference :1107-1119) */
+            if (banded || MODE != GLOBAL) {
+                const int pm = __reduce_max_sync(FULL, lmax);
+                const unsigned bm = __ballot_sync(FULL, lmax == pm && lfirst >= 0);
+                if (bm) {
+                    const int pl = __shfl_sync(FULL, lfirst, __ffs(bm) - 1);
+                    const int pr = __shfl_sync(FULL, llast, 31 - __clz(bm));
+                    if (pm > row_max) { row_max = pm; row_left = pl; row_right = pr; }
+                    else if (pm == row_max) row_right = pr;
+                }
+            }
+        }
+        if (lane == 0) { PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right; rowinfo[i] = ri; rowoff[i] = my_off; }
+        if (MODE == LOCAL) {
+            if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_left; }
+        } else if (MODE == EXTEND) {
+            if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_right; best_row = i; }
+            else if (prm->zdrop > 0) {
+                const int delta = jv.remain[best_row] - jv.remain[i];
+                if (best_score - row_max > prm->zdrop + e1 * abs(delta - (row_right - best_j))) stop = true;
+            }
+        }
+        __syncwarp();
+    }
+
+    /* ---------------- global mode: best end cell among the SINK's predecessors ---------------- */
+    if (MODE == GLOBAL) {
+        const int sb = jv.predoff[n_rows - 1], sn = jv.predoff[n_rows] - sb;
+        for (int k = 0; k < sn; ++k) {
+            const int prow = jv.pred[sb + k];
+            const PoaRowInfo pi = rowinfo[prow];
+            const int endc = qlen > pi.end ? pi.end : qlen;
+            const int pg0 = pi.beg >> 3;
+            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow] * POA_GROUP + (endc - pg0 * 8)] : NEG;
+            if (v > best_score) { best_score = v; best_i = prow; best_j = endc; }
+        }
+    }
+    res.best_score = best_score; res.best_i = best_i; res.best_j = best_j;
+    res.cells = cells; res.max_band = max_band; res.plane_units_used = cursor;
+    if (lane == 0) *jd.result = res;
+    __syncwarp();
+    if (prm->ret_cigar) poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+}
+
+/* ------------------------------------------------------------------ launcher */
+template <int GAP, typename ST>
+static cudaError_t launch_mode(int mode, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, cudaStream_t st) {
+    switch (mode) {
+    case GLOBAL: poa_align_kernel<GAP, ST, GLOBAL><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
+    case LOCAL:  poa_align_kernel<GAP, ST, LOCAL><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
+    default:     poa_align_kernel<GAP, ST, EXTEND><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
+    }
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
+                                        const PoaParamsDev *prm, int n_jobs, cudaStream_t st) {
+    if (n_jobs <= 0) return cudaSuccess;
+    if (bits == 16) {
+        if (gap_mode == LG) return launch_mode<LG, int16_t>(align_mode, jobs, prm, n_jobs, st);
+        if (gap_mode == AG) return launch_mode<AG, int16_t>(align_mode, jobs, prm, n_jobs, st);
+        return launch_mode<CG, int16_t>(align_mode, jobs, prm, n_jobs, st);
+    }
+    if (gap_mode == LG) return launch_mode<LG, int32_t>(align_mode, jobs, prm, n_jobs, st);
+    if (gap_mode == AG) return launch_mode<AG, int32_t>(align_mode, jobs, prm, n_jobs, st);
+    return launch_mode<CG, int32_t>(align_mode, jobs, prm, n_jobs, st);
+}

@@ -1,0 +1,30 @@
+"""pytest configuration: the `gpu` marker and shared helpers.
+
+`-m "not gpu"` : oracle vs golden vectors, host logic, ABI/symbol checks (CPU only).
+`-m gpu`       : parity of the CUDA path against the oracle, through the C ABI.
+"""
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    from abpoa_b200 import capi
+    return capi.product()
+
+
+@pytest.fixture(scope="session")
+def reference_lib():
+    from abpoa_b200 import capi
+    if not capi.REFERENCE_LIB.exists():
+        pytest.skip("oracle/_ref/libabpoa_ref.so not built (reference tree absent and no prebuilt copy)")
+    return capi.reference()

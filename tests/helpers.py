@@ -1,0 +1,62 @@
+"""Shared test helpers (pure Python, no alignment logic)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from abpoa_b200.aligner import PoaConfig, PoaSession, encode
+
+INPUTS = Path(__file__).resolve().parent / "golden" / "inputs"
+
+
+def read_fasta(path: Path, m: int = 5) -> list[np.ndarray]:
+    seqs, cur = [], []
+    lines = Path(path).read_text().splitlines()
+    is_fq = lines and lines[0].startswith("@")
+    if is_fq:
+        return [encode(lines[i + 1], m) for i in range(0, len(lines) - 1, 4)]
+    for ln in lines:
+        if ln.startswith(">"):
+            if cur:
+                seqs.append(encode("".join(cur), m))
+            cur = []
+        elif ln.strip():
+            cur.append(ln.strip())
+    if cur:
+        seqs.append(encode("".join(cur), m))
+    return seqs
+
+
+def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True):
+    """Progressive POA of one group through `lib`; returns per-read records + consensus (+ MSA)."""
+    cfg = PoaConfig(**{**cfg.__dict__, "out_msa": want_msa})
+    with PoaSession(cfg, lib) as s:
+        alns = s.run_reads(reads)
+        s.generate()
+        return {
+            "alns": alns,
+            "cons": s.consensus(),
+            "cov": s.consensus_cov(),
+            "msa": s.msa_rows(),
+        }
+
+
+def assert_group_equal(a, b, tag=""):
+    assert len(a["alns"]) == len(b["alns"])
+    for i, (x, y) in enumerate(zip(a["alns"], b["alns"])):
+        assert x.aligned == y.aligned, f"{tag} read {i}: aligned flag"
+        if not x.aligned:
+            continue
+        assert x.best_score == y.best_score, f"{tag} read {i}: best_score {x.best_score} != {y.best_score}"
+        assert x.cigar.shape == y.cigar.shape and np.array_equal(x.cigar, y.cigar), f"{tag} read {i}: graph_cigar differs"
+        assert (x.node_s, x.node_e, x.query_s, x.query_e) == (y.node_s, y.node_e, y.query_s, y.query_e), f"{tag} read {i}: ends"
+        assert x.cells == y.cells, f"{tag} read {i}: DP cells {x.cells} != {y.cells}"
+    assert len(a["cons"]) == len(b["cons"])
+    for x, y in zip(a["cons"], b["cons"]):
+        assert np.array_equal(x, y), f"{tag}: consensus differs"
+    for x, y in zip(a["cov"], b["cov"]):
+        assert np.array_equal(x, y), f"{tag}: consensus coverage differs"
+    assert len(a["msa"]) == len(b["msa"])
+    for x, y in zip(a["msa"], b["msa"]):
+        assert np.array_equal(x, y), f"{tag}: RC-MSA differs"
