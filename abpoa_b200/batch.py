@@ -1,0 +1,151 @@
+"""ctypes binding of include/abpoa_gpu.h -- the batched, multi-stream engine.
+
+``BatchEngine.run(cfg, groups)`` is what fills a B200: it advances many independent read groups
+concurrently (one warp per alignment, worker threads fusing graph-CIGARs on the host while other
+chunks compute) and returns, per group, what ``abpoa_msa()`` would have left in ``ab->abc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+
+from . import capi
+from .aligner import PoaConfig, make_para
+from .capi import c_int_p, c_u8_p, c_u64_p
+
+ABPOA_GPU_RECORD_READS = 0x1
+
+
+class abpoa_gpu_group_t(C.Structure):
+    _fields_ = [("n_seq", C.c_int), ("seq_lens", c_int_p), ("seqs", C.POINTER(c_u8_p)), ("qual_weights", C.POINTER(c_int_p))]
+
+
+class abpoa_gpu_group_result_t(C.Structure):
+    _fields_ = [
+        ("n_cons", C.c_int), ("cons_len", c_int_p), ("cons_base", C.POINTER(c_u8_p)), ("cons_cov", C.POINTER(c_int_p)),
+        ("msa_len", C.c_int), ("n_msa_rows", C.c_int), ("msa_base", C.POINTER(c_u8_p)),
+        ("dp_cells", C.c_int64), ("n_aligned", C.c_int),
+        ("read_best_score", C.POINTER(C.c_int32)), ("read_n_cigar", C.POINTER(C.c_int32)), ("read_cigar_hash", c_u64_p),
+    ]
+
+
+class abpoa_gpu_stats_t(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("wall_ms", C.c_double),
+                ("cells", C.c_int64), ("alignments", C.c_int64), ("launches", C.c_int64), ("retries", C.c_int64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int)]
+
+
+@dataclass
+class GroupResult:
+    cons: list[np.ndarray]
+    cov: list[np.ndarray]
+    msa: list[np.ndarray]
+    dp_cells: int
+    n_aligned: int
+    read_best_score: np.ndarray | None = None
+    read_n_cigar: np.ndarray | None = None
+    read_cigar_hash: np.ndarray | None = None
+
+
+def _bind(lib):
+    d = lib.dll
+    d.abpoa_gpu_device_count.restype = C.c_int
+    d.abpoa_gpu_batch_init.restype = C.c_void_p
+    d.abpoa_gpu_batch_init.argtypes = [C.c_int, C.c_int, C.c_int]
+    d.abpoa_gpu_batch_free.argtypes = [C.c_void_p]
+    d.abpoa_gpu_msa_batch.restype = C.c_int
+    d.abpoa_gpu_msa_batch.argtypes = [C.c_void_p, capi.abpoa_para_t_p, C.c_int, C.POINTER(abpoa_gpu_group_t),
+                                      C.POINTER(abpoa_gpu_group_result_t), C.c_int]
+    d.abpoa_gpu_group_result_free.argtypes = [C.POINTER(abpoa_gpu_group_result_t)]
+    d.abpoa_gpu_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(abpoa_gpu_stats_t)]
+    d.abpoa_gpu_batch_reset_stats.argtypes = [C.c_void_p]
+    return d
+
+
+def fnv1a_words(words: np.ndarray) -> int:
+    """FNV-1a over the bytes of the CIGAR words (what the engine records per read)."""
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(words, dtype=np.uint64).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+class PackedGroups:
+    """Host-side argument block for abpoa_gpu_msa_batch (keeps the numpy buffers alive)."""
+
+    def __init__(self, groups: Sequence[Sequence[np.ndarray]]):
+        self.n = len(groups)
+        self._keep = []
+        self.arr = (abpoa_gpu_group_t * self.n)()
+        self.total_bases = 0
+        self.total_reads = 0
+        for g, reads in enumerate(groups):
+            n = len(reads)
+            arrs = [np.ascontiguousarray(r, dtype=np.uint8) for r in reads]
+            lens = (C.c_int * n)(*[len(a) for a in arrs])
+            ptrs = (c_u8_p * n)(*[a.ctypes.data_as(c_u8_p) for a in arrs])
+            self._keep += [arrs, lens, ptrs]
+            self.arr[g].n_seq = n
+            self.arr[g].seq_lens = C.cast(lens, c_int_p)
+            self.arr[g].seqs = C.cast(ptrs, C.POINTER(c_u8_p))
+            self.arr[g].qual_weights = None
+            self.total_bases += sum(len(a) for a in arrs)
+            self.total_reads += n
+
+
+class BatchEngine:
+    def __init__(self, device: int = -1, n_workers: int = 0, groups_per_launch: int = 0, lib=None):
+        self.lib = lib if lib is not None else capi.product()
+        self.d = _bind(self.lib)
+        self.h = self.d.abpoa_gpu_batch_init(device, n_workers, groups_per_launch)
+
+    def close(self):
+        if self.h:
+            self.d.abpoa_gpu_batch_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def run_packed(self, abpt, packed: PackedGroups, record_reads: bool = False, keep_results: bool = True):
+        res = (abpoa_gpu_group_result_t * packed.n)()
+        self.d.abpoa_gpu_msa_batch(self.h, abpt, packed.n, packed.arr, res, ABPOA_GPU_RECORD_READS if record_reads else 0)
+        out = []
+        for g in range(packed.n):
+            r = res[g]
+            if keep_results:
+                n_seq = packed.arr[g].n_seq
+                cons = [np.ctypeslib.as_array(r.cons_base[i], shape=(r.cons_len[i],)).copy() for i in range(r.n_cons)]
+                cov = [np.ctypeslib.as_array(r.cons_cov[i], shape=(r.cons_len[i],)).copy() for i in range(r.n_cons)]
+                msa = [np.ctypeslib.as_array(r.msa_base[i], shape=(r.msa_len,)).copy() for i in range(r.n_msa_rows)]
+                gr = GroupResult(cons, cov, msa, int(r.dp_cells), int(r.n_aligned))
+                if record_reads and n_seq > 0:
+                    gr.read_best_score = np.ctypeslib.as_array(r.read_best_score, shape=(n_seq,)).copy()
+                    gr.read_n_cigar = np.ctypeslib.as_array(r.read_n_cigar, shape=(n_seq,)).copy()
+                    gr.read_cigar_hash = np.ctypeslib.as_array(r.read_cigar_hash, shape=(n_seq,)).copy()
+                out.append(gr)
+            else:
+                out.append((int(r.dp_cells), int(r.n_aligned), int(sum(r.cons_len[i] for i in range(r.n_cons)))))
+            self.d.abpoa_gpu_group_result_free(C.byref(r))
+        return out
+
+    def run(self, cfg: PoaConfig, groups, record_reads: bool = False):
+        abpt = make_para(self.lib, cfg)
+        try:
+            return self.run_packed(abpt, PackedGroups(groups), record_reads)
+        finally:
+            self.lib.abpoa_free_para(abpt)
+
+    def stats(self) -> dict:
+        s = abpoa_gpu_stats_t()
+        self.d.abpoa_gpu_batch_get_stats(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in abpoa_gpu_stats_t._fields_}
+
+    def reset_stats(self):
+        self.d.abpoa_gpu_batch_reset_stats(self.h)

@@ -1,0 +1,320 @@
+/* poa_batch.cu -- the batched engine behind abpoa_gpu.h (host-only C++; compiled by nvcc
+ * only so that it shares the CUDA runtime of the library).
+ *
+ * Reads inside a group are sequential; groups are independent.  The engine keeps the GPU
+ * full by advancing many groups at once:
+ *
+ *   - W worker threads, each owning a stream context (CUDA stream + pinned staging + HBM
+ *     work buffers) and pulling chunks of G groups from a shared counter;
+ *   - a chunk advances in rounds: round r flattens the graphs of its groups, launches ONE
+ *     kernel grid (one warp per alignment of read r), receives the graph-CIGARs, and fuses
+ *     them into the host graphs (abpoa_add_graph_alignment);
+ *   - while one worker fuses on its core, the kernels of the other workers' chunks occupy
+ *     the SMs: up to W x G alignments in flight;
+ *   - the score planes (the bulk of HBM use) come from ONE arena shared by all streams and
+ *     are held only from launch to result copy, so the arena bounds concurrency, not W x G.
+ *
+ * The per-read loop reproduces abpoa_poa (reference src/abpoa_align.c:312-352) including
+ * the optional reverse-complement retry (-s); the final output step is abpoa_output
+ * (reference :354-370) with out_fp = NULL.
+ */
+#include <cuda_runtime.h>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+#include <string.h>
+#include "abpoa_gpu.h"
+#include "poa_internal.h"
+#include "poa_engine.h"
+
+struct abpoa_gpu_batch {
+    int dev, n_workers, groups_per_launch;
+    poa_arena *arena;
+    std::vector<poa_dev_ctx *> ctx;
+    double wall_ms;
+};
+
+extern "C" int abpoa_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, int groups_per_launch) {
+    if (abpoa_gpu_device_count() <= 0)
+        poa_die("libabpoa_b200", "no CUDA device available. This library has no CPU path: the DP runs only on the GPU.");
+    abpoa_gpu_batch *e = new abpoa_gpu_batch();
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    e->dev = device;
+    if (cudaSetDevice(device) != cudaSuccess) poa_die("libabpoa_b200", "cannot select CUDA device %d", device);
+    unsigned hc = std::thread::hardware_concurrency();
+    if (n_workers <= 0) {
+        const char *env = getenv("ABPOA_GPU_WORKERS");
+        n_workers = env && *env ? atoi(env) : (int)(hc ? hc : 8);
+        if (n_workers > 64) n_workers = 64;
+        if (n_workers < 2) n_workers = 2;
+    }
+    if (groups_per_launch <= 0) {
+        const char *env = getenv("ABPOA_GPU_GROUPS_PER_LAUNCH");
+        groups_per_launch = env && *env ? atoi(env) : 32;
+    }
+    e->n_workers = n_workers; e->groups_per_launch = groups_per_launch;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) poa_die("libabpoa_b200", "cudaMemGetInfo failed");
+    /* planes arena: most of the free HBM, leaving room for the per-stream staging buffers */
+    size_t want = (size_t)((double)free_b * 0.80);
+    const char *env = getenv("ABPOA_GPU_ARENA_MB");
+    if (env && *env) want = (size_t)atoll(env) << 20;
+    e->arena = poa_arena_new(device, want);
+    for (int w = 0; w < n_workers; ++w) {
+        poa_dev_ctx *c = poa_dev_ctx_new_on(device);
+        poa_dev_ctx_use_arena(c, e->arena);
+        e->ctx.push_back(c);
+    }
+    e->wall_ms = 0;
+    return e;
+}
+
+extern "C" void abpoa_gpu_batch_free(abpoa_gpu_batch_t *e) {
+    if (!e) return;
+    for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_free(c);
+    poa_arena_destroy(e->arena);
+    delete e;
+}
+
+extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_t *out) {
+    memset(out, 0, sizeof *out);
+    for (poa_dev_ctx *c : e->ctx) {
+        const poa_engine_stats *s = poa_dev_ctx_stats(c);
+        out->kernel_ms += s->kernel_ms; out->cells += s->cells; out->alignments += s->alignments;
+        out->launches += s->launches; out->retries += s->retries; out->h2d_bytes += s->h2d_bytes; out->d2h_bytes += s->d2h_bytes;
+    }
+    out->wall_ms = e->wall_ms; out->n_workers = e->n_workers; out->device = e->dev;
+}
+
+extern "C" void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *e) {
+    for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_reset_stats(c);
+    e->wall_ms = 0;
+}
+
+extern "C" void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r) {
+    if (!r) return;
+    for (int i = 0; i < r->n_cons; ++i) { free(r->cons_base[i]); free(r->cons_cov[i]); }
+    free(r->cons_len); free(r->cons_base); free(r->cons_cov);
+    for (int i = 0; i < r->n_msa_rows; ++i) free(r->msa_base[i]);
+    free(r->msa_base);
+    free(r->read_best_score); free(r->read_n_cigar); free(r->read_cigar_hash);
+    memset(r, 0, sizeof *r);
+}
+
+namespace {
+
+struct GroupState {
+    const abpoa_gpu_group_t *in;
+    abpoa_gpu_group_result_t *out;
+    abpoa_t *ab;
+    int **weights;                      /* per read, as abpoa_msa builds them */
+    int next_read;
+};
+
+struct Pending {                        /* one alignment in flight */
+    GroupState *gs;
+    abpoa_res_t res;
+    bool have;
+};
+
+uint64_t fnv1a(const abpoa_cigar_t *a, int n) {
+    uint64_t h = 1469598103934665603ull;
+    const uint8_t *p = (const uint8_t *)a;
+    for (size_t i = 0; i < (size_t)n * 8; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+struct Worker {
+    abpoa_gpu_batch *eng; poa_dev_ctx *ctx; abpoa_para_t *abpt; int flags;
+    std::atomic<int> *next_chunk; int n_groups; const abpoa_gpu_group_t *groups; abpoa_gpu_group_result_t *results;
+};
+
+struct SinkCtx { abpoa_para_t *abpt; };
+
+void sink_to_res(void *user, poa_job *j) {
+    SinkCtx *sc = (SinkCtx *)user;
+    Pending *pd = (Pending *)j->tag;
+    memset(&pd->res, 0, sizeof pd->res);
+    poa_job_to_res(j, sc->abpt, &pd->res);       /* copies the CIGAR out of the pinned buffer */
+    pd->gs->out->dp_cells += j->cells;
+    pd->gs->out->n_aligned += 1;
+    pd->have = true;
+}
+
+void finish_group(GroupState &gs, abpoa_para_t *abpt) {
+    abpoa_t *ab = gs.ab;
+    abpoa_gpu_group_result_t *o = gs.out;
+    abpoa_output(ab, abpt, NULL);
+    const abpoa_cons_t *abc = ab->abc;
+    if (abpt->out_cons && abc->n_cons > 0) {
+        o->n_cons = abc->n_cons;
+        o->cons_len = (int *)poa_xmalloc(sizeof(int) * abc->n_cons);
+        o->cons_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * abc->n_cons);
+        o->cons_cov = (int **)poa_xmalloc(sizeof(int *) * abc->n_cons);
+        for (int c = 0; c < abc->n_cons; ++c) {
+            const int l = abc->cons_len[c];
+            o->cons_len[c] = l;
+            o->cons_base[c] = (uint8_t *)poa_xmalloc((size_t)(l > 0 ? l : 1));
+            o->cons_cov[c] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1));
+            memcpy(o->cons_base[c], abc->cons_base[c], (size_t)l);
+            memcpy(o->cons_cov[c], abc->cons_cov[c], sizeof(int) * (size_t)l);
+        }
+    }
+    if (abpt->out_msa && abc->msa_len > 0) {
+        o->msa_len = abc->msa_len; o->n_msa_rows = abc->n_seq + abc->n_cons;
+        o->msa_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * (size_t)o->n_msa_rows);
+        for (int r = 0; r < o->n_msa_rows; ++r) {
+            o->msa_base[r] = (uint8_t *)poa_xmalloc((size_t)abc->msa_len);
+            memcpy(o->msa_base[r], abc->msa_base[r], (size_t)abc->msa_len);
+        }
+    }
+}
+
+void worker_main(Worker wk) {
+    if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
+    abpoa_para_t *abpt = wk.abpt;
+    const int G = wk.eng->groups_per_launch;
+    std::vector<abpoa_t *> handles;                     /* reused across chunks */
+    SinkCtx sc = { abpt };
+    for (;;) {
+        const int chunk = wk.next_chunk->fetch_add(1);
+        const int g0 = chunk * G;
+        if (g0 >= wk.n_groups) break;
+        const int g1 = g0 + G < wk.n_groups ? g0 + G : wk.n_groups;
+        const int ng = g1 - g0;
+        while ((int)handles.size() < ng) handles.push_back(abpoa_init());
+        std::vector<GroupState> gs(ng);
+        int max_reads = 0;
+        for (int t = 0; t < ng; ++t) {
+            GroupState &s = gs[t];
+            s.in = &wk.groups[g0 + t]; s.out = &wk.results[g0 + t]; s.ab = handles[t]; s.next_read = 0;
+            memset(s.out, 0, sizeof *s.out);
+            const int n = s.in->n_seq;
+            if (n > max_reads) max_reads = n;
+            int max_len = 1024;
+            for (int i = 0; i < n; ++i) if (s.in->seq_lens[i] > max_len) max_len = s.in->seq_lens[i];
+            abpoa_reset(s.ab, abpt, max_len);
+            abpoa_seq_t *abs = s.ab->abs;
+            abs->n_seq = n; poa_seq_reserve(abs);
+            for (int i = 0; i < n; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
+            s.weights = (int **)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int *));
+            for (int i = 0; i < n; ++i) {
+                const int l = s.in->seq_lens[i];
+                const int *qw = (abpt->use_qv && s.in->qual_weights && s.in->qual_weights[i]) ? s.in->qual_weights[i] : NULL;
+                if (qw) { s.weights[i] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1)); memcpy(s.weights[i], qw, sizeof(int) * (size_t)l); }
+            }
+            if (wk.flags & ABPOA_GPU_RECORD_READS) {
+                s.out->read_best_score = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+                s.out->read_n_cigar = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+                s.out->read_cigar_hash = (uint64_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(uint64_t));
+            }
+        }
+        std::vector<poa_job> jobs; std::vector<Pending> pend(ng); std::vector<int> owner;
+        for (int r = 0; r < max_reads; ++r) {
+            jobs.clear(); owner.clear();
+            for (int t = 0; t < ng; ++t) {
+                GroupState &s = gs[t];
+                pend[t].gs = &s; pend[t].have = false; memset(&pend[t].res, 0, sizeof(abpoa_res_t));
+                if (r >= s.in->n_seq) continue;
+                abpoa_graph_t *abg = s.ab->abg;
+                if (abg->node_n <= 2) continue;                  /* empty graph: no DP (reference :195) */
+                if (!abg->is_topological_sorted) abpoa_topological_sort(abg, abpt);
+                poa_job j; memset(&j, 0, sizeof j);
+                j.abg = abg; j.beg_node_id = ABPOA_SRC_NODE_ID; j.end_node_id = ABPOA_SINK_NODE_ID;
+                j.query = s.in->seqs[r]; j.tag = &pend[t];
+                poa_blob_plan_make(&j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, s.in->seq_lens[r]);
+                jobs.push_back(j); owner.push_back(t);
+            }
+            if (!jobs.empty()) poa_engine_run(wk.ctx, abpt, jobs.data(), (int)jobs.size(), sink_to_res, &sc);
+
+            /* optional strand retry (-s): align the reverse complement of weak hits */
+            std::vector<uint8_t *> rc_seq(ng, (uint8_t *)NULL); std::vector<int *> rc_w(ng, (int *)NULL);
+            if (abpt->amb_strand) {
+                std::vector<poa_job> rjobs; std::vector<Pending> rpend(ng);
+                for (int t = 0; t < ng; ++t) {
+                    GroupState &s = gs[t];
+                    if (!pend[t].have) continue;
+                    const int qlen = s.in->seq_lens[r];
+                    const int lim = qlen < s.ab->abg->node_n - 2 ? qlen : s.ab->abg->node_n - 2;
+                    if (!(pend[t].res.best_score < lim * abpt->max_mat * .3333)) continue;
+                    rc_seq[t] = (uint8_t *)poa_xmalloc((size_t)qlen); rc_w[t] = (int *)poa_xmalloc(sizeof(int) * (size_t)qlen);
+                    for (int k = 0; k < qlen; ++k) {
+                        const uint8_t b = s.in->seqs[r][qlen - 1 - k];
+                        rc_seq[t][k] = b < 4 ? (uint8_t)(3 - b) : 4;
+                        rc_w[t][k] = s.weights[r] ? s.weights[r][qlen - 1 - k] : 1;
+                    }
+                    poa_job j; memset(&j, 0, sizeof j);
+                    j.abg = s.ab->abg; j.beg_node_id = ABPOA_SRC_NODE_ID; j.end_node_id = ABPOA_SINK_NODE_ID;
+                    j.query = rc_seq[t]; rpend[t].gs = &s; rpend[t].have = false; j.tag = &rpend[t];
+                    poa_blob_plan_make(&j.plan, s.ab->abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, qlen);
+                    rjobs.push_back(j);
+                }
+                if (!rjobs.empty()) {
+                    poa_engine_run(wk.ctx, abpt, rjobs.data(), (int)rjobs.size(), sink_to_res, &sc);
+                    for (int t = 0; t < ng; ++t) {
+                        if (!rc_seq[t]) continue;
+                        if (rpend[t].res.best_score > pend[t].res.best_score) {
+                            if (pend[t].res.n_cigar) free(pend[t].res.graph_cigar);
+                            pend[t].res = rpend[t].res;
+                            gs[t].ab->abs->is_rc[r] = 1;
+                        } else {
+                            if (rpend[t].res.n_cigar) free(rpend[t].res.graph_cigar);
+                            free(rc_seq[t]); free(rc_w[t]); rc_seq[t] = NULL; rc_w[t] = NULL;
+                        }
+                    }
+                }
+            }
+
+            /* fuse: abpoa_add_graph_alignment for every group that has a read r */
+            for (int t = 0; t < ng; ++t) {
+                GroupState &s = gs[t];
+                if (r >= s.in->n_seq) continue;
+                const int qlen = s.in->seq_lens[r];
+                uint8_t *q = rc_seq[t] ? rc_seq[t] : (uint8_t *)s.in->seqs[r];
+                int *w = rc_seq[t] ? rc_w[t] : s.weights[r];
+                if (wk.flags & ABPOA_GPU_RECORD_READS) {
+                    s.out->read_best_score[r] = pend[t].have ? pend[t].res.best_score : 0;
+                    s.out->read_n_cigar[r] = pend[t].res.n_cigar;
+                    s.out->read_cigar_hash[r] = fnv1a(pend[t].res.graph_cigar, pend[t].res.n_cigar);
+                }
+                abpoa_add_graph_alignment(s.ab, abpt, q, w, qlen, NULL, pend[t].res, r, s.in->n_seq, 1);
+                if (pend[t].res.n_cigar) free(pend[t].res.graph_cigar);
+                free(rc_seq[t]); free(rc_w[t]);
+            }
+        }
+        for (int t = 0; t < ng; ++t) {
+            finish_group(gs[t], abpt);
+            for (int i = 0; i < gs[t].in->n_seq; ++i) free(gs[t].weights[i]);
+            free(gs[t].weights);
+        }
+    }
+    for (abpoa_t *ab : handles) abpoa_free(ab);
+}
+
+}  // namespace
+
+extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
+                                   abpoa_gpu_group_result_t *results, int flags) {
+    if (n_groups <= 0) return 0;
+    if (!((abpt->disable_seeding && abpt->progressive_poa == 0) || abpt->align_mode != ABPOA_GLOBAL_MODE))
+        poa_die(__func__, "minimizer seeding / guide-tree partitioning (-S / -p) is outside the scope of the B200 hot-path library.");
+    const auto t0 = std::chrono::steady_clock::now();
+    std::atomic<int> next_chunk(0);
+    const int n_chunks = (n_groups + e->groups_per_launch - 1) / e->groups_per_launch;
+    const int nw = e->n_workers < n_chunks ? e->n_workers : n_chunks;
+    std::vector<std::thread> th;
+    for (int w = 0; w < nw; ++w) {
+        Worker wk = { e, e->ctx[w], abpt, flags, &next_chunk, n_groups, groups, results };
+        th.emplace_back(worker_main, wk);
+    }
+    for (auto &t : th) t.join();
+    e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}

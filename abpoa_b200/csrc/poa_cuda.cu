@@ -16,6 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
+#include <condition_variable>
+#include <algorithm>
 #include "poa_internal.h"
 #include "poa_device.cuh"
 #include "poa_engine.h"
@@ -28,14 +31,63 @@ extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, 
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+/* ------------------------------------------------------------------ shared plane arena */
+struct poa_arena {
+    int dev; uint8_t *base; size_t cap;
+    std::mutex mu; std::condition_variable cv;
+    std::vector<std::pair<size_t, size_t>> free_list;      /* (offset, length), sorted by offset */
+};
+
+poa_arena *poa_arena_new(int dev, size_t bytes) {
+    poa_arena *a = new poa_arena();
+    a->dev = dev; a->cap = bytes & ~(size_t)255; a->base = NULL;
+    CK(cudaSetDevice(dev));
+    cudaError_t e = cudaMalloc((void **)&a->base, a->cap);
+    if (e != cudaSuccess) poa_die("libabpoa_b200/cuda", "cannot reserve %zu bytes of HBM for DP planes: %s", a->cap, cudaGetErrorString(e));
+    a->free_list.push_back({0, a->cap});
+    return a;
+}
+void poa_arena_destroy(poa_arena *a) { if (!a) return; cudaSetDevice(a->dev); cudaFree(a->base); delete a; }
+size_t poa_arena_capacity(const poa_arena *a) { return a->cap; }
+
+static uint8_t *arena_take(poa_arena *a, size_t bytes) {
+    bytes = al256(bytes);
+    if (bytes > a->cap) poa_die("libabpoa_b200/cuda", "one launch needs %zu bytes of DP planes, arena holds %zu", bytes, a->cap);
+    std::unique_lock<std::mutex> lk(a->mu);
+    for (;;) {
+        for (size_t i = 0; i < a->free_list.size(); ++i)
+            if (a->free_list[i].second >= bytes) {
+                size_t off = a->free_list[i].first;
+                a->free_list[i].first += bytes; a->free_list[i].second -= bytes;
+                if (a->free_list[i].second == 0) a->free_list.erase(a->free_list.begin() + i);
+                return a->base + off;
+            }
+        a->cv.wait(lk);
+    }
+}
+static void arena_give(poa_arena *a, uint8_t *p, size_t bytes) {
+    bytes = al256(bytes);
+    const size_t off = (size_t)(p - a->base);
+    {
+        std::lock_guard<std::mutex> lk(a->mu);
+        auto it = std::lower_bound(a->free_list.begin(), a->free_list.end(), std::make_pair(off, (size_t)0));
+        it = a->free_list.insert(it, {off, bytes});
+        if (it + 1 != a->free_list.end() && it->first + it->second == (it + 1)->first) { it->second += (it + 1)->second; a->free_list.erase(it + 1); }
+        if (it != a->free_list.begin() && (it - 1)->first + (it - 1)->second == it->first) { (it - 1)->second += it->second; a->free_list.erase(it); }
+    }
+    a->cv.notify_all();
+}
+
 struct poa_dev_ctx {
     int dev;
+    poa_arena *arena;
     cudaStream_t st;
     cudaEvent_t ev_k0, ev_k1;
     uint8_t *h_in, *h_out, *d_in, *d_work, *d_planes;
     size_t h_in_cap, h_out_cap, d_in_cap, d_work_cap, d_planes_cap;
     size_t planes_limit;              /* hard cap for the plane slab (bytes); 0 = ask the device */
     poa_engine_stats stats;
+    PoaJobDesc last_desc; int last_bits, last_gap, last_rows;   /* debug: job 0 of the most recent launch */
 };
 
 static void require_gpu(void) {
@@ -46,16 +98,21 @@ static void require_gpu(void) {
                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 }
 
-poa_dev_ctx *poa_dev_ctx_new(void) {
+poa_dev_ctx *poa_dev_ctx_new_on(int dev) {
     require_gpu();
     poa_dev_ctx *c = (poa_dev_ctx *)poa_xcalloc(1, sizeof(poa_dev_ctx));
-    const char *env = getenv("ABPOA_GPU_DEVICE");
-    if (env && *env) { c->dev = atoi(env); CK(cudaSetDevice(c->dev)); }
+    if (dev >= 0) { c->dev = dev; CK(cudaSetDevice(c->dev)); }
     else CK(cudaGetDevice(&c->dev));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_k0)); CK(cudaEventCreate(&c->ev_k1));
     return c;
 }
+
+poa_dev_ctx *poa_dev_ctx_new(void) {
+    const char *env = getenv("ABPOA_GPU_DEVICE");
+    return poa_dev_ctx_new_on(env && *env ? atoi(env) : -1);
+}
+void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a) { c->arena = a; }
 
 void poa_dev_ctx_free(poa_dev_ctx *c) {
     if (!c) return;
@@ -114,7 +171,7 @@ static uint64_t plane_units_for(const poa_job *j, int gap_mode, int generous) {
     const uint64_t full = (uint64_t)((j->plan.qlen + 1 + 7) / 8 + 1);
     uint64_t per_row = full;
     if (!generous && j->plan.w >= 0) {
-        const uint64_t est = (uint64_t)((2 * j->plan.w + 1 + 96 + 7) / 8 + 2);
+        const uint64_t est = (uint64_t)((2 * j->plan.w + 1 + 32 + 7) / 8 + 2);
         if (est < per_row) per_row = est;
     }
     return per_row * (uint64_t)P * (uint64_t)j->plan.n_rows;
@@ -148,7 +205,9 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     grow_host(&c->h_in, &c->h_in_cap, in_bytes);
     grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
     grow_dev(&c->d_work, &c->d_work_cap, work_bytes, 1);
-    grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1);
+    uint8_t *planes_base;
+    if (c->arena) planes_base = arena_take(c->arena, plane_bytes);
+    else { grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1); planes_base = c->d_planes; }
 
     poa_fill_params((PoaParamsDev *)c->h_in, abpt, bits);
     PoaJobDesc *desc = (PoaJobDesc *)(c->h_in + off_desc);
@@ -156,7 +215,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         poa_job &j = jobs[idx[t]];
         poa_blob_fill(c->h_in + blob_off[t], &j.plan, j.abg, abpt, j.beg_node_id, j.end_node_id, j.query);
         desc[t].blob = c->d_in + blob_off[t];
-        desc[t].planes = c->d_planes + (size_t)plane_off[t] * POA_GROUP * S;
+        desc[t].planes = planes_base + (size_t)plane_off[t] * POA_GROUP * S;
         desc[t].plane_cap_units = units[t];
         desc[t].rowinfo = (PoaRowInfo *)(c->d_work + work_off[t]);
         desc[t].rowoff = (uint32_t *)(c->d_work + work_off[t] + al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)));
@@ -165,6 +224,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         desc[t].pad = 0;
         desc[t].result = (PoaResultDev *)c->d_work + t;
     }
+    c->last_desc = desc[0]; c->last_bits = bits; c->last_gap = abpt->gap_mode; c->last_rows = jobs[idx[0]].plan.n_rows;
     CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
     CK(cudaEventRecord(c->ev_k0, c->st));
     CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
@@ -175,6 +235,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     grow_host(&c->h_out, &c->h_out_cap, out_bytes);
     CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    if (c->arena) arena_give(c->arena, planes_base, plane_bytes);      /* the backtrace is done: planes are dead */
     float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
     c->stats.kernel_ms += ms; c->stats.launches += 1; c->stats.h2d_bytes += in_bytes;
 
@@ -218,17 +279,29 @@ void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int
     if (n <= 0) return;
     std::vector<int> w16, w32;
     for (int t = 0; t < n; ++t) (poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows) == 16 ? w16 : w32).push_back(t);
+    /* a launch may borrow at most this much of the plane memory (leave room for other streams) */
+    size_t limit = c->planes_limit;
+    if (c->arena) limit = poa_arena_capacity(c->arena) / 4;
     for (int pass = 0; pass < 2; ++pass) {
         std::vector<int> &v = pass == 0 ? w16 : w32;
         const int bits = pass == 0 ? 16 : 32;
-        if (v.empty()) continue;
-        run_same_width(c, abpt, jobs, v.data(), (int)v.size(), bits, 0);
-        std::vector<int> redo;
-        for (int t : v) { if (jobs[t].status == POA_ST_PLANE_OVF) redo.push_back(t); else sink(user, &jobs[t]); }
-        for (int t : redo) {
-            c->stats.retries += 1;
-            run_same_width(c, abpt, jobs, &t, 1, bits, 1);
-            sink(user, &jobs[t]);
+        size_t pos = 0;
+        while (pos < v.size()) {
+            size_t bytes = 0, end = pos;
+            while (end < v.size()) {
+                const size_t b = (size_t)plane_units_for(&jobs[v[end]], abpt->gap_mode, 0) * POA_GROUP * (bits / 8);
+                if (end > pos && limit && bytes + b > limit) break;
+                bytes += b; ++end;
+            }
+            run_same_width(c, abpt, jobs, v.data() + pos, (int)(end - pos), bits, 0);
+            std::vector<int> redo;
+            for (size_t t = pos; t < end; ++t) { if (jobs[v[t]].status == POA_ST_PLANE_OVF) redo.push_back(v[t]); else sink(user, &jobs[v[t]]); }
+            for (int t : redo) {
+                c->stats.retries += 1;
+                run_same_width(c, abpt, jobs, &t, 1, bits, 1);
+                sink(user, &jobs[t]);
+            }
+            pos = end;
         }
     }
 }
@@ -293,4 +366,29 @@ int poa_cuda_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int beg
     single_sink_arg a = { ab, abpt, res };
     poa_engine_run(c, abpt, &j, 1, single_sink, &a);
     return 0;
+}
+
+/* ------------------------------------------------------------------ debugging aid
+ * Copy one DP row of the most recent single alignment of `ab` back from HBM: planes as
+ * int32 [n_planes][cap], and the row's (beg, end, left, right).  Returns the number of
+ * planes, or -1.  Used by tests/debug_planes.py to compare against the oracle cell by cell. */
+extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, int32_t *info4) {
+    poa_dev_ctx *c = (poa_dev_ctx *)ab->abm->s_mem;
+    if (!c || c->arena || row < 0 || row >= c->last_rows) return -1;
+    CK(cudaSetDevice(c->dev));
+    PoaRowInfo ri; uint32_t off;
+    CK(cudaMemcpy(&ri, c->last_desc.rowinfo + row, sizeof ri, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&off, c->last_desc.rowoff + row, sizeof off, cudaMemcpyDeviceToHost));
+    info4[0] = ri.beg; info4[1] = ri.end; info4[2] = ri.left; info4[3] = ri.right;
+    const int P = planes_of(c->last_gap), S = c->last_bits / 8;
+    const int g0 = ri.beg >> 3, ng = (ri.end >> 3) - g0 + 1, wd = ri.end - ri.beg + 1;
+    if (wd <= 0 || wd > cap) return -1;
+    std::vector<uint8_t> buf((size_t)ng * 8 * P * S);
+    CK(cudaMemcpy(buf.data(), (uint8_t *)c->last_desc.planes + (size_t)off * POA_GROUP * S, buf.size(), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < P; ++p)
+        for (int j = ri.beg; j <= ri.end; ++j) {
+            const size_t k = (size_t)p * ng * 8 + (size_t)(j - g0 * 8);
+            out[(size_t)p * cap + (j - ri.beg)] = S == 2 ? (int32_t)((int16_t *)buf.data())[k] : ((int32_t *)buf.data())[k];
+        }
+    return P;
 }

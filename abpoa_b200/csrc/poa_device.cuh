@@ -71,6 +71,7 @@ typedef struct PoaParamsDev {
     int32_t zdrop;
     int32_t put_gap_on_right, put_gap_at_end;
     int32_t ret_cigar;
+    int32_t zero;                       /* always 0 (see poa_kernels.cu: LOCAL floors) */
     int32_t pn;                         /* lanes of the reference's AVX2 vector for the chosen
                                            score width (16 / 8): only used for its beg-clamp rule */
     int32_t mat[POA_MAX_M * POA_MAX_M];

@@ -32,6 +32,15 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
 } poa_engine_stats;
 
+/* One big HBM region shared by the stream contexts of a batch engine: score planes live
+ * only between a launch and its result copy, so streams borrow and return slices. */
+typedef struct poa_arena poa_arena;
+poa_arena *poa_arena_new(int dev, size_t bytes);
+void poa_arena_destroy(poa_arena *a);
+size_t poa_arena_capacity(const poa_arena *a);
+poa_dev_ctx *poa_dev_ctx_new_on(int dev);
+void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a);
+
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);
 void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res);
 void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes);

@@ -532,3 +532,53 @@ int abpoa_add_graph_alignment(abpoa_t *ab, abpoa_para_t *abpt, uint8_t *seq, int
     return abpoa_add_subgraph_alignment(ab, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, seq, weight, seq_l, qpos_to_node_id,
                                         res, read_id, tot_read_n, inc_both_ends);
 }
+
+/* ------------------------------------------------------------------ sub-graph windows
+ * abpoa_subgraph_nodes (reference src/abpoa_graph.c:595-687): widen the index window
+ * [inc_beg, inc_end] until no edge enters it from outside, and return the node ids just
+ * outside it as the exclusive begin / end of a sub-graph alignment. */
+static int window_closed_upstream(const abpoa_graph_t *abg, int up, int down, int lo, int hi) {
+    const int min_i = POA_MIN(up, lo), max_i = POA_MAX(down, hi);
+    for (int i = up + 1; i <= down; ++i) {
+        const abpoa_node_t *nd = &abg->node[abg->index_to_node_id[i]];
+        for (int e = 0; e < nd->in_edge_n; ++e) {
+            const int pi = abg->node_id_to_index[nd->in_id[e]];
+            if (pi < min_i || pi > max_i) return 0;
+        }
+    }
+    return 1;
+}
+
+static int widen_upstream(const abpoa_graph_t *abg, int lo, int hi) {
+    for (;;) {
+        int min_i = lo;
+        for (int i = lo; i <= hi; ++i) {
+            const abpoa_node_t *nd = &abg->node[abg->index_to_node_id[i]];
+            for (int e = 0; e < nd->in_edge_n; ++e) min_i = POA_MIN(min_i, abg->node_id_to_index[nd->in_id[e]]);
+        }
+        if (window_closed_upstream(abg, min_i, lo, lo, hi)) return min_i;
+        hi = lo; lo = min_i;
+    }
+}
+
+static int widen_downstream(const abpoa_graph_t *abg, int lo, int hi) {
+    for (;;) {
+        int max_i = hi;
+        for (int i = lo; i <= hi; ++i) {
+            const abpoa_node_t *nd = &abg->node[abg->index_to_node_id[i]];
+            for (int e = 0; e < nd->out_edge_n; ++e) max_i = POA_MAX(max_i, abg->node_id_to_index[nd->out_id[e]]);
+        }
+        if (window_closed_upstream(abg, hi, max_i, lo, hi)) return max_i;
+        lo = hi; hi = max_i;
+    }
+}
+
+void abpoa_subgraph_nodes(abpoa_t *ab, abpoa_para_t *abpt, int inc_beg, int inc_end, int *exc_beg, int *exc_end) {
+    abpoa_graph_t *abg = ab->abg;
+    if (abg->is_topological_sorted == 0) abpoa_topological_sort(abg, abpt);
+    const int lo = abg->node_id_to_index[inc_beg], hi = abg->node_id_to_index[inc_end];
+    const int up = widen_upstream(abg, lo, hi), down = widen_downstream(abg, lo, hi);
+    if (up < 0 || down >= abg->node_n) poa_die(__func__, "Error in subgraph_nodes");
+    *exc_beg = abg->index_to_node_id[up];
+    *exc_end = abg->index_to_node_id[down];
+}

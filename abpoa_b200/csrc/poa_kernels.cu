@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     const bool banded = w >= 0;
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
     const int pnv = prm->pn;
+    const int zr = prm->zero;            /* run-time 0: keeps ptxas from fusing the LOCAL floors into VIMNMX.RELU */
 
     PoaResultDev res;
     res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 if (GAP == LG) {
                     x1 = max(x1, a1[c]);                    /* inclusive: H[j] = max(H0[j], H[j-1]-e) */
                     int h = max(x1 - e1 * jr, NEG);
-                    if (MODE == LOCAL) h = max(h, 0);
+                    if (MODE == LOCAL) h = max(h, zr);
                     H[c] = inb[c] ? h : NEG;
                 } else {
                     const int f1 = max(x1 - e1 * (jr - 1), NEG);
@@ -496,17 +497,22 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                     if (GAP == AG) {
                         const int t = max(M[c], X1[c]);
                         int h = max(t, f1);
-                        if (MODE == LOCAL) h = max(h, 0);
-                        E1o[c] = (h == t) ? max(X1[c] - e1, h - oe1) : (MODE == LOCAL ? 0 : NEG);
+                        if (MODE == LOCAL) h = max(h, zr);
+                        /* NOTE (ptxas 12.9, sm_100a): with a literal 0 floor, "max(max(t,f),0) == t" was
+                         * fused into VIMNMX.RELU's predicate output and evaluated false for equal
+                         * operands (seen on B200: the LOCAL affine kernel stored E = 0 everywhere).
+                         * The floor therefore comes from a run-time zero (prm->zero), see `zr`. */
+                        const bool from_t = (h == t);
+                        E1o[c] = from_t ? max(X1[c] - e1, h - oe1) : (MODE == LOCAL ? 0 : NEG);
                         H[c] = h;
                     } else {
                         const int f2 = max(x2 - e2 * (jr - 1), NEG);
                         x2 = max(x2, a2[c]);
                         Fb[c] = f2;
                         int h = max(T[c], max(f1, f2));
-                        if (MODE == LOCAL) h = max(h, 0);
+                        if (MODE == LOCAL) h = max(h, zr);
                         int eo1 = max(X1[c] - e1, h - oe1), eo2 = max(X2[c] - e2, h - oe2);
-                        if (MODE == LOCAL) { eo1 = max(eo1, 0); eo2 = max(eo2, 0); }
+                        if (MODE == LOCAL) { eo1 = max(eo1, zr); eo2 = max(eo2, zr); }
                         E1o[c] = eo1; E2o[c] = eo2; H[c] = h;
                     }
                     if (!inb[c]) { H[c] = NEG; E1o[c] = NEG; if (GAP == CG) E2o[c] = NEG; }

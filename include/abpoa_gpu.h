@@ -1,0 +1,76 @@
+/* abpoa_gpu.h -- ADDITIVE entry points of libabpoa_b200: batched, multi-stream, multi-GPU
+ * partial-order alignment.  abpoa.h stays a pure mirror of the reference interface; nothing
+ * here exists in the reference (it is single-threaded and has no batch API).
+ *
+ * Why: reads of one group are strictly sequential, so one abpoa_msa() call can keep only a
+ * single warp of the GPU busy.  A batch of independent groups (the reference CLI's `-l`
+ * list mode, src/abpoa.c:148-168, one abpoa_msa1 per file) is what fills the device: the
+ * engine advances many groups concurrently -- worker threads each own a CUDA stream, launch
+ * the DP/backtrace kernels for the current read of a chunk of groups (one warp per
+ * alignment) and fuse the returned graph-CIGARs on the host while other chunks compute.
+ *
+ * Results are identical to calling abpoa_msa() group by group (reference
+ * src/abpoa_align.c:401-471) with the same abpoa_para_t.
+ */
+#ifndef ABPOA_GPU_H
+#define ABPOA_GPU_H
+
+#include <stdint.h>
+#include "abpoa.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct abpoa_gpu_batch abpoa_gpu_batch_t;      /* opaque engine */
+
+/* one read group = the arguments of one abpoa_msa() call (reads already encoded 0..m-1) */
+typedef struct {
+    int n_seq;
+    const int *seq_lens;
+    const uint8_t *const *seqs;
+    const int *const *qual_weights;     /* NULL, or per read NULL / weights (used when abpt->use_qv) */
+} abpoa_gpu_group_t;
+
+/* what abpoa_msa() leaves in ab->abc, plus per-group accounting; arrays are malloc'ed by
+ * the library and released with abpoa_gpu_group_result_free() */
+typedef struct {
+    int n_cons; int *cons_len; uint8_t **cons_base; int **cons_cov;
+    int msa_len, n_msa_rows; uint8_t **msa_base;      /* filled when abpt->out_msa               */
+    int64_t dp_cells;                                  /* DP cells of all alignments of the group */
+    int n_aligned;                                     /* alignments performed (n_seq - 1)        */
+    /* per-read records, filled when ABPOA_GPU_RECORD_READS is passed (NULL otherwise) */
+    int32_t *read_best_score;                          /* [n_seq] (0 for the first read)          */
+    int32_t *read_n_cigar;                             /* [n_seq]                                 */
+    uint64_t *read_cigar_hash;                         /* [n_seq] FNV-1a over the CIGAR words     */
+} abpoa_gpu_group_result_t;
+
+typedef struct {
+    double kernel_ms;                   /* sum over streams of CUDA-event time of the alignment kernels */
+    double wall_ms;                     /* wall time of the last abpoa_gpu_msa_batch call               */
+    int64_t cells, alignments, launches, retries;
+    uint64_t h2d_bytes, d2h_bytes;
+    int n_workers, device;
+} abpoa_gpu_stats_t;
+
+#define ABPOA_GPU_RECORD_READS 0x1
+
+int abpoa_gpu_device_count(void);
+
+/* device < 0: the calling thread's current CUDA device.  n_workers <= 0 / groups_per_launch
+ * <= 0: choose from the host core count and the device memory. */
+abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, int groups_per_launch);
+void abpoa_gpu_batch_free(abpoa_gpu_batch_t *eng);
+
+/* Run n_groups independent MSAs; results[g] is overwritten.  Returns 0. */
+int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *eng, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
+                        abpoa_gpu_group_result_t *results, int flags);
+void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r);
+
+void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *eng, abpoa_gpu_stats_t *out);
+void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *eng);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -28,11 +28,25 @@ def read_fasta(path: Path, m: int = 5) -> list[np.ndarray]:
     return seqs
 
 
-def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True):
-    """Progressive POA of one group through `lib`; returns per-read records + consensus (+ MSA)."""
+def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: bool = False):
+    """Progressive POA of one group through `lib`; returns per-read records + consensus (+ MSA).
+
+    use_oracle=True: the graph / consensus / MSA code of `lib` is driven, but every
+    alignment comes from the scalar oracle (oracle/libpoa_oracle.so).  That is how the
+    CPU-only suite exercises the product's host layer without a GPU -- a test harness
+    arrangement, not a product path."""
     cfg = PoaConfig(**{**cfg.__dict__, "out_msa": want_msa})
     with PoaSession(cfg, lib) as s:
-        alns = s.run_reads(reads)
+        if use_oracle:
+            from oracle_binding import oracle_align
+            s.reset(max((len(r) for r in reads), default=1024))
+            alns = []
+            for r in reads:
+                a, res = oracle_align(s, r)
+                alns.append(a)
+                s.add(r, res, len(reads))
+        else:
+            alns = s.run_reads(reads)
         s.generate()
         return {
             "alns": alns,
@@ -60,3 +74,29 @@ def assert_group_equal(a, b, tag=""):
     assert len(a["msa"]) == len(b["msa"])
     for x, y in zip(a["msa"], b["msa"]):
         assert np.array_equal(x, y), f"{tag}: RC-MSA differs"
+
+
+def group_digest(r, m: int = 5):
+    """Same shape as the entries of tests/golden/golden.json."""
+    import hashlib
+
+    from abpoa_b200.aligner import decode
+
+    def sha(a):
+        return hashlib.sha1(a.tobytes()).hexdigest()
+    return {
+        "alns": [{"aligned": a.aligned, "score": a.best_score, "cells": a.cells, "n_cigar": int(len(a.cigar)), "cigar_sha1": sha(a.cigar),
+                  "ends": [a.node_s, a.node_e, a.query_s, a.query_e]} for a in r["alns"]],
+        "cons": [decode(c, m) for c in r["cons"]],
+        "cov_sha1": [sha(c) for c in r["cov"]],
+        "msa_sha1": [sha(x) for x in r["msa"]],
+        "msa_len": int(len(r["msa"][0])) if r["msa"] else 0,
+    }
+
+
+def assert_digest_equal(got, want, tag=""):
+    assert len(got["alns"]) == len(want["alns"]), tag
+    for i, (x, y) in enumerate(zip(got["alns"], want["alns"])):
+        assert x == y, f"{tag} read {i}: {x} != {y}"
+    for k in ("cons", "cov_sha1", "msa_len", "msa_sha1"):
+        assert got[k] == want[k], f"{tag}: {k} differs"

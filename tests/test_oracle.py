@@ -1,0 +1,35 @@
+"""CPU suite, part 1: pin the oracle.
+
+* the scalar restatement (oracle/poa_oracle.c) reproduces the golden vectors generated from
+  the unmodified reference (tests/golden/golden.json, made by tests/golden/make_golden.py);
+* when oracle/_ref is present, it is also compared live, read by read, against the reference
+  (scores, CIGAR words, end points, DP-cell counts).
+The alignments come from the oracle; graph fusion / consensus / MSA run in the product's host
+layer, so this also pins that layer on the CPU.
+"""
+import json
+from pathlib import Path
+
+import pytest
+
+from abpoa_b200.aligner import PoaConfig
+from cases import CASES, case_reads
+from helpers import assert_digest_equal, assert_group_equal, group_digest, run_group
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_golden(product_lib, name):
+    case = CASES[name]
+    cfg = PoaConfig(**case["cfg"])
+    got = group_digest(run_group(product_lib, cfg, case_reads(case), use_oracle=True), cfg.m)
+    assert_digest_equal(got, GOLDEN["cases"][name], name)
+
+
+@pytest.mark.parametrize("name", ["seq_affine", "syn_convex_2k", "syn_local_linear", "syn_aa_blosum62", "syn_ragged"])
+def test_oracle_matches_live_reference(product_lib, reference_lib, name):
+    case = CASES[name]
+    cfg = PoaConfig(**case["cfg"])
+    reads = case_reads(case)
+    assert_group_equal(run_group(product_lib, cfg, reads, use_oracle=True), run_group(reference_lib, cfg, reads), name)
