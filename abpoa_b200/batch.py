@@ -35,7 +35,8 @@ class abpoa_gpu_group_result_t(C.Structure):
 class abpoa_gpu_stats_t(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("wall_ms", C.c_double),
                 ("cells", C.c_int64), ("alignments", C.c_int64), ("launches", C.c_int64), ("retries", C.c_int64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int),
+                ("fwd_clk", C.c_int64), ("bt_clk", C.c_int64)]
 
 
 @dataclass

@@ -89,6 +89,7 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
         const poa_engine_stats *s = poa_dev_ctx_stats(c);
         out->kernel_ms += s->kernel_ms; out->cells += s->cells; out->alignments += s->alignments;
         out->launches += s->launches; out->retries += s->retries; out->h2d_bytes += s->h2d_bytes; out->d2h_bytes += s->d2h_bytes;
+        out->fwd_clk += s->fwd_clk; out->bt_clk += s->bt_clk;
     }
     out->wall_ms = e->wall_ms; out->n_workers = e->n_workers; out->device = e->dev;
 }
@@ -177,7 +178,15 @@ void finish_group(GroupState &gs, abpoa_para_t *abpt) {
     }
 }
 
+struct PhaseClock {
+    double plan = 0, run = 0, fuse = 0, finish = 0, setup = 0;
+    std::chrono::steady_clock::time_point t;
+    void tic() { t = std::chrono::steady_clock::now(); }
+    double toc() { auto n = std::chrono::steady_clock::now(); double d = std::chrono::duration<double, std::milli>(n - t).count(); t = n; return d; }
+};
+
 void worker_main(Worker wk) {
+    PhaseClock pc; const bool prof = getenv("ABPOA_GPU_PROFILE") != NULL;
     if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
     abpoa_para_t *abpt = wk.abpt;
     const int G = wk.eng->groups_per_launch;
@@ -192,6 +201,7 @@ void worker_main(Worker wk) {
         while ((int)handles.size() < ng) handles.push_back(abpoa_init());
         std::vector<GroupState> gs(ng);
         int max_reads = 0;
+        pc.tic();
         for (int t = 0; t < ng; ++t) {
             GroupState &s = gs[t];
             s.in = &wk.groups[g0 + t]; s.out = &wk.results[g0 + t]; s.ab = handles[t]; s.next_read = 0;
@@ -217,8 +227,15 @@ void worker_main(Worker wk) {
             }
         }
         std::vector<poa_job> jobs; std::vector<Pending> pend(ng); std::vector<int> owner;
+        {   /* graphs of ~5 % error reads end near 2.5x the read length; leave headroom */
+            int qmax = 0;
+            for (int t = 0; t < ng; ++t) for (int i = 0; i < gs[t].in->n_seq; ++i) if (gs[t].in->seq_lens[i] > qmax) qmax = gs[t].in->seq_lens[i];
+            poa_dev_ctx_reserve(wk.ctx, ng, 3 * qmax + 64, qmax);
+        }
+        pc.setup += pc.toc();
         for (int r = 0; r < max_reads; ++r) {
             jobs.clear(); owner.clear();
+            pc.tic();
             for (int t = 0; t < ng; ++t) {
                 GroupState &s = gs[t];
                 pend[t].gs = &s; pend[t].have = false; memset(&pend[t].res, 0, sizeof(abpoa_res_t));
@@ -232,7 +249,9 @@ void worker_main(Worker wk) {
                 poa_blob_plan_make(&j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, s.in->seq_lens[r]);
                 jobs.push_back(j); owner.push_back(t);
             }
+            pc.plan += pc.toc();
             if (!jobs.empty()) poa_engine_run(wk.ctx, abpt, jobs.data(), (int)jobs.size(), sink_to_res, &sc);
+            pc.run += pc.toc();
 
             /* optional strand retry (-s): align the reverse complement of weak hits */
             std::vector<uint8_t *> rc_seq(ng, (uint8_t *)NULL); std::vector<int *> rc_w(ng, (int *)NULL);
@@ -288,14 +307,22 @@ void worker_main(Worker wk) {
                 if (pend[t].res.n_cigar) free(pend[t].res.graph_cigar);
                 free(rc_seq[t]); free(rc_w[t]);
             }
+            pc.fuse += pc.toc();
         }
+        pc.tic();
         for (int t = 0; t < ng; ++t) {
             finish_group(gs[t], abpt);
             for (int i = 0; i < gs[t].in->n_seq; ++i) free(gs[t].weights[i]);
             free(gs[t].weights);
         }
     }
+    pc.finish += pc.toc();
     for (abpoa_t *ab : handles) abpoa_free(ab);
+    if (prof) {
+        const poa_engine_stats *st = poa_dev_ctx_stats(wk.ctx);
+        fprintf(stderr, "[worker] setup %.0f plan %.0f run %.0f (kernel %.0f, fill %.0f, wait %.0f, copy %.0f) fuse %.0f finish %.0f ms\n",
+                pc.setup, pc.plan, pc.run, st->kernel_ms, st->fill_ms, st->wait_ms, st->copy_ms, pc.fuse, pc.finish);
+    }
 }
 
 }  // namespace

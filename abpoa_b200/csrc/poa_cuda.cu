@@ -19,12 +19,14 @@
 #include <mutex>
 #include <condition_variable>
 #include <algorithm>
+#include <chrono>
 #include "poa_internal.h"
 #include "poa_device.cuh"
 #include "poa_engine.h"
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
-                                        const PoaParamsDev *prm, int n_jobs, cudaStream_t st);
+                                        const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st);
+extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     poa_die("libabpoa_b200/cuda", "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
@@ -135,19 +137,32 @@ int poa_dev_ctx_device(const poa_dev_ctx *c) { return c->dev; }
 
 static void grow_host(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return;
-    size_t n = al256(need + need / 4);
+    size_t n = al256(need * 2);
     if (*p) CK(cudaFreeHost(*p));
     CK(cudaHostAlloc((void **)p, n, cudaHostAllocDefault));
     *cap = n;
 }
 static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
     if (need <= *cap) return;
-    size_t n = al256(slack ? need + need / 4 : need);
+    size_t n = al256(slack ? need * 2 : need);
     if (*p) CK(cudaFree(*p));
     cudaError_t e = cudaMalloc((void **)p, n);
     if (e != cudaSuccess && slack) { cudaGetLastError(); n = al256(need); e = cudaMalloc((void **)p, n); }
     if (e != cudaSuccess) poa_die("libabpoa_b200/cuda", "cudaMalloc of %zu bytes failed: %s", n, cudaGetErrorString(e));
     *cap = n;
+}
+
+/* Size the staging buffers once for a known workload (rows / query length per job, jobs per
+ * launch) so that steady-state launches never call cudaMalloc / cudaFree (both serialise
+ * the device across all streams). */
+void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint) {
+    CK(cudaSetDevice(c->dev));
+    const size_t r = (size_t)rows_hint, q = (size_t)qlen_hint, j = (size_t)jobs;
+    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 20 + (q + r + 8) * 8 + 1024), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
+    if (in_b > c->h_in_cap) grow_host(&c->h_in, &c->h_in_cap, in_b / 2 + 1);
+    if (in_b > c->d_in_cap) grow_dev(&c->d_in, &c->d_in_cap, in_b / 2 + 1, 1);
+    if (work_b > c->d_work_cap) grow_dev(&c->d_work, &c->d_work_cap, work_b / 2 + 1, 1);
+    if (out_b > c->h_out_cap) grow_host(&c->h_out, &c->h_out_cap, out_b / 2 + 1);
 }
 
 void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
@@ -179,8 +194,13 @@ static uint64_t plane_units_for(const poa_job *j, int gap_mode, int generous) {
 
 /* Run `n` jobs that share parameters and score width.  Results land in pinned host memory
  * owned by the context (valid until the next run on this context). */
+static inline double now_ms(void) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
     CK(cudaSetDevice(c->dev));
+    const double t_begin = now_ms();
     const int S = bits / 8;
     /* ---- layout of the input arena: params | descs | blobs ---- */
     size_t in_bytes = al256(sizeof(PoaParamsDev)) + al256((size_t)n * sizeof(PoaJobDesc));
@@ -225,16 +245,28 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         desc[t].result = (PoaResultDev *)c->d_work + t;
     }
     c->last_desc = desc[0]; c->last_bits = bits; c->last_gap = abpt->gap_mode; c->last_rows = jobs[idx[0]].plan.n_rows;
+    const double t_filled = now_ms();
     CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
     CK(cudaEventRecord(c->ev_k0, c->st));
+    /* shared-memory ring: wide enough for the widest expected band of this launch */
+    int band_cells = 0;
+    for (int t = 0; t < n; ++t) {
+        const poa_blob_plan &pl = jobs[idx[t]].plan;
+        const int bc = pl.w >= 0 ? (2 * pl.w + 1 + 40 + 7) / 8 * 8 : (pl.qlen + 1 + 7) / 8 * 8 + 8;
+        if (bc > band_cells) band_cells = bc;
+    }
+    static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
+    int ring_rows = 2, ring_cells = 64;
+    poa_pick_ring(abpt->gap_mode, bits, band_cells, smem_budget, &ring_rows, &ring_cells);
     CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
-                        (const PoaParamsDev *)c->d_in, n, c->st));
+                        (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     CK(cudaEventRecord(c->ev_k1, c->st));
     /* ---- results first (they say how many cigar words each job produced) ---- */
     size_t out_bytes = al256((size_t)n * sizeof(PoaResultDev));
     grow_host(&c->h_out, &c->h_out_cap, out_bytes);
     CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    const double t_waited = now_ms();
     if (c->arena) arena_give(c->arena, planes_base, plane_bytes);      /* the backtrace is done: planes are dead */
     float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
     c->stats.kernel_ms += ms; c->stats.launches += 1; c->stats.h2d_bytes += in_bytes;
@@ -257,6 +289,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     }
     CK(cudaStreamSynchronize(c->st));
     c->stats.d2h_bytes += out_bytes;
+    c->stats.fill_ms += t_filled - t_begin; c->stats.wait_ms += t_waited - t_filled; c->stats.copy_ms += now_ms() - t_waited;
     for (int t = 0; t < n; ++t) {
         poa_job &j = jobs[idx[t]];
         j.status = resv[t].status;
@@ -267,7 +300,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         j.n_ops = resv[t].status == POA_ST_OK ? resv[t].n_ops : 0;
         j.ops = (const uint64_t *)(c->h_out + out_cig[t]);
         j.bands = j.want_bands ? (const int32_t *)(c->h_out + out_band[t]) : NULL;
-        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; }
+        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; }
     }
 }
 

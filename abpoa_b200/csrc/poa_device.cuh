@@ -47,6 +47,7 @@ typedef struct PoaResultDev {
     int32_t max_band;                   /* widest row (cells)                               */
     int64_t cells;                      /* sum over DP rows of (end - beg + 1)              */
     uint64_t plane_units_used;          /* 8-cell units of plane storage consumed           */
+    int64_t fwd_clk, bt_clk;            /* SM clock cycles spent in the forward DP / the backtrace */
 } PoaResultDev;
 
 /* device pointers of one job */

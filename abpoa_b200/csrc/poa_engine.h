@@ -30,6 +30,8 @@ typedef struct {
     double kernel_ms;               /* CUDA-event time of the alignment kernels               */
     int64_t cells, alignments, launches, retries;
     uint64_t h2d_bytes, d2h_bytes;
+    int64_t fwd_clk, bt_clk;            /* SM cycles in the forward DP / backtrace, summed over alignments */
+    double fill_ms, wait_ms, copy_ms;   /* host-side phases of a launch: blob fill, kernel wait, result copies */
 } poa_engine_stats;
 
 /* One big HBM region shared by the stream contexts of a batch engine: score planes live
@@ -40,6 +42,7 @@ void poa_arena_destroy(poa_arena *a);
 size_t poa_arena_capacity(const poa_arena *a);
 poa_dev_ctx *poa_dev_ctx_new_on(int dev);
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a);
+void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint);
 
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);
 void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res);

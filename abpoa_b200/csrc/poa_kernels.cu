@@ -281,13 +281,28 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
 }
 
 /* ================================================================== forward DP + backtrace */
+/* planes a successor row reads from its predecessors: H (+E1 (+E2)) */
+template <int GAP> struct RingPlanes { static constexpr int N = GAP == LG ? 1 : (GAP == AG ? 2 : 3); };
+
 template <int GAP, typename ST, int MODE>
-__global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm, int n_jobs) {
+__global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
+                                                       int n_jobs, int ring_rows, int ring_cells) {
     typedef Planes<GAP> PL;
-    __shared__ int mat_s[POA_MAX_M * POA_MAX_M];
+    constexpr int RN = RingPlanes<GAP>::N;
+    /* shared memory: substitution matrix | ring of the last `ring_rows` rows' (band, arg-max, slab offset)
+     * | ring of their H/E planes.  Predecessors are almost always within a few rows (BFS order), so the
+     * row recurrence is fed from shared memory; HBM only receives the planes the backtrace will need. */
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    int *mat_s = reinterpret_cast<int *>(dyn_smem);
+    PoaRowInfo *ring_info = reinterpret_cast<PoaRowInfo *>(dyn_smem + POA_MAX_M * POA_MAX_M * sizeof(int));
+    uint32_t *ring_off = reinterpret_cast<uint32_t *>(ring_info + ring_rows);
+    ST *ring_data = reinterpret_cast<ST *>(reinterpret_cast<uint8_t *>(ring_off) + (((size_t)ring_rows * 4 + 15) & ~(size_t)15));
+    const int rmask = ring_rows - 1, ring_groups = ring_cells >> 3;
+
     const int lane = threadIdx.x;
     const int job = blockIdx.x;
     if (job >= n_jobs) return;
+    const long long clk0 = clock64();
     const int m = prm->m;
     for (int t = lane; t < m * m; t += 32) mat_s[t] = prm->mat[t];
     __syncwarp();
@@ -298,6 +313,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
     const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
     const bool banded = w >= 0;
+    const bool use_remain = banded || (MODE == EXTEND && prm->zdrop > 0);
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
     const int pnv = prm->pn;
     const int zr = prm->zero;            /* run-time 0: keeps ptxas from fusing the LOCAL floors into VIMNMX.RELU */
@@ -305,6 +321,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     PoaResultDev res;
     res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
     res.start_i = res.start_j = 0; res.n_aln_bases = res.n_matched_bases = 0; res.max_band = 0; res.cells = 0; res.plane_units_used = 0;
+    res.fwd_clk = 0; res.bt_clk = 0;
 
     uint64_t cursor = 0;                 /* bump allocator over the job's plane slab, in 8-cell units */
     int64_t cells = 0; int max_band = 0;
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     /* ---------------- row 0 (the begin node): reference first_dp, :582-688 ---------------- */
     {
         int end0 = qlen;
-        if (banded) end0 = min(qlen, max(0, qlen - jv.remain[0]) + w);
+        if (banded) end0 = min(qlen, max(0, qlen - __ldg(jv.remain)) + w);
         const int g1 = end0 >> 3, ngrp = g1 + 1;
         if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
@@ -337,19 +354,41 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 st8(rp, h);
                 if (GAP != LG) { st8(rp + (size_t)PL::E1 * ngrp * POA_GROUP, ea); st8(rp + (size_t)PL::F1 * ngrp * POA_GROUP, fa); }
                 if (GAP == CG) { st8(rp + (size_t)PL::E2 * ngrp * POA_GROUP, eb); st8(rp + (size_t)PL::F2 * ngrp * POA_GROUP, fb); }
+                if (g < ring_groups) {
+                    ST *rq = ring_data + (size_t)g * POA_GROUP;               /* slot 0 */
+                    st8(rq, h);
+                    if (GAP != LG) st8(rq + ring_cells, ea);
+                    if (GAP == CG) st8(rq + 2 * ring_cells, eb);
+                }
             }
         }
-        if (lane == 0) { PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0; rowinfo[0] = r0; rowoff[0] = 0; }
+        if (lane == 0) {
+            PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0;
+            rowinfo[0] = r0; rowoff[0] = 0; ring_info[0] = r0; ring_off[0] = 0;
+        }
         cursor = (uint64_t)ngrp * PL::N;
         cells += end0 + 1; max_band = end0 + 1;
         __syncwarp();
     }
 
-    /* ---------------- rows 1 .. n_rows-2 in topological order ---------------- */
+    /* ---------------- rows 1 .. n_rows-2 in topological order ----------------
+     * The graph side of a row (predecessor list, residue, band centre) is static: it is fetched
+     * one row ahead so that its latency never sits on the row-to-row dependency chain. */
+    int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
+    if (n_rows > 2) {
+        pb = __ldg(jv.predoff + 1); pe = __ldg(jv.predoff + 2); rbase = __ldg(jv.base + 1);
+        if (use_remain) rem = __ldg(jv.remain + 1);
+        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
+    }
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
-        if (jv.live && !jv.live[i]) continue;
-        const int pb = jv.predoff[i], np = jv.predoff[i + 1] - pb;
-        const int rbase = jv.base[i];
+        int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
+        if (i + 1 < n_rows - 1) {
+            n_pe = __ldg(jv.predoff + i + 2); n_rbase = __ldg(jv.base + i + 1);
+            if (use_remain) n_rem = __ldg(jv.remain + i + 1);
+            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
+        }
+        const int np = pe - pb;
+        if (!(jv.live && !__ldg(jv.live + i))) {
 
         /* lane k holds predecessor k (chunk 0); band hints are reductions over all of them */
         int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
@@ -358,10 +397,14 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             const int k = kb + lane;
             int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
             if (k < np) {
-                const int prow = jv.pred[pb + k];
-                const PoaRowInfo pi = rowinfo[prow];
+                const int prow = kb == 0 ? mypred : __ldg(jv.pred + pb + k);
+                const bool near = (i - prow) <= rmask;
+                const PoaRowInfo pi = near ? ring_info[prow & rmask] : rowinfo[prow];
                 l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
-                if (kb == 0) { pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_off = rowoff[prow]; pk_ps = jv.predscore ? jv.predscore[pb + k] : 0; }
+                if (kb == 0) {
+                    pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_ps = myps;
+                    pk_off = near ? ring_off[prow & rmask] : rowoff[prow];
+                }
             }
             if (banded) {
                 ml = min(ml, __reduce_min_sync(FULL, l1));
@@ -371,7 +414,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         }
         int beg = 0, end = qlen;
         if (banded) {
-            const int r = qlen - jv.remain[i];
+            const int r = qlen - rem;
             beg = max(0, min(ml, r) - w);
             end = min(qlen, max(mr, r) + w);
             if (np > 0 && beg / pnv < min_pre_beg / pnv) beg = min_pre_beg;      /* reference's vector-granular clamp */
@@ -384,6 +427,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         const uint32_t my_off = (uint32_t)cursor;
         cursor += (uint64_t)ngrp * PL::N;
         ST *rowp = planes + (size_t)my_off * POA_GROUP;
+        ST *ringp = ring_data + (size_t)(i & rmask) * RN * ring_cells;
         cells += (end >= beg) ? (end - beg + 1) : 0;
         max_band = max(max_band, end - beg + 1);
 
@@ -394,6 +438,9 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         for (int gp = g0; gp <= g1; gp += 32) {
             const int g = gp + lane;
             const bool active = g <= g1;
+            /* this lane's 8 query residues; independent of the predecessors, so issued first */
+            uint2 qv = make_uint2(0u, 0u);
+            if (active) qv = __ldg(reinterpret_cast<const uint2 *>(jv.qs + (size_t)g * 8));
             int M[8], X1[8], X2[8];                         /* M: diagonal term; X1/X2: E1/E2 inputs (LG: X1 = vertical term) */
             fill8(M, NEG); fill8(X1, NEG); if (GAP == CG) fill8(X2, NEG);
 
@@ -402,29 +449,39 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 if (kb > 0) {                               /* rare: more than 32 predecessors */
                     const int k = kb + lane; c_row = -1;
                     if (k < np) {
-                        c_row = jv.pred[pb + k]; const PoaRowInfo pi = rowinfo[c_row];
-                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? jv.predscore[pb + k] : 0;
+                        c_row = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
+                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? __ldg(jv.predscore + pb + k) : 0;
                     }
                 }
                 const int nk = min(32, np - kb);
                 for (int k = 0; k < nk; ++k) {
+                    const int p_row = __shfl_sync(FULL, c_row, k);
                     const int p_beg = __shfl_sync(FULL, c_beg, k), p_end = __shfl_sync(FULL, c_end, k);
                     const uint32_t p_off = __shfl_sync(FULL, c_off, k);
                     const int ps = jv.predscore ? __shfl_sync(FULL, c_ps, k) : 0;
                     const int pg0 = p_beg >> 3, pg1 = p_end >> 3, png = pg1 - pg0 + 1;
-                    const ST *ph = planes + (size_t)p_off * POA_GROUP;
+                    const bool near = (i - p_row) <= rmask;
+                    const ST *ph = planes + (size_t)p_off * POA_GROUP;                       /* HBM copy   */
+                    const ST *rh = ring_data + (size_t)(p_row & rmask) * RN * ring_cells;    /* smem copy  */
                     int hp[8], ep1[8], ep2[8];
                     const bool inr = active && g >= pg0 && g <= pg1;
-                    if (inr) {
-                        const ST *q = ph + (size_t)(g - pg0) * POA_GROUP;
+                    const int rel = g - pg0;
+                    if (inr && near && rel < ring_groups) {
+                        const ST *q = rh + (size_t)rel * POA_GROUP;
+                        ld8(q, hp);
+                        if (GAP != LG) ld8(q + ring_cells, ep1);
+                        if (GAP == CG) ld8(q + 2 * ring_cells, ep2);
+                    } else if (inr) {
+                        const ST *q = ph + (size_t)rel * POA_GROUP;
                         ld8(q, hp);
                         if (GAP != LG) ld8(q + (size_t)PL::E1 * png * POA_GROUP, ep1);
                         if (GAP == CG) ld8(q + (size_t)PL::E2 * png * POA_GROUP, ep2);
                     } else { fill8(hp, NEG); if (GAP != LG) fill8(ep1, NEG); if (GAP == CG) fill8(ep2, NEG); }
                     int hm1 = __shfl_up_sync(FULL, hp[7], 1);
                     if (lane == 0) {
-                        const int gm = g - 1;
-                        hm1 = (gm >= pg0 && gm <= pg1) ? (int)ph[(size_t)(gm - pg0) * POA_GROUP + 7] : NEG;
+                        const int relm = rel - 1;
+                        hm1 = NEG;
+                        if (relm >= 0 && relm < png) hm1 = (near && relm < ring_groups) ? (int)rh[(size_t)relm * POA_GROUP + 7] : (int)ph[(size_t)relm * POA_GROUP + 7];
                         if (MODE == LOCAL && g == 0) hm1 = 0;
                     }
                     M[0] = max(M[0], hm1 + ps);
@@ -445,8 +502,6 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             }
 
             /* substitution scores of this row's residue against the lane's 8 query bases */
-            uint2 qv = make_uint2(0u, 0u);
-            if (active) qv = *reinterpret_cast<const uint2 *>(jv.qs + (size_t)g * 8);
             const int *mrow = mat_s + rbase * m;
             int T[8], H[8], Fa[8], Fb[8];
             bool inb[8];
@@ -524,7 +579,14 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             }
 
             if (active) {
-                ST *q = rowp + (size_t)(g - g0) * POA_GROUP;
+                const int rel = g - g0;
+                if (rel < ring_groups) {                    /* what successors read: shared memory */
+                    ST *rq = ringp + (size_t)rel * POA_GROUP;
+                    st8(rq, H);
+                    if (GAP != LG) st8(rq + ring_cells, E1o);
+                    if (GAP == CG) st8(rq + 2 * ring_cells, E2o);
+                }
+                ST *q = rowp + (size_t)rel * POA_GROUP;    /* what the backtrace reads: HBM */
                 st8(q, H);
                 if (GAP != LG) { st8(q + (size_t)PL::E1 * ngrp * POA_GROUP, E1o); st8(q + (size_t)PL::F1 * ngrp * POA_GROUP, Fa); }
                 if (GAP == CG) { st8(q + (size_t)PL::E2 * ngrp * POA_GROUP, E2o); st8(q + (size_t)PL::F2 * ngrp * POA_GROUP, Fb); }
@@ -542,17 +604,23 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 }
             }
         }
-        if (lane == 0) { PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right; rowinfo[i] = ri; rowoff[i] = my_off; }
+        if (lane == 0) {
+            PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
+            ring_info[i & rmask] = ri; ring_off[i & rmask] = my_off;
+            rowinfo[i] = ri; rowoff[i] = my_off;
+        }
         if (MODE == LOCAL) {
             if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_left; }
         } else if (MODE == EXTEND) {
             if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_right; best_row = i; }
             else if (prm->zdrop > 0) {
-                const int delta = jv.remain[best_row] - jv.remain[i];
+                const int delta = __ldg(jv.remain + best_row) - rem;
                 if (best_score - row_max > prm->zdrop + e1 * abs(delta - (row_right - best_j))) stop = true;
             }
         }
         __syncwarp();
+        }   /* live row */
+        pb = pe; pe = n_pe; rbase = n_rbase; rem = n_rem; mypred = n_mypred; myps = n_myps;
     }
 
     /* ---------------- global mode: best end cell among the SINK's predecessors ---------------- */
@@ -569,31 +637,64 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     }
     res.best_score = best_score; res.best_i = best_i; res.best_j = best_j;
     res.cells = cells; res.max_band = max_band; res.plane_units_used = cursor;
+    const long long clk1 = clock64();
+    res.fwd_clk = clk1 - clk0;
     if (lane == 0) *jd.result = res;
     __syncwarp();
-    if (prm->ret_cigar) poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+    if (prm->ret_cigar) {
+        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+        if (lane == 0) jd.result->bt_clk = clock64() - clk1;
+    }
 }
 
 /* ------------------------------------------------------------------ launcher */
-template <int GAP, typename ST>
-static cudaError_t launch_mode(int mode, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, cudaStream_t st) {
-    switch (mode) {
-    case GLOBAL: poa_align_kernel<GAP, ST, GLOBAL><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
-    case LOCAL:  poa_align_kernel<GAP, ST, LOCAL><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
-    default:     poa_align_kernel<GAP, ST, EXTEND><<<n_jobs, 32, 0, st>>>(jobs, prm, n_jobs); break;
+static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells) {
+    const int rn = gap == LG ? 1 : (gap == AG ? 2 : 3);
+    return (size_t)POA_MAX_M * POA_MAX_M * sizeof(int) + (size_t)ring_rows * sizeof(PoaRowInfo) + (((size_t)ring_rows * 4 + 15) & ~(size_t)15)
+           + (size_t)ring_rows * rn * ring_cells * (bits / 8);
+}
+
+template <int GAP, typename ST, int MODE>
+static cudaError_t launch_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
+    const size_t smem = ring_smem_bytes(GAP, (int)sizeof(ST) * 8, ring_rows, ring_cells);
+    static size_t configured = 0;                         /* per instantiation */
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 227 * 1024;
     }
+    poa_align_kernel<GAP, ST, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
     return cudaGetLastError();
 }
 
+template <int GAP, typename ST>
+static cudaError_t launch_mode(int mode, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, cudaStream_t st) {
+    switch (mode) {
+    case GLOBAL: return launch_one<GAP, ST, GLOBAL>(jobs, prm, n_jobs, rr, rc, st);
+    case LOCAL:  return launch_one<GAP, ST, LOCAL>(jobs, prm, n_jobs, rr, rc, st);
+    default:     return launch_one<GAP, ST, EXTEND>(jobs, prm, n_jobs, rr, rc, st);
+    }
+}
+
+/* Pick the shared-memory ring geometry for a launch: slots wide enough for the expected band
+ * (`band_cells`, already a multiple of 8) and as many rows as fit the per-CTA budget. */
+extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells) {
+    int rc = band_cells < 64 ? 64 : band_cells;
+    int rr = 64;
+    while (rr > 2 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rr >>= 1;
+    while (rc > 64 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rc -= 64;   /* very wide rows: cache a prefix */
+    *ring_rows = rr; *ring_cells = rc;
+}
+
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
-                                        const PoaParamsDev *prm, int n_jobs, cudaStream_t st) {
+                                        const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
     if (bits == 16) {
-        if (gap_mode == LG) return launch_mode<LG, int16_t>(align_mode, jobs, prm, n_jobs, st);
-        if (gap_mode == AG) return launch_mode<AG, int16_t>(align_mode, jobs, prm, n_jobs, st);
-        return launch_mode<CG, int16_t>(align_mode, jobs, prm, n_jobs, st);
+        if (gap_mode == LG) return launch_mode<LG, int16_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+        if (gap_mode == AG) return launch_mode<AG, int16_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+        return launch_mode<CG, int16_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
     }
-    if (gap_mode == LG) return launch_mode<LG, int32_t>(align_mode, jobs, prm, n_jobs, st);
-    if (gap_mode == AG) return launch_mode<AG, int32_t>(align_mode, jobs, prm, n_jobs, st);
-    return launch_mode<CG, int32_t>(align_mode, jobs, prm, n_jobs, st);
+    if (gap_mode == LG) return launch_mode<LG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    if (gap_mode == AG) return launch_mode<AG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    return launch_mode<CG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
 }

@@ -51,6 +51,7 @@ typedef struct {
     int64_t cells, alignments, launches, retries;
     uint64_t h2d_bytes, d2h_bytes;
     int n_workers, device;
+    int64_t fwd_clk, bt_clk;            /* SM clock cycles inside the forward DP / the backtrace, summed over alignments */
 } abpoa_gpu_stats_t;
 
 #define ABPOA_GPU_RECORD_READS 0x1

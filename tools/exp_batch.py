@@ -25,4 +25,4 @@ with BatchEngine(n_workers=workers, groups_per_launch=gpl) as eng:
         cells = sum(r[0] for r in res)
         print(f"{name} groups={n_groups} workers={workers} gpl={gpl}: wall {dt:.2f}s cells {cells/1e9:.2f}G -> {cells/dt/1e9:.2f} GCUPS e2e, "
               f"reads/s {packed.total_reads/dt:.0f}; kernel_ms(sum over streams) {st['kernel_ms']:.0f} launches {st['launches']} retries {st['retries']} "
-              f"h2d {st['h2d_bytes']/1e9:.2f}GB d2h {st['d2h_bytes']/1e9:.2f}GB", flush=True)
+              f"h2d {st['h2d_bytes']/1e9:.2f}GB d2h {st['d2h_bytes']/1e9:.2f}GB; per-aln fwd {st['fwd_clk']/max(st['alignments'],1)/1e3:.0f}k clk bt {st['bt_clk']/max(st['alignments'],1)/1e3:.0f}k clk", flush=True)
