@@ -17,6 +17,7 @@ from .aligner import PoaConfig, make_para
 from .capi import c_int_p, c_u8_p, c_u64_p
 
 ABPOA_GPU_RECORD_READS = 0x1
+ABPOA_GPU_CAPTURE_JOBS = 0x2
 
 
 class abpoa_gpu_group_t(C.Structure):
@@ -37,6 +38,13 @@ class abpoa_gpu_stats_t(C.Structure):
                 ("cells", C.c_int64), ("alignments", C.c_int64), ("launches", C.c_int64), ("retries", C.c_int64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int),
                 ("fwd_clk", C.c_int64), ("bt_clk", C.c_int64)]
+
+
+class abpoa_gpu_replay_t(C.Structure):
+    _fields_ = [("n_jobs", C.c_int64), ("cells", C.c_int64), ("rows", C.c_int64), ("preds", C.c_int64),
+                ("jobs16", C.c_int64), ("cells16", C.c_int64),
+                ("kernel_ms", C.c_double), ("kernel_ms_min", C.c_double), ("launches", C.c_int64), ("mismatches", C.c_int64),
+                ("input_bytes", C.c_uint64)]
 
 
 @dataclass
@@ -63,6 +71,9 @@ def _bind(lib):
     d.abpoa_gpu_group_result_free.argtypes = [C.POINTER(abpoa_gpu_group_result_t)]
     d.abpoa_gpu_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(abpoa_gpu_stats_t)]
     d.abpoa_gpu_batch_reset_stats.argtypes = [C.c_void_p]
+    d.abpoa_gpu_replay.restype = C.c_int
+    d.abpoa_gpu_replay.argtypes = [C.c_void_p, capi.abpoa_para_t_p, C.c_int, C.c_int, C.POINTER(abpoa_gpu_replay_t)]
+    d.abpoa_gpu_capture_clear.argtypes = [C.c_void_p]
     return d
 
 
@@ -114,9 +125,10 @@ class BatchEngine:
     def __exit__(self, *exc):
         self.close()
 
-    def run_packed(self, abpt, packed: PackedGroups, record_reads: bool = False, keep_results: bool = True):
+    def run_packed(self, abpt, packed: PackedGroups, record_reads: bool = False, keep_results: bool = True, capture: bool = False):
         res = (abpoa_gpu_group_result_t * packed.n)()
-        self.d.abpoa_gpu_msa_batch(self.h, abpt, packed.n, packed.arr, res, ABPOA_GPU_RECORD_READS if record_reads else 0)
+        flags = (ABPOA_GPU_RECORD_READS if record_reads else 0) | (ABPOA_GPU_CAPTURE_JOBS if capture else 0)
+        self.d.abpoa_gpu_msa_batch(self.h, abpt, packed.n, packed.arr, res, flags)
         out = []
         for g in range(packed.n):
             r = res[g]
@@ -142,6 +154,17 @@ class BatchEngine:
             return self.run_packed(abpt, PackedGroups(groups), record_reads)
         finally:
             self.lib.abpoa_free_para(abpt)
+
+    def replay(self, abpt, warmup: int = 1, repeats: int = 3) -> dict:
+        """Device-resident re-run of the jobs captured by run_packed(..., capture=True)."""
+        r = abpoa_gpu_replay_t()
+        rc = self.d.abpoa_gpu_replay(self.h, abpt, warmup, repeats, C.byref(r))
+        if rc != 0:
+            raise RuntimeError("nothing captured to replay")
+        return {k: getattr(r, k) for k, _ in abpoa_gpu_replay_t._fields_}
+
+    def clear_capture(self):
+        self.d.abpoa_gpu_capture_clear(self.h)
 
     def stats(self) -> dict:
         s = abpoa_gpu_stats_t()

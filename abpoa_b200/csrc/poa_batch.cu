@@ -23,12 +23,17 @@
 #include <chrono>
 #include <thread>
 #include <vector>
+#include <mutex>
+#include <algorithm>
 #include <string.h>
 #include "abpoa_gpu.h"
 #include "poa_internal.h"
 #include "poa_engine.h"
 
+struct CapturedJob { uint8_t *blob; size_t bytes; int n_rows, qlen, w, n_pred, bits, best_score, n_ops; int64_t cells; };
+
 struct abpoa_gpu_batch {
+    std::mutex cap_mu; std::vector<CapturedJob> captured;
     int dev, n_workers, groups_per_launch;
     poa_arena *arena;
     std::vector<poa_dev_ctx *> ctx;
@@ -76,8 +81,76 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     return e;
 }
 
+extern "C" void abpoa_gpu_capture_clear(abpoa_gpu_batch_t *e) {
+    for (CapturedJob &c : e->captured) free(c.blob);
+    e->captured.clear();
+}
+
+static void capture_cb(void *user, const poa_captured_job *cj) {
+    abpoa_gpu_batch *e = (abpoa_gpu_batch *)user;
+    CapturedJob c; c.bytes = cj->bytes; c.blob = (uint8_t *)poa_xmalloc(cj->bytes); memcpy(c.blob, cj->blob, cj->bytes);
+    c.n_rows = cj->n_rows; c.qlen = cj->qlen; c.w = cj->w; c.n_pred = cj->n_pred; c.bits = cj->bits;
+    c.best_score = cj->best_score; c.n_ops = cj->n_ops; c.cells = cj->cells;
+    std::lock_guard<std::mutex> lk(e->cap_mu);
+    e->captured.push_back(c);
+}
+
+extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int warmup, int repeats, abpoa_gpu_replay_t *out) {
+    memset(out, 0, sizeof *out);
+    if (e->captured.empty()) return -1;
+    if (cudaSetDevice(e->dev) != cudaSuccess) return -1;
+    /* similar-sized jobs next to each other: a launch finishes when its longest job does */
+    std::vector<CapturedJob> jobs = e->captured;
+    std::stable_sort(jobs.begin(), jobs.end(), [](const CapturedJob &a, const CapturedJob &b) {
+        if (a.bits != b.bits) return a.bits < b.bits;
+        return a.cells > b.cells; });
+    size_t total = 0; std::vector<size_t> off(jobs.size());
+    for (size_t t = 0; t < jobs.size(); ++t) { off[t] = total; total += (jobs[t].bytes + 255) & ~(size_t)255; }
+    uint8_t *d_blobs = NULL;
+    if (cudaMalloc((void **)&d_blobs, total) != cudaSuccess) poa_die(__func__, "cannot place %zu bytes of captured jobs in HBM", total);
+    for (size_t t = 0; t < jobs.size(); ++t)
+        if (cudaMemcpy(d_blobs + off[t], jobs[t].blob, jobs[t].bytes, cudaMemcpyHostToDevice) != cudaSuccess) poa_die(__func__, "upload failed");
+    out->input_bytes = total; out->n_jobs = (int64_t)jobs.size();
+    for (const CapturedJob &c : jobs) {
+        out->cells += c.cells; out->rows += c.n_rows - 1; out->preds += c.n_pred;
+        if (c.bits == 16) { out->jobs16 += 1; out->cells16 += c.cells; }
+    }
+    /* waves: as many jobs per launch as a quarter of the plane arena holds (same width only) */
+    const size_t wave_bytes = poa_arena_capacity(e->arena) / 2;
+    const int P = abpt->gap_mode == ABPOA_LINEAR_GAP ? 1 : (abpt->gap_mode == ABPOA_AFFINE_GAP ? 3 : 5);
+    std::vector<std::pair<size_t, size_t>> waves;
+    for (size_t pos = 0; pos < jobs.size();) {
+        size_t end = pos, bytes = 0;
+        while (end < jobs.size() && jobs[end].bits == jobs[pos].bits && end - pos < 4096) {
+            const size_t per_row = jobs[end].w >= 0 ? (size_t)((2 * jobs[end].w + 1 + 32 + 7) / 8 + 2) : (size_t)((jobs[end].qlen + 8) / 8 + 1);
+            const size_t b = per_row * P * (size_t)jobs[end].n_rows * 8 * (jobs[end].bits / 8);
+            if (end > pos && bytes + b > wave_bytes) break;
+            bytes += b; ++end;
+        }
+        waves.push_back({pos, end}); pos = end;
+    }
+    poa_dev_ctx *c = e->ctx[0];
+    std::vector<poa_replay_job> rj; std::vector<int32_t> sc, no; std::vector<int64_t> ce;
+    double sum_ms = 0, min_ms = 1e30;
+    for (int rep = 0; rep < warmup + repeats; ++rep) {
+        double ms = 0; int64_t mism = 0;
+        for (auto &wv : waves) {
+            const size_t n = wv.second - wv.first;
+            rj.resize(n); sc.resize(n); no.resize(n); ce.resize(n);
+            for (size_t t = 0; t < n; ++t) { const CapturedJob &cj = jobs[wv.first + t]; rj[t].d_blob = d_blobs + off[wv.first + t]; rj[t].n_rows = cj.n_rows; rj[t].qlen = cj.qlen; rj[t].w = cj.w; }
+            ms += poa_dev_ctx_replay_launch(c, abpt, rj.data(), (int)n, jobs[wv.first].bits, sc.data(), no.data(), ce.data());
+            for (size_t t = 0; t < n; ++t) { const CapturedJob &cj = jobs[wv.first + t]; if (sc[t] != cj.best_score || no[t] != cj.n_ops || ce[t] != cj.cells) ++mism; }
+        }
+        if (rep >= warmup) { sum_ms += ms; if (ms < min_ms) min_ms = ms; out->mismatches += mism; }
+    }
+    out->kernel_ms = sum_ms / (repeats > 0 ? repeats : 1); out->kernel_ms_min = min_ms; out->launches = (int64_t)waves.size();
+    cudaFree(d_blobs);
+    return 0;
+}
+
 extern "C" void abpoa_gpu_batch_free(abpoa_gpu_batch_t *e) {
     if (!e) return;
+    abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_free(c);
     poa_arena_destroy(e->arena);
     delete e;
@@ -108,6 +181,8 @@ extern "C" void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r) {
     free(r->read_best_score); free(r->read_n_cigar); free(r->read_cigar_hash);
     memset(r, 0, sizeof *r);
 }
+
+extern "C" { extern __thread double poa_prof_ms[8]; }
 
 namespace {
 
@@ -303,7 +378,7 @@ void worker_main(Worker wk) {
                     s.out->read_n_cigar[r] = pend[t].res.n_cigar;
                     s.out->read_cigar_hash[r] = fnv1a(pend[t].res.graph_cigar, pend[t].res.n_cigar);
                 }
-                abpoa_add_graph_alignment(s.ab, abpt, q, w, qlen, NULL, pend[t].res, r, s.in->n_seq, 1);
+                poa_add_alignment_nosync(s.ab, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, q, w, qlen, NULL, pend[t].res, r, s.in->n_seq, 1);
                 if (pend[t].res.n_cigar) free(pend[t].res.graph_cigar);
                 free(rc_seq[t]); free(rc_w[t]);
             }
@@ -320,6 +395,8 @@ void worker_main(Worker wk) {
     for (abpoa_t *ab : handles) abpoa_free(ab);
     if (prof) {
         const poa_engine_stats *st = poa_dev_ctx_stats(wk.ctx);
+        fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f span %.0f ms\n",
+                poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3], poa_prof_ms[4]);
         fprintf(stderr, "[worker] setup %.0f plan %.0f run %.0f (kernel %.0f, fill %.0f, wait %.0f, copy %.0f) fuse %.0f finish %.0f ms\n",
                 pc.setup, pc.plan, pc.run, st->kernel_ms, st->fill_ms, st->wait_ms, st->copy_ms, pc.fuse, pc.finish);
     }
@@ -333,6 +410,8 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     if (!((abpt->disable_seeding && abpt->progressive_poa == 0) || abpt->align_mode != ABPOA_GLOBAL_MODE))
         poa_die(__func__, "minimizer seeding / guide-tree partitioning (-S / -p) is outside the scope of the B200 hot-path library.");
     const auto t0 = std::chrono::steady_clock::now();
+    if (flags & ABPOA_GPU_CAPTURE_JOBS) abpoa_gpu_capture_clear(e);
+    for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_set_capture(c, (flags & ABPOA_GPU_CAPTURE_JOBS) ? capture_cb : NULL, e);
     std::atomic<int> next_chunk(0);
     const int n_chunks = (n_groups + e->groups_per_launch - 1) / e->groups_per_launch;
     const int nw = e->n_workers < n_chunks ? e->n_workers : n_chunks;

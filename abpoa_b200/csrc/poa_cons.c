@@ -105,6 +105,7 @@ static void heaviest_bundling(abpoa_graph_t *abg, abpoa_cons_t *abc) {
 
 void abpoa_generate_consensus(abpoa_t *ab, abpoa_para_t *abpt) {
     abpoa_graph_t *abg = ab->abg;
+    poa_graph_sync_public(abg);
     if (abg->is_called_cons == 1 || abg->node_n <= 2) return;
     if (abpt->max_n_cons > 1) poa_die(__func__, "multi-consensus clustering (max_n_cons > 1) is outside the scope of the B200 hot-path library.");
     if (abpt->cons_algrm != ABPOA_HB) poa_die(__func__, "most-frequent-base consensus is outside the scope of the B200 hot-path library.");
@@ -123,6 +124,7 @@ static int msa_column(const abpoa_graph_t *abg, int id) {
 
 void abpoa_generate_rc_msa(abpoa_t *ab, abpoa_para_t *abpt) {
     abpoa_graph_t *abg = ab->abg;
+    poa_graph_sync_public(abg);
     if (abg->node_n <= 2) return;
     poa_set_msa_rank(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
     if (abpt->out_cons) abpoa_generate_consensus(ab, abpt);
@@ -210,6 +212,7 @@ void abpoa_dump_pog(abpoa_t *ab, abpoa_para_t *abpt) {
 }
 
 void abpoa_output(abpoa_t *ab, abpoa_para_t *abpt, FILE *out_fp) {
+    poa_graph_sync_public(ab->abg);
     if (abpt->out_gfa) abpoa_generate_gfa(ab, abpt, out_fp);
     else {
         if (abpt->out_msa) abpoa_generate_rc_msa(ab, abpt);

@@ -84,11 +84,12 @@ struct poa_dev_ctx {
     int dev;
     poa_arena *arena;
     cudaStream_t st;
-    cudaEvent_t ev_k0, ev_k1;
+    cudaEvent_t ev_k0, ev_k1, ev_done;       /* ev_done: blocking-sync event, the host thread sleeps while the GPU works */
     uint8_t *h_in, *h_out, *d_in, *d_work, *d_planes;
     size_t h_in_cap, h_out_cap, d_in_cap, d_work_cap, d_planes_cap;
     size_t planes_limit;              /* hard cap for the plane slab (bytes); 0 = ask the device */
     poa_engine_stats stats;
+    poa_capture_fn capture; void *capture_user;
     PoaJobDesc last_desc; int last_bits, last_gap, last_rows;   /* debug: job 0 of the most recent launch */
 };
 
@@ -107,6 +108,7 @@ poa_dev_ctx *poa_dev_ctx_new_on(int dev) {
     else CK(cudaGetDevice(&c->dev));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_k0)); CK(cudaEventCreate(&c->ev_k1));
+    CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
     return c;
 }
 
@@ -115,6 +117,7 @@ poa_dev_ctx *poa_dev_ctx_new(void) {
     return poa_dev_ctx_new_on(env && *env ? atoi(env) : -1);
 }
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a) { c->arena = a; }
+void poa_dev_ctx_set_capture(poa_dev_ctx *c, poa_capture_fn fn, void *user) { c->capture = fn; c->capture_user = user; }
 
 void poa_dev_ctx_free(poa_dev_ctx *c) {
     if (!c) return;
@@ -125,7 +128,7 @@ void poa_dev_ctx_free(poa_dev_ctx *c) {
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_work) cudaFree(c->d_work);
     if (c->d_planes) cudaFree(c->d_planes);
-    cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
+    cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); cudaEventDestroy(c->ev_done);
     cudaStreamDestroy(c->st);
     free(c);
 }
@@ -134,6 +137,12 @@ void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes) { c->planes_limi
 const poa_engine_stats *poa_dev_ctx_stats(const poa_dev_ctx *c) { return &c->stats; }
 void poa_dev_ctx_reset_stats(poa_dev_ctx *c) { memset(&c->stats, 0, sizeof c->stats); }
 int poa_dev_ctx_device(const poa_dev_ctx *c) { return c->dev; }
+
+/* wait for everything queued on the context's stream without spinning on a core */
+static void stream_wait(poa_dev_ctx *c) {
+    CK(cudaEventRecord(c->ev_done, c->st));
+    CK(cudaEventSynchronize(c->ev_done));
+}
 
 static void grow_host(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return;
@@ -265,7 +274,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     size_t out_bytes = al256((size_t)n * sizeof(PoaResultDev));
     grow_host(&c->h_out, &c->h_out_cap, out_bytes);
     CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    stream_wait(c);
     const double t_waited = now_ms();
     if (c->arena) arena_give(c->arena, planes_base, plane_bytes);      /* the backtrace is done: planes are dead */
     float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
@@ -287,7 +296,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         if (j.want_bands)
             CK(cudaMemcpyAsync(c->h_out + out_band[t], c->d_work + work_off[t], (size_t)j.plan.n_rows * sizeof(PoaRowInfo), cudaMemcpyDeviceToHost, c->st));
     }
-    CK(cudaStreamSynchronize(c->st));
+    stream_wait(c);
     c->stats.d2h_bytes += out_bytes;
     c->stats.fill_ms += t_filled - t_begin; c->stats.wait_ms += t_waited - t_filled; c->stats.copy_ms += now_ms() - t_waited;
     for (int t = 0; t < n; ++t) {
@@ -300,6 +309,13 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         j.n_ops = resv[t].status == POA_ST_OK ? resv[t].n_ops : 0;
         j.ops = (const uint64_t *)(c->h_out + out_cig[t]);
         j.bands = j.want_bands ? (const int32_t *)(c->h_out + out_band[t]) : NULL;
+        if (c->capture && resv[t].status == POA_ST_OK) {
+            poa_captured_job cj;
+            cj.blob = c->h_in + blob_off[t]; cj.bytes = j.plan.bytes; cj.n_rows = j.plan.n_rows; cj.qlen = j.plan.qlen; cj.w = j.plan.w;
+            cj.n_pred = ((const int32_t *)(cj.blob + ((const PoaJobHeader *)cj.blob)->off_predoff))[j.plan.n_rows];
+            cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells;
+            c->capture(c->capture_user, &cj);
+        }
         if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; }
     }
 }
@@ -424,4 +440,69 @@ extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, 
             out[(size_t)p * cap + (j - ri.beg)] = S == 2 ? (int32_t)((int16_t *)buf.data())[k] : ((int32_t *)buf.data())[k];
         }
     return P;
+}
+
+/* ------------------------------------------------------------------ replay of HBM-resident jobs
+ * One launch over `n` jobs whose blobs already live in device memory.  Only descriptors are
+ * uploaded (outside the timed region); returns the CUDA-event time of the kernel in ms. */
+double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const poa_replay_job *rj, int n, int bits,
+                                 int32_t *out_score, int32_t *out_nops, int64_t *out_cells) {
+    CK(cudaSetDevice(c->dev));
+    const int S = bits / 8;
+    const size_t off_desc = al256(sizeof(PoaParamsDev));
+    const size_t in_bytes = off_desc + al256((size_t)n * sizeof(PoaJobDesc));
+    size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
+    std::vector<size_t> work_off(n), cig_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    uint64_t tot_units = 0; int band_cells = 0;
+    for (int t = 0; t < n; ++t) {
+        work_off[t] = work_bytes;
+        work_bytes += al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)) + al256((size_t)rj[t].n_rows * 4);
+        cig_off[t] = work_bytes;
+        work_bytes += al256((size_t)(rj[t].qlen + rj[t].n_rows + 8) * 8);
+        poa_job tmp; memset(&tmp, 0, sizeof tmp); tmp.plan.n_rows = rj[t].n_rows; tmp.plan.qlen = rj[t].qlen; tmp.plan.w = rj[t].w;
+        units[t] = plane_units_for(&tmp, abpt->gap_mode, 0);
+        plane_off[t] = tot_units; tot_units += units[t];
+        const int bc = rj[t].w >= 0 ? (2 * rj[t].w + 1 + 40 + 7) / 8 * 8 : (rj[t].qlen + 1 + 7) / 8 * 8 + 8;
+        if (bc > band_cells) band_cells = bc;
+    }
+    const size_t plane_bytes = (size_t)tot_units * POA_GROUP * S;
+    grow_host(&c->h_in, &c->h_in_cap, in_bytes);
+    grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
+    grow_dev(&c->d_work, &c->d_work_cap, work_bytes, 1);
+    uint8_t *planes_base;
+    if (c->arena) planes_base = arena_take(c->arena, plane_bytes);
+    else { grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, 1); planes_base = c->d_planes; }
+    poa_fill_params((PoaParamsDev *)c->h_in, abpt, bits);
+    PoaJobDesc *desc = (PoaJobDesc *)(c->h_in + off_desc);
+    for (int t = 0; t < n; ++t) {
+        desc[t].blob = rj[t].d_blob;
+        desc[t].planes = planes_base + (size_t)plane_off[t] * POA_GROUP * S;
+        desc[t].plane_cap_units = units[t];
+        desc[t].rowinfo = (PoaRowInfo *)(c->d_work + work_off[t]);
+        desc[t].rowoff = (uint32_t *)(c->d_work + work_off[t] + al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)));
+        desc[t].cigar = (uint64_t *)(c->d_work + cig_off[t]);
+        desc[t].cigar_cap = rj[t].qlen + rj[t].n_rows + 8;
+        desc[t].pad = 0;
+        desc[t].result = (PoaResultDev *)c->d_work + t;
+    }
+    static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
+    int ring_rows = 2, ring_cells = 64;
+    poa_pick_ring(abpt->gap_mode, bits, band_cells, smem_budget, &ring_rows, &ring_cells);
+    CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaEventRecord(c->ev_k0, c->st));
+    CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                        (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    CK(cudaEventRecord(c->ev_k1, c->st));
+    grow_host(&c->h_out, &c->h_out_cap, (size_t)n * sizeof(PoaResultDev));
+    CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (c->arena) arena_give(c->arena, planes_base, plane_bytes);
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
+    const PoaResultDev *r = (const PoaResultDev *)c->h_out;
+    for (int t = 0; t < n; ++t) {
+        out_score[t] = r[t].status == POA_ST_OK ? r[t].best_score : INT32_MIN;
+        out_nops[t] = r[t].n_ops; out_cells[t] = r[t].cells;
+    }
+    return (double)ms;
 }

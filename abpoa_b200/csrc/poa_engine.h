@@ -26,6 +26,14 @@ typedef struct {
 
 typedef void (*poa_job_sink)(void *user, poa_job *job);
 
+/* a captured job: the exact bytes that were sent to the device, plus what came back */
+typedef struct {
+    uint8_t *blob; size_t bytes;
+    int n_rows, qlen, w, n_pred, bits;
+    int best_score, n_ops; int64_t cells;
+} poa_captured_job;
+typedef void (*poa_capture_fn)(void *user, const poa_captured_job *cj);
+
 typedef struct {
     double kernel_ms;               /* CUDA-event time of the alignment kernels               */
     int64_t cells, alignments, launches, retries;
@@ -42,6 +50,11 @@ void poa_arena_destroy(poa_arena *a);
 size_t poa_arena_capacity(const poa_arena *a);
 poa_dev_ctx *poa_dev_ctx_new_on(int dev);
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a);
+void poa_dev_ctx_set_capture(poa_dev_ctx *c, poa_capture_fn fn, void *user);
+/* replay support: run pre-uploaded blobs (device pointers) as one launch on the context's stream */
+typedef struct { const uint8_t *d_blob; int n_rows, qlen, w; } poa_replay_job;
+double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const poa_replay_job *jobs, int n, int bits,
+                                 int32_t *out_score, int32_t *out_nops, int64_t *out_cells);
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint);
 
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);

@@ -33,7 +33,8 @@ void poa_blob_plan_make(poa_blob_plan *pl, const abpoa_graph_t *abg, const abpoa
     pl->with_remain = (abpt->wb >= 0 || abpt->zdrop > 0);
     pl->with_score = abpt->inc_path_score ? 1 : 0;
     int n_pred = 0;
-    for (int r = 1; r < pl->n_rows; ++r) n_pred += abg->node[abg->index_to_node_id[beg_index + r]].in_edge_n;
+    if (pl->whole_graph) n_pred = (int)poa_graph_edge_count(abg);          /* every in-edge exactly once */
+    else { const int *cin = poa_graph_in_degrees(abg); for (int r = 1; r < pl->n_rows; ++r) n_pred += cin[abg->index_to_node_id[beg_index + r]]; }
     pl->n_pred_max = n_pred;
     const size_t nr = (size_t)pl->n_rows;
     size_t b = al16(sizeof(struct PoaJobHeader));
@@ -92,16 +93,18 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
         }
     }
     const int end_remain = remain ? abg->node_id_to_max_remain[end_node_id] : 0;
+    const uint8_t *cbase = poa_graph_bases(abg); const int *cin = poa_graph_in_degrees(abg);
+    const int *id_of_index = abg->index_to_node_id + beg_index, *index_of_id = abg->node_id_to_index, *max_remain = abg->node_id_to_max_remain;
     int np = 0;
     predoff[0] = 0;
     for (int r = 0; r < n_rows; ++r) {
-        const int id = abg->index_to_node_id[beg_index + r];
-        const abpoa_node_t *nd = &abg->node[id];
-        nodeid[r] = id; base[r] = nd->base;
-        if (remain) remain[r] = abg->node_id_to_max_remain[id] - end_remain - 1;
+        const int id = id_of_index[r];
+        nodeid[r] = id; base[r] = cbase[id];
+        if (remain) remain[r] = max_remain[id] - end_remain - 1;
         if (r > 0) {
-            for (int e = 0; e < nd->in_edge_n; ++e) {
-                const int pr = abg->node_id_to_index[nd->in_id[e]] - beg_index;
+            const int ni = cin[id]; const int *iid = poa_graph_in_ids(abg, id);
+            for (int e = 0; e < ni; ++e) {
+                const int pr = index_of_id[iid[e]] - beg_index;
                 if (pr < 0 || pr >= n_rows) continue;
                 if (live && !live[pr]) continue;
                 if (pscore) pscore[np] = poa_edge_path_score(abg, id, e);

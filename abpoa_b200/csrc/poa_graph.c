@@ -21,16 +21,41 @@
  * (degree counters, BFS queue) lives in a private tail of the graph object instead.
  */
 #include <math.h>
+#include <time.h>
 #include "poa_internal.h"
+
+/* optional per-thread phase timers (ABPOA_GPU_PROFILE): where does host graph time go */
+__thread double poa_prof_ms[8];
+static inline double prof_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
+#define POA_INL 4                 /* inline edge slots per node and direction */
 
 typedef struct {
     abpoa_graph_t pub;          /* must stay first: callers hold &pub */
     int *deg;                   /* degree counters for the Kahn passes */
     int *queue;                 /* BFS queue / DFS stack storage        */
     int scratch_m;
+    /* Compact, node-id-indexed mirror of what the per-read passes (two Kahn traversals, edge
+     * ordering, flattening for the device) read.  abpoa_node_t is 120 B with separately
+     * malloc'ed edge arrays; walking 25 k of those per read is cache-miss bound.  Here the edge
+     * lists of nodes with <= POA_INL edges per direction LIVE in four dense slabs (the ABI
+     * pointers node[].in_id etc. point into them; capacity field == POA_INL), and degrees /
+     * residues / aligned-set sizes are mirrored in dense arrays, so a pass touches ~40 B per node. */
+    int slab_m;
+    int *in_id4, *in_w4, *out_id4, *out_w4;     /* [slab_m][POA_INL] */
+    int *cin, *cout;                            /* == node[].in_edge_n / out_edge_n */
+    int *caln;                                  /* == node[].aligned_node_n          */
+    uint8_t *cbase;                             /* == node[].base                    */
+    int *cnread, *cspan;                        /* AUTHORITATIVE n_read / n_span_read while public_stale is set */
+    int span_pending;                           /* whole-graph "+1 span read on every node" not yet folded into cspan */
+    int public_stale;                           /* node[].n_read / n_span_read lag behind the dense arrays */
+    int has_read_ids;                           /* some out-edge carries a read-id bitset */
+    int *touched; int n_touched, touched_m; uint8_t *touch_mark;   /* nodes whose edge lists changed since the last ordering */
+    int64_t n_edges;                            /* total in-edges in the graph        */
 } poa_graph_x;
 
 static inline poa_graph_x *gx(abpoa_graph_t *abg) { return (poa_graph_x *)abg; }
+static inline const poa_graph_x *cgx(const abpoa_graph_t *abg) { return (const poa_graph_x *)abg; }
 
 static void scratch_reserve(abpoa_graph_t *abg, int n) {
     poa_graph_x *x = gx(abg);
@@ -48,25 +73,55 @@ static void node_blank(abpoa_node_t *nd, int id) {
 }
 
 static void node_release(abpoa_node_t *nd) {
-    if (nd->in_edge_m > 0) { free(nd->in_id); free(nd->in_edge_weight); }
-    if (nd->out_edge_m > 0) {
-        free(nd->out_id); free(nd->out_edge_weight);
-        if (nd->read_ids) {
-            if (nd->read_ids_n > 0)
-                for (int j = 0; j < nd->out_edge_m; ++j) free(nd->read_ids[j]);
-            free(nd->read_ids);
-        }
+    if (nd->in_edge_m > POA_INL) { free(nd->in_id); free(nd->in_edge_weight); }
+    if (nd->out_edge_m > POA_INL) { free(nd->out_id); free(nd->out_edge_weight); }
+    if (nd->read_ids) {
+        if (nd->read_ids_n > 0)
+            for (int j = 0; j < nd->out_edge_m; ++j) free(nd->read_ids[j]);
+        free(nd->read_ids);
     }
     if (nd->m_read > 0) free(nd->read_weight);
     if (nd->aligned_node_m > 0) free(nd->aligned_node_id);
 }
 
+/* grow the node array and the mirror; inline edge pointers are re-aimed at the moved slabs */
 static void nodes_reserve(abpoa_graph_t *abg, int want) {
     if (want <= abg->node_m) return;
-    int m = poa_roundup32(want);
+    poa_graph_x *x = gx(abg);
+    const int old = abg->node_m, m = poa_roundup32(want);
     abg->node = (abpoa_node_t *)poa_xrealloc(abg->node, (size_t)m * sizeof(abpoa_node_t));
-    for (int i = abg->node_m; i < m; ++i) node_blank(&abg->node[i], i);
+    for (int i = old; i < m; ++i) node_blank(&abg->node[i], i);
     abg->node_m = m;
+    x->in_id4 = (int *)poa_xrealloc(x->in_id4, (size_t)m * POA_INL * sizeof(int));
+    x->in_w4 = (int *)poa_xrealloc(x->in_w4, (size_t)m * POA_INL * sizeof(int));
+    x->out_id4 = (int *)poa_xrealloc(x->out_id4, (size_t)m * POA_INL * sizeof(int));
+    x->out_w4 = (int *)poa_xrealloc(x->out_w4, (size_t)m * POA_INL * sizeof(int));
+    x->cin = (int *)poa_xrealloc(x->cin, (size_t)m * sizeof(int));
+    x->cout = (int *)poa_xrealloc(x->cout, (size_t)m * sizeof(int));
+    x->caln = (int *)poa_xrealloc(x->caln, (size_t)m * sizeof(int));
+    x->cbase = (uint8_t *)poa_xrealloc(x->cbase, (size_t)m);
+    x->cnread = (int *)poa_xrealloc(x->cnread, (size_t)m * sizeof(int)); x->cspan = (int *)poa_xrealloc(x->cspan, (size_t)m * sizeof(int));
+    memset(x->cnread + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cspan + old, 0, (size_t)(m - old) * sizeof(int));
+    x->touch_mark = (uint8_t *)poa_xrealloc(x->touch_mark, (size_t)m);
+    memset(x->cin + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cout + old, 0, (size_t)(m - old) * sizeof(int));
+    memset(x->caln + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cbase + old, 0, (size_t)(m - old));
+    memset(x->touch_mark + old, 0, (size_t)(m - old));
+    x->slab_m = m;
+    for (int i = 0; i < old; ++i) {
+        abpoa_node_t *nd = &abg->node[i];
+        if (nd->in_edge_m == POA_INL) { nd->in_id = x->in_id4 + (size_t)i * POA_INL; nd->in_edge_weight = x->in_w4 + (size_t)i * POA_INL; }
+        if (nd->out_edge_m == POA_INL) { nd->out_id = x->out_id4 + (size_t)i * POA_INL; nd->out_edge_weight = x->out_w4 + (size_t)i * POA_INL; }
+    }
+}
+
+static inline void touch(poa_graph_x *x, int id) {
+    if (x->touch_mark[id]) return;
+    x->touch_mark[id] = 1;
+    if (x->n_touched == x->touched_m) {
+        x->touched_m = x->touched_m ? x->touched_m << 1 : 1024;
+        x->touched = (int *)poa_xrealloc(x->touched, (size_t)x->touched_m * sizeof(int));
+    }
+    x->touched[x->n_touched++] = id;
 }
 
 abpoa_graph_t *poa_graph_new(void) {
@@ -86,6 +141,8 @@ void poa_graph_free(abpoa_graph_t *abg) {
     free(abg->index_to_node_id); free(abg->node_id_to_index); free(abg->node_id_to_msa_rank);
     free(abg->node_id_to_max_pos_left); free(abg->node_id_to_max_pos_right); free(abg->node_id_to_max_remain);
     free(x->deg); free(x->queue);
+    free(x->in_id4); free(x->in_w4); free(x->out_id4); free(x->out_w4);
+    free(x->cin); free(x->cout); free(x->caln); free(x->cbase); free(x->cnread); free(x->cspan); free(x->touched); free(x->touch_mark);
     free(x);
 }
 
@@ -176,6 +233,15 @@ void abpoa_reset(abpoa_t *ab, abpoa_para_t *abpt, int qlen) {
         nd->in_edge_n = nd->out_edge_n = nd->aligned_node_n = 0;
         nd->n_read = nd->n_span_read = 0;
     }
+    {
+        poa_graph_x *x = gx(abg);
+        memset(x->cin, 0, (size_t)abg->node_n * sizeof(int)); memset(x->cout, 0, (size_t)abg->node_n * sizeof(int));
+        memset(x->caln, 0, (size_t)abg->node_n * sizeof(int));
+        memset(x->cnread, 0, (size_t)abg->node_n * sizeof(int)); memset(x->cspan, 0, (size_t)abg->node_n * sizeof(int));
+        x->span_pending = 0; x->public_stale = 0; x->has_read_ids = 0;
+        for (int t = 0; t < x->n_touched; ++t) x->touch_mark[x->touched[t]] = 0;
+        x->n_touched = 0; x->n_edges = 0;
+    }
     abg->node_n = 2;
     nodes_reserve(abg, qlen + 2);
     index_arrays_reserve(abg, abpt, abg->node_m);
@@ -184,19 +250,36 @@ void abpoa_reset(abpoa_t *ab, abpoa_para_t *abpt, int qlen) {
 }
 
 /* ------------------------------------------------------------------ edges */
-static void in_edges_reserve(abpoa_node_t *nd, int want) {
+/* edge storage: the first POA_INL edges live inline in the slabs, more spill to the heap */
+static void in_edges_reserve(poa_graph_x *x, int id, int want) {
+    abpoa_node_t *nd = &x->pub.node[id];
     if (want <= nd->in_edge_m) return;
-    int m = POA_MAX(2, poa_roundup32(want));
-    nd->in_id = (int *)(nd->in_edge_m ? poa_xrealloc(nd->in_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
-    nd->in_edge_weight = (int *)(nd->in_edge_m ? poa_xrealloc(nd->in_edge_weight, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
-    nd->in_edge_m = m;
+    if (want <= POA_INL) {
+        nd->in_id = x->in_id4 + (size_t)id * POA_INL; nd->in_edge_weight = x->in_w4 + (size_t)id * POA_INL; nd->in_edge_m = POA_INL;
+        return;
+    }
+    const int m = poa_roundup32(want);
+    int *ids = (int *)poa_xmalloc((size_t)m * sizeof(int)), *ws = (int *)poa_xmalloc((size_t)m * sizeof(int));
+    memcpy(ids, nd->in_id, (size_t)nd->in_edge_n * sizeof(int)); memcpy(ws, nd->in_edge_weight, (size_t)nd->in_edge_n * sizeof(int));
+    if (nd->in_edge_m > POA_INL) { free(nd->in_id); free(nd->in_edge_weight); }
+    nd->in_id = ids; nd->in_edge_weight = ws; nd->in_edge_m = m;
 }
 
-static void out_edges_reserve(abpoa_node_t *nd, int want, int want_read_ids) {
+static void out_edges_reserve(poa_graph_x *x, int id, int want, int want_read_ids) {
+    abpoa_node_t *nd = &x->pub.node[id];
     if (want > nd->out_edge_m) {
-        int old = nd->out_edge_m, m = POA_MAX(2, poa_roundup32(want));
-        nd->out_id = (int *)(old ? poa_xrealloc(nd->out_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
-        nd->out_edge_weight = (int *)(old ? poa_xrealloc(nd->out_edge_weight, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
+        const int old = nd->out_edge_m;
+        int m;
+        if (want <= POA_INL) {
+            m = POA_INL;
+            nd->out_id = x->out_id4 + (size_t)id * POA_INL; nd->out_edge_weight = x->out_w4 + (size_t)id * POA_INL;
+        } else {
+            m = poa_roundup32(want);
+            int *ids = (int *)poa_xmalloc((size_t)m * sizeof(int)), *ws = (int *)poa_xmalloc((size_t)m * sizeof(int));
+            memcpy(ids, nd->out_id, (size_t)nd->out_edge_n * sizeof(int)); memcpy(ws, nd->out_edge_weight, (size_t)nd->out_edge_n * sizeof(int));
+            if (old > POA_INL) { free(nd->out_id); free(nd->out_edge_weight); }
+            nd->out_id = ids; nd->out_edge_weight = ws;
+        }
         if (nd->read_ids) {
             nd->read_ids = (uint64_t **)poa_xrealloc(nd->read_ids, (size_t)m * sizeof(uint64_t *));
             for (int j = old; j < m; ++j)
@@ -225,36 +308,72 @@ int abpoa_add_graph_node(abpoa_graph_t *abg, uint8_t base) {
     int id = abg->node_n;
     nodes_reserve(abg, id + 1);
     abg->node[id].base = base;
+    gx(abg)->cbase[id] = base;
     abg->node_n = id + 1;
     return id;
 }
 
+/* Fold the dense n_read / n_span_read counters back into the ABI node structs.  The per-read
+ * fusion loop only updates the dense arrays (it would otherwise drag every 120-byte node of
+ * the path through the cache once more); every PUBLIC entry point that finishes a mutation,
+ * and everything that reads the counters, calls this first. */
+void poa_graph_sync_public(abpoa_graph_t *abg) {
+    poa_graph_x *x = gx(abg);
+    if (!x->public_stale && !x->span_pending) return;
+    const int n = abg->node_n, add = x->span_pending;
+    for (int i = 0; i < n; ++i) {
+        x->cspan[i] += add;
+        abg->node[i].n_read = x->cnread[i]; abg->node[i].n_span_read = x->cspan[i];
+    }
+    x->span_pending = 0; x->public_stale = 0;
+}
+
+static int edge_add(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, int w, uint8_t add_read_id,
+                    uint8_t add_read_weight, int read_id, int read_ids_n, int tot_read_n);
+
 int abpoa_add_graph_edge(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, int w, uint8_t add_read_id,
                          uint8_t add_read_weight, int read_id, int read_ids_n, int tot_read_n) {
+    const int r = edge_add(abg, from_id, to_id, check_edge, w, add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+    abg->node[from_id].n_read = gx(abg)->cnread[from_id];
+    return r;
+}
+
+static int edge_add(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, int w, uint8_t add_read_id,
+                    uint8_t add_read_weight, int read_id, int read_ids_n, int tot_read_n) {
     if (from_id < 0 || from_id >= abg->node_n || to_id < 0 || to_id >= abg->node_n)
         poa_die(__func__, "node_n: %d\tfrom_id: %d\tto_id: %d.", abg->node_n, from_id, to_id);
+    poa_graph_x *x = gx(abg);
     abpoa_node_t *from = &abg->node[from_id], *to = &abg->node[to_id];
     int slot = -1;
     if (check_edge) {            /* the edge may exist already: bump both copies of its weight */
-        for (int i = 0; i < to->in_edge_n; ++i)
-            if (to->in_id[i] == from_id) { to->in_edge_weight[i] += w; break; }
-        for (int i = 0; i < from->out_edge_n; ++i)
-            if (from->out_id[i] == to_id) { from->out_edge_weight[i] += w; slot = i; break; }
+        /* degrees and inline edge lists come from the dense mirror: no 120-byte node structs touched */
+        const int nin = x->cin[to_id], nout = x->cout[from_id];
+        int *iid = nin <= POA_INL ? x->in_id4 + (size_t)to_id * POA_INL : to->in_id;
+        int *iw = nin <= POA_INL ? x->in_w4 + (size_t)to_id * POA_INL : to->in_edge_weight;
+        int *oid = nout <= POA_INL ? x->out_id4 + (size_t)from_id * POA_INL : from->out_id;
+        int *ow = nout <= POA_INL ? x->out_w4 + (size_t)from_id * POA_INL : from->out_edge_weight;
+        for (int i = 0; i < nin; ++i)
+            if (iid[i] == from_id) { iw[i] += w; break; }
+        for (int i = 0; i < nout; ++i)
+            if (oid[i] == to_id) { ow[i] += w; slot = i; break; }
     }
     if (slot < 0) {              /* new edge, appended after the existing ones */
-        in_edges_reserve(to, to->in_edge_n + 1);
-        to->in_id[to->in_edge_n] = from_id; to->in_edge_weight[to->in_edge_n] = w; ++to->in_edge_n;
-        out_edges_reserve(from, from->out_edge_n + 1, add_read_id);
+        in_edges_reserve(x, to_id, to->in_edge_n + 1);
+        to->in_id[to->in_edge_n] = from_id; to->in_edge_weight[to->in_edge_n] = w; x->cin[to_id] = ++to->in_edge_n;
+        out_edges_reserve(x, from_id, from->out_edge_n + 1, add_read_id);
         slot = from->out_edge_n;
-        from->out_id[slot] = to_id; from->out_edge_weight[slot] = w; ++from->out_edge_n;
+        from->out_id[slot] = to_id; from->out_edge_weight[slot] = w; x->cout[from_id] = ++from->out_edge_n;
+        x->n_edges += 1;
     }
+    touch(x, from_id); touch(x, to_id);
     if (add_read_id) {           /* which reads run through this edge: feeds the RC-MSA */
         if (read_ids_n <= 0) poa_die(__func__, "Unexpected read_ids_n: %d.", read_ids_n);
-        out_edges_reserve(from, from->out_edge_n, 1);
+        out_edges_reserve(x, from_id, from->out_edge_n, 1);
         read_ids_widen(from, read_ids_n);
         from->read_ids[slot][read_id >> 6] |= 1ULL << (read_id & 63);
+        x->has_read_ids = 1;
     }
-    from->n_read += 1;
+    x->cnread[from_id] += 1; x->public_stale = 1;
     if (add_read_weight) {
         if (tot_read_n > from->m_read) {
             from->read_weight = (int *)poa_xrealloc(from->read_weight, (size_t)tot_read_n * sizeof(int));
@@ -277,20 +396,23 @@ static void aligned_push(abpoa_node_t *nd, int id) {
 }
 
 static void aligned_join(abpoa_graph_t *abg, int node_id, int new_id) {
-    abpoa_node_t *node = abg->node;
+    abpoa_node_t *node = abg->node; int *caln = gx(abg)->caln;
     for (int i = 0; i < node[node_id].aligned_node_n; ++i) {
         int sib = node[node_id].aligned_node_id[i];
-        aligned_push(&node[sib], new_id);
+        aligned_push(&node[sib], new_id); caln[sib] = node[sib].aligned_node_n;
         aligned_push(&node[new_id], sib);
     }
-    aligned_push(&node[node_id], new_id);
-    aligned_push(&node[new_id], node_id);
+    aligned_push(&node[node_id], new_id); caln[node_id] = node[node_id].aligned_node_n;
+    aligned_push(&node[new_id], node_id); caln[new_id] = node[new_id].aligned_node_n;
 }
 
 static int aligned_with_base(const abpoa_graph_t *abg, int node_id, uint8_t base) {
-    const abpoa_node_t *nd = &abg->node[node_id];
-    for (int i = 0; i < nd->aligned_node_n; ++i)
-        if (abg->node[nd->aligned_node_id[i]].base == base) return nd->aligned_node_id[i];
+    const poa_graph_x *x = cgx(abg);
+    const int na = x->caln[node_id];
+    if (na == 0) return -1;
+    const int *al = abg->node[node_id].aligned_node_id;
+    for (int i = 0; i < na; ++i)
+        if (x->cbase[al[i]] == base) return al[i];
     return -1;
 }
 
@@ -298,28 +420,39 @@ static int aligned_with_base(const abpoa_graph_t *abg, int node_id, uint8_t base
 /* Topological index = dequeue order of a FIFO Kahn traversal in which a node becomes
  * ready only together with all nodes of its aligned group; the group is enqueued as
  * (trigger node, then its aligned list in stored order). */
+/* edge list of node v in direction `out`: inline slab row or the heap spill */
+static inline const int *out_ids_of(const poa_graph_x *x, int v) { return x->cout[v] <= POA_INL ? x->out_id4 + (size_t)v * POA_INL : x->pub.node[v].out_id; }
+static inline const int *out_ws_of(const poa_graph_x *x, int v) { return x->cout[v] <= POA_INL ? x->out_w4 + (size_t)v * POA_INL : x->pub.node[v].out_edge_weight; }
+static inline const int *in_ids_of(const poa_graph_x *x, int v) { return x->cin[v] <= POA_INL ? x->in_id4 + (size_t)v * POA_INL : x->pub.node[v].in_id; }
+
 void abpoa_BFS_set_node_index(abpoa_graph_t *abg, int src_id, int sink_id) {
     const int n = abg->node_n;
     scratch_reserve(abg, n);
+    const poa_graph_x *x = gx(abg);
     int *deg = gx(abg)->deg, *q = gx(abg)->queue;
     const abpoa_node_t *node = abg->node;
-    for (int i = 0; i < n; ++i) deg[i] = node[i].in_edge_n;
+    memcpy(deg, x->cin, (size_t)n * sizeof(int));
+    int *index_to_node_id = abg->index_to_node_id, *node_id_to_index = abg->node_id_to_index;
     int head = 0, tail = 0, index = 0;
     q[tail++] = src_id;
     while (head < tail) {
-        int cur = q[head++];
-        abg->index_to_node_id[index] = cur;
-        abg->node_id_to_index[cur] = index++;
+        const int cur = q[head++];
+        index_to_node_id[index] = cur;
+        node_id_to_index[cur] = index++;
         if (cur == sink_id) return;
-        for (int e = 0; e < node[cur].out_edge_n; ++e) {
-            int v = node[cur].out_id[e];
+        const int ne = x->cout[cur]; const int *oid = out_ids_of(x, cur);
+        for (int e = 0; e < ne; ++e) {
+            const int v = oid[e];
             if (--deg[v] != 0) continue;
-            int ready = 1;
-            for (int a = 0; a < node[v].aligned_node_n; ++a)
-                if (deg[node[v].aligned_node_id[a]] != 0) { ready = 0; break; }
-            if (!ready) continue;
-            q[tail++] = v;
-            for (int a = 0; a < node[v].aligned_node_n; ++a) q[tail++] = node[v].aligned_node_id[a];
+            const int na = x->caln[v];
+            if (na) {                                   /* ready only together with its whole aligned group */
+                const int *al = node[v].aligned_node_id;
+                int ready = 1;
+                for (int a = 0; a < na; ++a) if (deg[al[a]] != 0) { ready = 0; break; }
+                if (!ready) continue;
+                q[tail++] = v;
+                for (int a = 0; a < na; ++a) q[tail++] = al[a];
+            } else q[tail++] = v;
         }
     }
     poa_die(__func__, "Failed to set node index.");
@@ -327,24 +460,44 @@ void abpoa_BFS_set_node_index(abpoa_graph_t *abg, int src_id, int sink_id) {
 
 /* Edge lists ordered by weight, heaviest first.  This is the DP's predecessor order and
  * the order every tie is broken in, so the permutation must be the one the reference's
- * in-place exchange pass produces (swap whenever w[j] < w[k], j < k; not stable). */
+ * in-place exchange pass produces (swap whenever w[j] < w[k], j < k; not stable).  The pass
+ * is idempotent (a list it produced is left unchanged), so only nodes whose lists changed
+ * since the previous ordering need it. */
+static void order_edges_of(abpoa_node_t *nd) {
+    for (int j = 0; j + 1 < nd->in_edge_n; ++j)
+        for (int k = j + 1; k < nd->in_edge_n; ++k)
+            if (nd->in_edge_weight[j] < nd->in_edge_weight[k]) {
+                int t = nd->in_id[j]; nd->in_id[j] = nd->in_id[k]; nd->in_id[k] = t;
+                t = nd->in_edge_weight[j]; nd->in_edge_weight[j] = nd->in_edge_weight[k]; nd->in_edge_weight[k] = t;
+            }
+    for (int j = 0; j + 1 < nd->out_edge_n; ++j)
+        for (int k = j + 1; k < nd->out_edge_n; ++k)
+            if (nd->out_edge_weight[j] < nd->out_edge_weight[k]) {
+                int t = nd->out_id[j]; nd->out_id[j] = nd->out_id[k]; nd->out_id[k] = t;
+                t = nd->out_edge_weight[j]; nd->out_edge_weight[j] = nd->out_edge_weight[k]; nd->out_edge_weight[k] = t;
+                if (nd->read_ids_n > 0) { uint64_t *r = nd->read_ids[j]; nd->read_ids[j] = nd->read_ids[k]; nd->read_ids[k] = r; }
+            }
+}
+
+static inline void exchange_order(int *ids, int *ws, int n) {
+    for (int j = 0; j + 1 < n; ++j)
+        for (int k = j + 1; k < n; ++k)
+            if (ws[j] < ws[k]) { int t = ids[j]; ids[j] = ids[k]; ids[k] = t; t = ws[j]; ws[j] = ws[k]; ws[k] = t; }
+}
+
 static void order_edges_by_weight(abpoa_graph_t *abg) {
-    for (int i = 0; i < abg->node_n; ++i) {
-        abpoa_node_t *nd = &abg->node[i];
-        for (int j = 0; j + 1 < nd->in_edge_n; ++j)
-            for (int k = j + 1; k < nd->in_edge_n; ++k)
-                if (nd->in_edge_weight[j] < nd->in_edge_weight[k]) {
-                    int t = nd->in_id[j]; nd->in_id[j] = nd->in_id[k]; nd->in_id[k] = t;
-                    t = nd->in_edge_weight[j]; nd->in_edge_weight[j] = nd->in_edge_weight[k]; nd->in_edge_weight[k] = t;
-                }
-        for (int j = 0; j + 1 < nd->out_edge_n; ++j)
-            for (int k = j + 1; k < nd->out_edge_n; ++k)
-                if (nd->out_edge_weight[j] < nd->out_edge_weight[k]) {
-                    int t = nd->out_id[j]; nd->out_id[j] = nd->out_id[k]; nd->out_id[k] = t;
-                    t = nd->out_edge_weight[j]; nd->out_edge_weight[j] = nd->out_edge_weight[k]; nd->out_edge_weight[k] = t;
-                    if (nd->read_ids_n > 0) { uint64_t *r = nd->read_ids[j]; nd->read_ids[j] = nd->read_ids[k]; nd->read_ids[k] = r; }
-                }
+    poa_graph_x *x = gx(abg);
+    for (int t = 0; t < x->n_touched; ++t) {
+        const int id = x->touched[t];
+        x->touch_mark[id] = 0;
+        if (id >= abg->node_n) continue;
+        const int ni = x->cin[id], no = x->cout[id];
+        if (!x->has_read_ids && ni <= POA_INL && no <= POA_INL) {       /* common case: all in the slabs */
+            if (ni > 1) exchange_order(x->in_id4 + (size_t)id * POA_INL, x->in_w4 + (size_t)id * POA_INL, ni);
+            if (no > 1) exchange_order(x->out_id4 + (size_t)id * POA_INL, x->out_w4 + (size_t)id * POA_INL, no);
+        } else order_edges_of(&abg->node[id]);
     }
+    x->n_touched = 0;
 }
 
 /* max_remain[v] = 1 + max_remain[heaviest out-neighbour, first on ties]; SINK = -1.
@@ -352,22 +505,24 @@ static void order_edges_by_weight(abpoa_graph_t *abg) {
 void abpoa_BFS_set_node_remain(abpoa_graph_t *abg, int src_id, int sink_id) {
     const int n = abg->node_n;
     scratch_reserve(abg, n);
+    const poa_graph_x *x = gx(abg);
     int *deg = gx(abg)->deg, *q = gx(abg)->queue, *remain = abg->node_id_to_max_remain;
-    const abpoa_node_t *node = abg->node;
-    for (int i = 0; i < n; ++i) { deg[i] = node[i].out_edge_n; remain[i] = 0; }
+    memcpy(deg, x->cout, (size_t)n * sizeof(int));
+    memset(remain, 0, (size_t)n * sizeof(int));
     int head = 0, tail = 0;
     q[tail++] = sink_id; remain[sink_id] = -1;
     while (head < tail) {
-        int cur = q[head++];
+        const int cur = q[head++];
         if (cur != sink_id) {
+            const int ne = x->cout[cur]; const int *oid = out_ids_of(x, cur), *ow = out_ws_of(x, cur);
             int best_w = -1, best = -1;
-            for (int e = 0; e < node[cur].out_edge_n; ++e)
-                if (node[cur].out_edge_weight[e] > best_w) { best_w = node[cur].out_edge_weight[e]; best = node[cur].out_id[e]; }
+            for (int e = 0; e < ne; ++e) if (ow[e] > best_w) { best_w = ow[e]; best = oid[e]; }
             remain[cur] = remain[best] + 1;
         }
         if (cur == src_id) return;
-        for (int e = 0; e < node[cur].in_edge_n; ++e) {
-            int u = node[cur].in_id[e];
+        const int ni = x->cin[cur]; const int *iid = in_ids_of(x, cur);
+        for (int e = 0; e < ni; ++e) {
+            const int u = iid[e];
             if (--deg[u] == 0) q[tail++] = u;
         }
     }
@@ -378,11 +533,15 @@ void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
     if (abg->node_n <= 0) { fprintf(stderr, "[%s] Empty graph.\n", __func__); return; }
     const int n = abg->node_n;
     index_arrays_reserve(abg, abpt, n);
+    double t0 = prof_now();
     abpoa_BFS_set_node_index(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    double t1 = prof_now(); poa_prof_ms[0] += t1 - t0;
     order_edges_by_weight(abg);
+    double t2 = prof_now(); poa_prof_ms[1] += t2 - t1;
     if (abpt->wb >= 0) {
         for (int i = 0; i < n; ++i) { abg->node_id_to_max_pos_right[i] = 0; abg->node_id_to_max_pos_left[i] = n; }
         abpoa_BFS_set_node_remain(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+        poa_prof_ms[2] += prof_now() - t2;
     } else if (abpt->zdrop > 0) {
         abpoa_BFS_set_node_remain(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
     }
@@ -439,10 +598,15 @@ int poa_edge_path_score(const abpoa_graph_t *abg, int node_id, int in_idx) {
 }
 
 /* ------------------------------------------------------------------ fusion */
+/* every node strictly between src and sink (topologically) is spanned by one more read.  For
+ * the whole graph with both ends included that is "every node": only counted, folded in later. */
 static void bump_span_reads(abpoa_graph_t *abg, int src_id, int sink_id, int inc_both_ends) {
+    poa_graph_x *x = gx(abg);
+    if (src_id == ABPOA_SRC_NODE_ID && sink_id == ABPOA_SINK_NODE_ID && inc_both_ends) { x->span_pending += 1; return; }
     int lo = abg->node_id_to_index[src_id], hi = abg->node_id_to_index[sink_id];
-    for (int i = lo + 1; i < hi; ++i) abg->node[abg->index_to_node_id[i]].n_span_read += 1;
-    if (inc_both_ends) { abg->node[src_id].n_span_read += 1; abg->node[sink_id].n_span_read += 1; }
+    for (int i = lo + 1; i < hi; ++i) x->cspan[abg->index_to_node_id[i]] += 1;
+    if (inc_both_ends) { x->cspan[src_id] += 1; x->cspan[sink_id] += 1; }
+    x->public_stale = 1;
 }
 
 /* first read of a group: a simple chain SRC -> b0 -> b1 ... -> SINK */
@@ -454,11 +618,11 @@ static void seed_graph_with_sequence(abpoa_graph_t *abg, abpoa_para_t *abpt, con
     for (int i = 0; i < seq_l; ++i) {
         int cur = abpoa_add_graph_node(abg, seq[i]);
         if (qpos_to_node_id) qpos_to_node_id[i] = cur;
-        abpoa_add_graph_edge(abg, last, cur, 0, weight[i], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
-        abg->node[cur].n_span_read = abg->node[last].n_span_read;
+        edge_add(abg, last, cur, 0, weight[i], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+        gx(abg)->cspan[cur] = gx(abg)->cspan[last];
         last = cur;
     }
-    abpoa_add_graph_edge(abg, last, ABPOA_SINK_NODE_ID, 0, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+    edge_add(abg, last, ABPOA_SINK_NODE_ID, 0, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
     abg->is_called_cons = abg->is_set_msa_rank = abg->is_topological_sorted = 0;
     abpoa_topological_sort(abg, abpt);
     bump_span_reads(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, 1);
@@ -471,9 +635,10 @@ static void seed_graph_with_sequence(abpoa_graph_t *abg, abpoa_para_t *abpt, con
  *   I                      -> one new node per inserted base
  *   D                      -> nothing
  * then close with an edge to end_node_id and re-sort. */
-int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *_weight,
-                                 int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends) {
+int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *_weight,
+                             int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends) {
     abpoa_graph_t *abg = ab->abg;
+    poa_graph_x *x = gx(abg);
     const int read_ids_n = 1 + ((tot_read_n - 1) >> 6);
     const uint8_t add_read_id = abpt->use_read_ids, add_read_weight = abpt->use_qv & (abpt->max_n_cons > 1);
     int *weight = _weight;
@@ -485,6 +650,7 @@ int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_i
     if (abg->node_n == 2) {
         seed_graph_with_sequence(abg, abpt, seq, weight, seq_l, qpos_to_node_id, add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
     } else if (res.n_cigar > 0) {
+        const double tf0 = prof_now();
         int qi = -1, last_id = beg_node_id, last_is_new = 0;
         for (int c = 0; c < res.n_cigar; ++c) {
             const abpoa_cigar_t cg = res.graph_cigar[c];
@@ -494,13 +660,13 @@ int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_i
                 ++qi;
                 const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
                 int target, target_is_new = 0;
-                if (abg->node[node_id].base == seq[qi]) target = node_id;
+                if (gx(abg)->cbase[node_id] == seq[qi]) target = node_id;
                 else if ((target = aligned_with_base(abg, node_id, seq[qi])) < 0) {
                     target = abpoa_add_graph_node(abg, seq[qi]); target_is_new = 1;
                 }
-                abpoa_add_graph_edge(abg, last_id, target, target_is_new ? 0 : 1 - last_is_new, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
-                if (target_is_new) abg->node[target].n_span_read = abg->node[last_id].n_span_read;
-                if (!add) abg->node[last_id].n_read--;
+                edge_add(abg, last_id, target, target_is_new ? 0 : 1 - last_is_new, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
+                if (target_is_new) x->cspan[target] = x->cspan[last_id];
+                if (!add) x->cnread[last_id]--;
                 if (target_is_new) aligned_join(abg, node_id, target);
                 last_id = target; last_is_new = target_is_new;
                 if (qpos_to_node_id) qpos_to_node_id[qi] = last_id;
@@ -510,21 +676,31 @@ int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_i
                     ++qi;
                     const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
                     int nid = abpoa_add_graph_node(abg, seq[qi]);
-                    abpoa_add_graph_edge(abg, last_id, nid, 0, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
-                    abg->node[nid].n_span_read = abg->node[last_id].n_span_read;
-                    if (!add) abg->node[last_id].n_read--;
+                    edge_add(abg, last_id, nid, 0, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
+                    x->cspan[nid] = x->cspan[last_id];
+                    if (!add) x->cnread[last_id]--;
                     last_id = nid; last_is_new = 1;
                     if (qpos_to_node_id) qpos_to_node_id[qi] = last_id;
                 }
             } /* ABPOA_CDEL: the read skips this node */
         }
-        abpoa_add_graph_edge(abg, last_id, end_node_id, 1 - last_is_new, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
+        edge_add(abg, last_id, end_node_id, 1 - last_is_new, weight[seq_l - 1], add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
         abg->is_called_cons = abg->is_set_msa_rank = abg->is_topological_sorted = 0;
+        poa_prof_ms[3] += prof_now() - tf0;
         abpoa_topological_sort(abg, abpt);
+        const double tf1 = prof_now();
         bump_span_reads(abg, beg_node_id, end_node_id, inc_both_ends);
+        poa_prof_ms[4] += prof_now() - tf1;
     }
     if (!_weight) free(weight);
     return 0;
+}
+
+int abpoa_add_subgraph_alignment(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *weight,
+                                 int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends) {
+    const int r = poa_add_alignment_nosync(ab, abpt, beg_node_id, end_node_id, seq, weight, seq_l, qpos_to_node_id, res, read_id, tot_read_n, inc_both_ends);
+    poa_graph_sync_public(ab->abg);          /* public API: leave the ABI structs coherent */
+    return r;
 }
 
 int abpoa_add_graph_alignment(abpoa_t *ab, abpoa_para_t *abpt, uint8_t *seq, int *weight, int seq_l, int *qpos_to_node_id,
@@ -581,4 +757,15 @@ void abpoa_subgraph_nodes(abpoa_t *ab, abpoa_para_t *abpt, int inc_beg, int inc_
     if (up < 0 || down >= abg->node_n) poa_die(__func__, "Error in subgraph_nodes");
     *exc_beg = abg->index_to_node_id[up];
     *exc_end = abg->index_to_node_id[down];
+}
+
+/* ------------------------------------------------------------------ compact views for the flattener */
+int64_t poa_graph_edge_count(const abpoa_graph_t *abg) { return cgx(abg)->n_edges; }
+const uint8_t *poa_graph_bases(const abpoa_graph_t *abg) { return cgx(abg)->cbase; }
+const int *poa_graph_in_degrees(const abpoa_graph_t *abg) { return cgx(abg)->cin; }
+const int *poa_graph_in_ids(const abpoa_graph_t *abg, int id) { return in_ids_of(cgx(abg), id); }
+
+/* debugging aid: copy out / clear this thread's phase timers */
+void poa_prof_snapshot(double *out8, int clear) {
+    for (int i = 0; i < 8; ++i) { out8[i] = poa_prof_ms[i]; if (clear) poa_prof_ms[i] = 0; }
 }

@@ -51,6 +51,14 @@ void poa_cons_clear(abpoa_cons_t *abc);            /* free members, keep the str
 void poa_cons_free(abpoa_cons_t *abc);
 void poa_set_msa_rank(abpoa_graph_t *abg, int src_id, int sink_id);
 int poa_edge_path_score(const abpoa_graph_t *abg, int node_id, int in_idx);  /* -G scores */
+/* dense, node-id-indexed views kept by poa_graph.c (see poa_graph_x) */
+void poa_graph_sync_public(abpoa_graph_t *abg);        /* fold dense n_read / n_span_read into node[] */
+int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *weight,
+                             int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends);
+int64_t poa_graph_edge_count(const abpoa_graph_t *abg);
+const uint8_t *poa_graph_bases(const abpoa_graph_t *abg);
+const int *poa_graph_in_degrees(const abpoa_graph_t *abg);
+const int *poa_graph_in_ids(const abpoa_graph_t *abg, int id);
 
 /* log2 / popcount tables the reference exposes as globals (src/abpoa_output.c:13-14) */
 void poa_set_65536_table(void);

@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the adaptive-banded sequence-to-POA-graph DP hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--groups G]
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): synthetic read groups,
+50 reads x 10 kbp, 5 % ONT-like error, global alignment, convex gaps (-O 4,24 -E 2,1).
+One STEP = one complete progressive MSA of every group of the batch (1000 groups at N=1;
+weak scaling: every rank gets its own 1000 groups) = 49 alignments per group.
+
+Printed JSON (rank 0):
+  value     whole-job GCUPS of the DP + backtrace kernels with every flattened alignment job
+            (graph + read) already resident in HBM: all jobs of the step are captured, uploaded
+            once, and re-launched back to back with CUDA-event timing (abpoa_gpu_replay).
+  e2e       the same metric through the public C ABI (abpoa_gpu_msa_batch) from HOST buffers:
+            graph flattening, H2D, kernels, D2H of graph-CIGARs, host graph fusion, consensus --
+            wall clock between barriers, max over ranks.
+  roofline  dominant kernel (poa_align_kernel): algorithmic bytes = cells x S x (P + R x d) with
+            the measured in-degree d, divided by the replay's kernel time, against the measured
+            HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/libabpoa_ref.so, AVX2) on the host cores,
+            one process per physical core, on a bounded sample of the same groups.
+--impl reference prints the reference arm's line (CPU only; rank 0 alone runs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "GCUPS (DP cells/s), global/convex 10 kbp"
+
+
+def physical_cores() -> int:
+    try:
+        out = subprocess.run(["lscpu", "-p=core,socket"], capture_output=True, text=True).stdout
+        cores = {ln for ln in out.splitlines() if ln and not ln.startswith("#")}
+        if cores:
+            return len(cores)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm (CPU): oracle/_ref/libabpoa_ref.so, one process per core, whole groups per process
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    wname, seeds, n_reads, length = args
+    from abpoa_b200 import capi, synth
+    from abpoa_b200.aligner import PoaSession
+    w = synth.WORKLOADS[wname]
+    lib = capi.reference()
+    cells = 0
+    reads_done = 0
+    groups = [synth.make_group(seed, n_reads, length, w.err, w.cfg.m) for seed in seeds]     # outside the timed window
+    with PoaSession(w.cfg, lib) as s:
+        t0 = time.perf_counter()
+        for reads in groups:
+            for a in s.run_reads(reads):
+                cells += a.cells
+            reads_done += len(reads)
+        dt = time.perf_counter() - t0
+    return cells, reads_done, dt
+
+
+def reference_pass(wname: str, n_groups: int, cores: int, n_reads: int, length: int, base_seed: int):
+    """Time the reference on `n_groups` groups spread over `cores` processes. Returns (cells, reads, wall_s)."""
+    seeds = [base_seed + g for g in range(n_groups)]
+    shards = [seeds[i::cores] for i in range(cores)]
+    shards = [s for s in shards if s]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(shards)) as pool:
+        res = pool.map(_ref_worker, [(wname, s, n_reads, length) for s in shards])
+    # all workers start together; the job ends when the slowest one does (process start-up,
+    # read generation and imports are outside each worker's clock)
+    wall = max(r[2] for r in res)
+    return sum(r[0] for r in res), sum(r[1] for r in res), wall
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="convex_10k")
+    ap.add_argument("--groups", type=int, default=0, help="groups per GPU (default: the config's 1000)")
+    ap.add_argument("--ref-groups", type=int, default=0, help="groups in one reference sample (default: one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from abpoa_b200 import synth
+    w = synth.WORKLOADS[args.workload]
+    n_groups = args.groups or w.n_groups
+    cores = physical_cores()
+    cfgdesc = {"workload": f"{args.workload}: {n_groups} groups/GPU x {w.n_reads} reads x {w.length} bp, err {w.err}, "
+                           f"{'global' if w.cfg.align_mode == 0 else 'local'}, O={w.cfg.gap_open1},{w.cfg.gap_open2} E={w.cfg.gap_ext1},{w.cfg.gap_ext2}",
+               "groups_per_gpu": n_groups, "reads_per_group": w.n_reads, "read_len": w.length,
+               "l2_policy": "inputs larger than L2 (job blobs + DP planes of one step >> 126 MB)"}
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ref_groups = args.ref_groups or cores
+        # bounded sample: one group per core per step keeps the whole run within minutes
+        per_step = []
+        for s in range(args.warmup + args.steps):
+            if s < args.warmup and s > 0:
+                continue                      # the CPU needs no repeated warm-up; one untimed pass suffices
+            cells, reads, wall = reference_pass(args.workload, ref_groups, cores, w.n_reads, w.length, 1000 + 7919 * s)
+            if s >= args.warmup:
+                per_step.append((cells, reads, wall))
+        cells = sum(p[0] for p in per_step)
+        reads = sum(p[1] for p in per_step)
+        wall = sum(p[2] for p in per_step)
+        val = cells / wall / 1e9
+        sample = f"{ref_groups} groups ({ref_groups * w.n_reads} reads) per step on {cores} processes (one per physical core); cells counted from ab->abm->dp_beg/dp_end"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall / max(len(per_step), 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/int32 (AVX2)", "data": "synthetic", "config": cfgdesc, "reads_per_s": reads / wall,
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from abpoa_b200 import capi
+    from abpoa_b200.aligner import make_para
+    from abpoa_b200.batch import BatchEngine, PackedGroups
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    groups = w.groups(n_groups, base_seed=1000 + 100000 * rank)       # independent groups per rank: no data-path collective
+    packed = PackedGroups(groups)
+    lib = capi.product()
+    abpt = make_para(lib, w.cfg)
+    workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(64, (os.cpu_count() or 8) // max(world, 1)))
+    gpl = int(os.environ.get("ABPOA_GPU_GROUPS_PER_LAUNCH", "0")) or max(1, min(32, (n_groups + workers - 1) // workers))
+    eng = BatchEngine(device=local_rank, n_workers=workers, groups_per_launch=gpl)
+
+    for _ in range(args.warmup):
+        eng.run_packed(abpt, packed, keep_results=False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    cells = 0
+    cons_bases = 0
+    for _ in range(args.steps):
+        res = eng.run_packed(abpt, packed, keep_results=False)
+        cells += sum(r[0] for r in res)
+        cons_bases += sum(r[2] for r in res)
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    st = eng.stats()
+    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(cells), float(packed.total_reads * args.steps), float(st["launches"]), float(st["h2d_bytes"]), float(st["d2h_bytes"])],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    elapsed = float(t.item())
+    tot_cells, tot_reads, launches, h2d, d2h = [float(x) for x in c.tolist()]
+    e2e_gcups = tot_cells / elapsed / 1e9
+
+    # device-resident pass: capture one step's jobs, upload once, replay with CUDA-event timing
+    eng.run_packed(abpt, packed, keep_results=False, capture=True)
+    barrier()
+    rp = eng.replay(abpt, warmup=1, repeats=max(args.steps, 2))
+    eng.clear_capture()
+    kt = torch.tensor([rp["kernel_ms"]], dtype=torch.float64, device="cuda")
+    kc = torch.tensor([float(rp["cells"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kc, op=dist.ReduceOp.SUM)
+    kernel_s = float(kt.item()) / 1e3
+    value = float(kc.item()) / kernel_s / 1e9
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (poa_align_kernel): algorithmic bytes per cell = S * (P + R * d)
+    gap = {0: (1, 1), 1: (3, 2), 2: (5, 3)}[2 if (w.cfg.gap_open1 and w.cfg.gap_open2) else (1 if w.cfg.gap_open1 else 0)]
+    P, R = gap
+    d = rp["preds"] / max(rp["rows"], 1)
+    bytes16 = rp["cells16"] * 2 * (P + R * d)
+    bytes32 = (rp["cells"] - rp["cells16"]) * 4 * (P + R * d)
+    achieved = (bytes16 + bytes32) / (rp["kernel_ms"] / 1e3) / 1e9
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak = json.loads(peaks_file.read_text())["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "poa_align_kernel", "bytes_per_cell": (bytes16 + bytes32) / max(rp["cells"], 1), "mean_in_degree": d,
+                "peak_source": peak_src, "launches_per_pass": rp["launches"], "replay_mismatches": rp["mismatches"],
+                "int16_cell_fraction": rp["cells16"] / max(rp["cells"], 1)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ref_groups = args.ref_groups or cores
+        rc, rr, rw = reference_pass(args.workload, ref_groups, cores, w.n_reads, w.length, 1000)
+        cpu = {"value": rc / rw / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference", "reads_per_s": rr / rw,
+               "sample": f"{ref_groups} groups of the same workload ({rr} reads, {rc / 1e9:.1f} G cells) on {cores} processes, one per physical core, {rw:.1f} s wall"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/int32 planes, int32 registers", "data": "synthetic", "config": cfgdesc,
+        "clocks": clocks, "reads_per_s": tot_reads / elapsed,
+        "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
+                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"]},
+    }))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

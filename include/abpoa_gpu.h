@@ -55,6 +55,7 @@ typedef struct {
 } abpoa_gpu_stats_t;
 
 #define ABPOA_GPU_RECORD_READS 0x1
+#define ABPOA_GPU_CAPTURE_JOBS 0x2      /* keep a copy of every flattened alignment job for abpoa_gpu_replay() */
 
 int abpoa_gpu_device_count(void);
 
@@ -67,6 +68,23 @@ void abpoa_gpu_batch_free(abpoa_gpu_batch_t *eng);
 int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *eng, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
                         abpoa_gpu_group_result_t *results, int flags);
 void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r);
+
+/* Device-resident measurement of the hot path: the jobs captured by the last
+ * abpoa_gpu_msa_batch(..., ABPOA_GPU_CAPTURE_JOBS) call (flattened graphs + reads) are uploaded to
+ * HBM once; then `repeats` timed passes launch the DP/backtrace kernels over ALL of them with no
+ * host work in between (CUDA events on the launching stream, L2-cold inputs: the job set is far
+ * larger than L2).  Results are checked against the captured run (score + CIGAR length). */
+typedef struct {
+    int64_t n_jobs, cells, rows, preds;     /* totals over the captured jobs                    */
+    int64_t jobs16, cells16;                /* of which computed with int16 planes               */
+    double kernel_ms;                       /* mean over the timed passes                        */
+    double kernel_ms_min;
+    int64_t launches;                       /* kernel launches per pass                          */
+    int64_t mismatches;                     /* jobs whose replayed result differs from the capture */
+    uint64_t input_bytes;                   /* HBM-resident job blobs                            */
+} abpoa_gpu_replay_t;
+int abpoa_gpu_replay(abpoa_gpu_batch_t *eng, abpoa_para_t *abpt, int warmup, int repeats, abpoa_gpu_replay_t *out);
+void abpoa_gpu_capture_clear(abpoa_gpu_batch_t *eng);
 
 void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *eng, abpoa_gpu_stats_t *out);
 void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *eng);
