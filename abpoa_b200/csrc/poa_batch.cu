@@ -26,6 +26,8 @@
 #include <mutex>
 #include <algorithm>
 #include <string.h>
+#include <sched.h>
+#include <pthread.h>
 #include "abpoa_gpu.h"
 #include "poa_internal.h"
 #include "poa_engine.h"
@@ -113,7 +115,7 @@ extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int wa
     out->input_bytes = total; out->n_jobs = (int64_t)jobs.size();
     for (const CapturedJob &c : jobs) {
         out->cells += c.cells; out->rows += c.n_rows - 1; out->preds += c.n_pred;
-        if (c.bits == 16) { out->jobs16 += 1; out->cells16 += c.cells; }
+        if (c.bits != 32) { out->jobs16 += 1; out->cells16 += c.cells; }
     }
     /* waves: as many jobs per launch as a quarter of the plane arena holds (same width only) */
     const size_t wave_bytes = poa_arena_capacity(e->arena) / 2;
@@ -207,7 +209,28 @@ uint64_t fnv1a(const abpoa_cigar_t *a, int n) {
     return h;
 }
 
+/* One worker per physical core: pin worker `w` to the (base + w)-th CPU the process may use.
+ * Linux numbers the first hardware thread of every core first, so consecutive workers land on
+ * distinct cores; ranks of a multi-GPU job pass disjoint bases (ABPOA_GPU_CPU_BASE). */
+void pin_worker(int w) {
+    const char *pin = getenv("ABPOA_GPU_PIN");
+    if (pin && *pin == '0') return;
+    cpu_set_t allowed; CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+    const int n = CPU_COUNT(&allowed);
+    if (n <= 0) return;
+    const char *b = getenv("ABPOA_GPU_CPU_BASE");
+    int want = ((b && *b ? atoi(b) : 0) + w) % n;
+    for (int c = 0; c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &allowed) && want-- == 0) {
+            cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+            return;
+        }
+}
+
 struct Worker {
+    int index;
     abpoa_gpu_batch *eng; poa_dev_ctx *ctx; abpoa_para_t *abpt; int flags;
     std::atomic<int> *next_chunk; int n_groups; const abpoa_gpu_group_t *groups; abpoa_gpu_group_result_t *results;
 };
@@ -262,6 +285,7 @@ struct PhaseClock {
 
 void worker_main(Worker wk) {
     PhaseClock pc; const bool prof = getenv("ABPOA_GPU_PROFILE") != NULL;
+    pin_worker(wk.index);
     if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
     abpoa_para_t *abpt = wk.abpt;
     const int G = wk.eng->groups_per_launch;
@@ -417,7 +441,7 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     const int nw = e->n_workers < n_chunks ? e->n_workers : n_chunks;
     std::vector<std::thread> th;
     for (int w = 0; w < nw; ++w) {
-        Worker wk = { e, e->ctx[w], abpt, flags, &next_chunk, n_groups, groups, results };
+        Worker wk = { w, e, e->ctx[w], abpt, flags, &next_chunk, n_groups, groups, results };
         th.emplace_back(worker_main, wk);
     }
     for (auto &t : th) t.join();

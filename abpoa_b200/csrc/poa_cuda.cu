@@ -20,12 +20,15 @@
 #include <condition_variable>
 #include <algorithm>
 #include <chrono>
+#include <time.h>
 #include "poa_internal.h"
 #include "poa_device.cuh"
 #include "poa_engine.h"
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
                                         const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st);
+extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, const PoaJobDesc *jobs,
+                                            const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st);
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
@@ -86,6 +89,7 @@ struct poa_dev_ctx {
     cudaStream_t st;
     cudaEvent_t ev_k0, ev_k1, ev_done;       /* ev_done: blocking-sync event, the host thread sleeps while the GPU works */
     uint8_t *h_in, *h_out, *d_in, *d_work, *d_planes;
+    uint8_t *h_res; size_t h_res_cap;     /* mapped pinned: completion counter + PoaResultDev[] written by the kernel */
     size_t h_in_cap, h_out_cap, d_in_cap, d_work_cap, d_planes_cap;
     size_t planes_limit;              /* hard cap for the plane slab (bytes); 0 = ask the device */
     poa_engine_stats stats;
@@ -125,6 +129,7 @@ void poa_dev_ctx_free(poa_dev_ctx *c) {
     cudaStreamSynchronize(c->st);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_res) cudaFreeHost(c->h_res);
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_work) cudaFree(c->d_work);
     if (c->d_planes) cudaFree(c->d_planes);
@@ -167,11 +172,13 @@ static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint) {
     CK(cudaSetDevice(c->dev));
     const size_t r = (size_t)rows_hint, q = (size_t)qlen_hint, j = (size_t)jobs;
-    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 20 + (q + r + 8) * 8 + 1024), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
+    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 20 + (q + r + 8) * 8 + 1024 + (q + 32) * 2 * 32), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
     if (in_b > c->h_in_cap) grow_host(&c->h_in, &c->h_in_cap, in_b / 2 + 1);
     if (in_b > c->d_in_cap) grow_dev(&c->d_in, &c->d_in_cap, in_b / 2 + 1, 1);
     if (work_b > c->d_work_cap) grow_dev(&c->d_work, &c->d_work_cap, work_b / 2 + 1, 1);
     if (out_b > c->h_out_cap) grow_host(&c->h_out, &c->h_out_cap, out_b / 2 + 1);
+    const size_t res_b = 256 + j * sizeof(PoaResultDev);
+    if (res_b > c->h_res_cap) grow_host(&c->h_res, &c->h_res_cap, res_b);
 }
 
 void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
@@ -183,7 +190,7 @@ void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
     p->zdrop = abpt->zdrop;
     p->put_gap_on_right = abpt->put_gap_on_right; p->put_gap_at_end = abpt->put_gap_at_end;
     p->ret_cigar = abpt->ret_cigar;
-    p->pn = bits == 16 ? 16 : 8;             /* AVX2: 256-bit vectors of int16 / int32 */
+    (void)bits;
     memcpy(p->mat, abpt->mat, (size_t)abpt->m * abpt->m * sizeof(int));
 }
 
@@ -210,11 +217,11 @@ static inline double now_ms(void) {
 static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
     CK(cudaSetDevice(c->dev));
     const double t_begin = now_ms();
-    const int S = bits / 8;
+    const int S = bits == 32 ? 4 : 2;          /* bits: 15 = packed int16x2 kernel, 16 / 32 = generic kernel */
     /* ---- layout of the input arena: params | descs | blobs ---- */
     size_t in_bytes = al256(sizeof(PoaParamsDev)) + al256((size_t)n * sizeof(PoaJobDesc));
     const size_t off_desc = al256(sizeof(PoaParamsDev));
-    std::vector<size_t> blob_off(n), work_off(n), cig_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    std::vector<size_t> blob_off(n), work_off(n), cig_off(n), qp_off(n); std::vector<uint64_t> units(n), plane_off(n);
     for (int t = 0; t < n; ++t) { blob_off[t] = in_bytes; in_bytes += al256(jobs[idx[t]].plan.bytes); }
     /* ---- work arena: results | per job (rowinfo, rowoff, cigar) ---- */
     size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
@@ -224,6 +231,8 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         work_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)) + al256((size_t)j.plan.n_rows * 4);
         cig_off[t] = work_bytes;
         work_bytes += al256((size_t)(j.plan.qlen + j.plan.n_rows + 8) * 8);
+        qp_off[t] = work_bytes;
+        if (bits == 15) work_bytes += al256((size_t)abpt->m * ((((size_t)j.plan.qlen + 1 + 7) & ~(size_t)7) + 8) * 2);
     }
     uint64_t tot_units = 0;
     for (int t = 0; t < n; ++t) {
@@ -232,6 +241,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     }
     const size_t plane_bytes = (size_t)tot_units * POA_GROUP * S;
     grow_host(&c->h_in, &c->h_in_cap, in_bytes);
+    grow_host(&c->h_res, &c->h_res_cap, 256 + (size_t)n * sizeof(PoaResultDev));
     grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
     grow_dev(&c->d_work, &c->d_work_cap, work_bytes, 1);
     uint8_t *planes_base;
@@ -251,12 +261,15 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         desc[t].cigar = (uint64_t *)(c->d_work + cig_off[t]);
         desc[t].cigar_cap = j.plan.qlen + j.plan.n_rows + 8;
         desc[t].pad = 0;
-        desc[t].result = (PoaResultDev *)c->d_work + t;
+        desc[t].result = (PoaResultDev *)(c->h_res + 256) + t;      /* mapped pinned host memory */
+        desc[t].done = NULL;
+        desc[t].qprof = (int16_t *)(c->d_work + qp_off[t]);
+        ((volatile PoaResultDev *)(c->h_res + 256))[t].t_end_ns = 0;
     }
+    __sync_synchronize();
     c->last_desc = desc[0]; c->last_bits = bits; c->last_gap = abpt->gap_mode; c->last_rows = jobs[idx[0]].plan.n_rows;
     const double t_filled = now_ms();
     CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
-    CK(cudaEventRecord(c->ev_k0, c->st));
     /* shared-memory ring: wide enough for the widest expected band of this launch */
     int band_cells = 0;
     for (int t = 0; t < n; ++t) {
@@ -266,22 +279,44 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     }
     static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
     int ring_rows = 2, ring_cells = 64;
-    poa_pick_ring(abpt->gap_mode, bits, band_cells, smem_budget, &ring_rows, &ring_cells);
-    CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
-                        (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
-    CK(cudaEventRecord(c->ev_k1, c->st));
-    /* ---- results first (they say how many cigar words each job produced) ---- */
-    size_t out_bytes = al256((size_t)n * sizeof(PoaResultDev));
-    grow_host(&c->h_out, &c->h_out_cap, out_bytes);
-    CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));
-    stream_wait(c);
+    poa_pick_ring(abpt->gap_mode, bits == 32 ? 32 : 16, band_cells, smem_budget, &ring_rows, &ring_cells);
+    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                                            (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                             (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    /* ---- wait for the launch: every job bumps the counter in mapped host memory when its results
+     *      (also written there) are complete.  No event / copy is queued behind the kernel, so
+     *      streams that share a hardware channel never serialise on it. ---- */
+    {
+        volatile PoaResultDev *rr = (volatile PoaResultDev *)(c->h_res + 256);
+        struct timespec nap = { 0, 100 * 1000 };
+        const double t_wait0 = now_ms();
+        int spins = 0, next = 0;
+        while (next < n) {
+            if (rr[next].t_end_ns != 0) { ++next; continue; }
+            if (++spins > 20) nanosleep(&nap, NULL);
+            if ((spins & 1023) == 0) {
+                cudaError_t e = cudaStreamQuery(c->st);
+                if (e != cudaSuccess && e != cudaErrorNotReady) CK(e);
+                if (e == cudaSuccess && rr[next].t_end_ns == 0) { __sync_synchronize(); if (rr[next].t_end_ns == 0) poa_die("libabpoa_b200/cuda", "kernel finished without reporting job %d", next); }
+                if (now_ms() - t_wait0 > 600e3) poa_die("libabpoa_b200/cuda", "alignment launch did not finish within 600 s");
+            }
+        }
+        __sync_synchronize();
+    }
     const double t_waited = now_ms();
     if (c->arena) arena_give(c->arena, planes_base, plane_bytes);      /* the backtrace is done: planes are dead */
-    float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
-    c->stats.kernel_ms += ms; c->stats.launches += 1; c->stats.h2d_bytes += in_bytes;
+    size_t out_bytes = 0;
+    {
+        const PoaResultDev *rr = (const PoaResultDev *)(c->h_res + 256);
+        uint64_t t0 = UINT64_MAX, t1 = 0;
+        for (int t = 0; t < n; ++t) { if (rr[t].t_start_ns < t0) t0 = rr[t].t_start_ns; if (rr[t].t_end_ns > t1) t1 = rr[t].t_end_ns; }
+        if (t1 > t0) c->stats.kernel_ms += (double)(t1 - t0) * 1e-6;     /* first warp in .. last warp out, %globaltimer */
+    }
+    c->stats.launches += 1; c->stats.h2d_bytes += in_bytes;
 
     std::vector<PoaResultDev> resv(n);
-    memcpy(resv.data(), c->h_out, (size_t)n * sizeof(PoaResultDev));
+    memcpy(resv.data(), c->h_res + 256, (size_t)n * sizeof(PoaResultDev));
     std::vector<size_t> out_cig(n), out_band(n);
     for (int t = 0; t < n; ++t) {
         const poa_job &j = jobs[idx[t]];
@@ -326,29 +361,42 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
  * `sink` callback right after the launch that produced them. */
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user) {
     if (n <= 0) return;
-    std::vector<int> w16, w32;
-    for (int t = 0; t < n; ++t) (poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows) == 16 ? w16 : w32).push_back(t);
+    static const int use_p16 = [] { const char *e = getenv("ABPOA_GPU_NO_P16"); return !(e && *e == '1'); }();
+    std::vector<int> kinds[3];                      /* 0: packed int16x2, 1: generic int16, 2: generic int32 */
+    for (int t = 0; t < n; ++t) {
+        const int rb = poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows);
+        jobs[t].ref_bits = rb;
+        if (use_p16 && poa_p16_ok(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows)) kinds[0].push_back(t);
+        else kinds[rb == 16 ? 1 : 2].push_back(t);
+    }
     /* a launch may borrow at most this much of the plane memory (leave room for other streams) */
     size_t limit = c->planes_limit;
     if (c->arena) limit = poa_arena_capacity(c->arena) / 4;
-    for (int pass = 0; pass < 2; ++pass) {
-        std::vector<int> &v = pass == 0 ? w16 : w32;
-        const int bits = pass == 0 ? 16 : 32;
+    static const int kind_bits[3] = { 15, 16, 32 };
+    for (int pass = 0; pass < 3; ++pass) {
+        std::vector<int> &v = kinds[pass];
+        const int bits = kind_bits[pass];
         size_t pos = 0;
         while (pos < v.size()) {
             size_t bytes = 0, end = pos;
             while (end < v.size()) {
-                const size_t b = (size_t)plane_units_for(&jobs[v[end]], abpt->gap_mode, 0) * POA_GROUP * (bits / 8);
+                const size_t b = (size_t)plane_units_for(&jobs[v[end]], abpt->gap_mode, 0) * POA_GROUP * (bits == 32 ? 4 : 2);
                 if (end > pos && limit && bytes + b > limit) break;
                 bytes += b; ++end;
             }
             run_same_width(c, abpt, jobs, v.data() + pos, (int)(end - pos), bits, 0);
             std::vector<int> redo;
-            for (size_t t = pos; t < end; ++t) { if (jobs[v[t]].status == POA_ST_PLANE_OVF) redo.push_back(v[t]); else sink(user, &jobs[v[t]]); }
+            for (size_t t = pos; t < end; ++t) {
+                const int st = jobs[v[t]].status;
+                if (st == POA_ST_PLANE_OVF) redo.push_back(v[t]);
+                else if (st == POA_ST_RANGE) { c->stats.retries += 1; kinds[jobs[v[t]].ref_bits == 16 ? 1 : 2].push_back(v[t]); }   /* later pass redoes it */
+                else sink(user, &jobs[v[t]]);
+            }
             for (int t : redo) {
                 c->stats.retries += 1;
                 run_same_width(c, abpt, jobs, &t, 1, bits, 1);
-                sink(user, &jobs[t]);
+                if (jobs[t].status == POA_ST_RANGE) kinds[jobs[t].ref_bits == 16 ? 1 : 2].push_back(t);
+                else sink(user, &jobs[t]);
             }
             pos = end;
         }
@@ -398,7 +446,7 @@ static void single_sink(void *user, poa_job *j) {
         abm->dp_end_sn = (int *)poa_xrealloc(abm->dp_end_sn, (size_t)m * sizeof(int));
         abm->rang_m = m;
     }
-    const int pn = j->bits == 16 ? 16 : 8;
+    const int pn = j->ref_bits == 16 ? 16 : 8;
     for (int r = 0; r < nr - 1; ++r) {
         abm->dp_beg[r] = j->bands[4 * r]; abm->dp_end[r] = j->bands[4 * r + 1];
         abm->dp_beg_sn[r] = abm->dp_beg[r] / pn; abm->dp_end_sn[r] = abm->dp_end[r] / pn;
@@ -429,7 +477,7 @@ extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, 
     CK(cudaMemcpy(&ri, c->last_desc.rowinfo + row, sizeof ri, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&off, c->last_desc.rowoff + row, sizeof off, cudaMemcpyDeviceToHost));
     info4[0] = ri.beg; info4[1] = ri.end; info4[2] = ri.left; info4[3] = ri.right;
-    const int P = planes_of(c->last_gap), S = c->last_bits / 8;
+    const int P = planes_of(c->last_gap), S = c->last_bits == 32 ? 4 : 2;
     const int g0 = ri.beg >> 3, ng = (ri.end >> 3) - g0 + 1, wd = ri.end - ri.beg + 1;
     if (wd <= 0 || wd > cap) return -1;
     std::vector<uint8_t> buf((size_t)ng * 8 * P * S);
@@ -448,17 +496,19 @@ extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, 
 double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const poa_replay_job *rj, int n, int bits,
                                  int32_t *out_score, int32_t *out_nops, int64_t *out_cells) {
     CK(cudaSetDevice(c->dev));
-    const int S = bits / 8;
+    const int S = bits == 32 ? 4 : 2;
     const size_t off_desc = al256(sizeof(PoaParamsDev));
     const size_t in_bytes = off_desc + al256((size_t)n * sizeof(PoaJobDesc));
     size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
-    std::vector<size_t> work_off(n), cig_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    std::vector<size_t> work_off(n), cig_off(n), qp_off(n); std::vector<uint64_t> units(n), plane_off(n);
     uint64_t tot_units = 0; int band_cells = 0;
     for (int t = 0; t < n; ++t) {
         work_off[t] = work_bytes;
         work_bytes += al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)) + al256((size_t)rj[t].n_rows * 4);
         cig_off[t] = work_bytes;
         work_bytes += al256((size_t)(rj[t].qlen + rj[t].n_rows + 8) * 8);
+        qp_off[t] = work_bytes;
+        if (bits == 15) work_bytes += al256((size_t)abpt->m * ((((size_t)rj[t].qlen + 1 + 7) & ~(size_t)7) + 8) * 2);
         poa_job tmp; memset(&tmp, 0, sizeof tmp); tmp.plan.n_rows = rj[t].n_rows; tmp.plan.qlen = rj[t].qlen; tmp.plan.w = rj[t].w;
         units[t] = plane_units_for(&tmp, abpt->gap_mode, 0);
         plane_off[t] = tot_units; tot_units += units[t];
@@ -484,15 +534,19 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         desc[t].cigar_cap = rj[t].qlen + rj[t].n_rows + 8;
         desc[t].pad = 0;
         desc[t].result = (PoaResultDev *)c->d_work + t;
+        desc[t].done = NULL;
+        desc[t].qprof = (int16_t *)(c->d_work + qp_off[t]);
     }
     static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
     int ring_rows = 2, ring_cells = 64;
-    poa_pick_ring(abpt->gap_mode, bits, band_cells, smem_budget, &ring_rows, &ring_cells);
+    poa_pick_ring(abpt->gap_mode, bits == 32 ? 32 : 16, band_cells, smem_budget, &ring_rows, &ring_cells);
     CK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaEventRecord(c->ev_k0, c->st));
-    CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
-                        (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                                            (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
+                             (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     CK(cudaEventRecord(c->ev_k1, c->st));
     grow_host(&c->h_out, &c->h_out_cap, (size_t)n * sizeof(PoaResultDev));
     CK(cudaMemcpyAsync(c->h_out, c->d_work, (size_t)n * sizeof(PoaResultDev), cudaMemcpyDeviceToHost, c->st));

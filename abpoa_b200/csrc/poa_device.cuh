@@ -14,6 +14,7 @@
 #define POA_ST_PLANE_OVF  1         /* band planes did not fit the slab handed to the job  */
 #define POA_ST_BT_ERROR   2         /* backtrack found no valid move (reference: fatal)    */
 #define POA_ST_CIGAR_OVF  3
+#define POA_ST_RANGE      4         /* packed int16 kernel: scores left the safe window, redo in 32 bits */
 
 /* Input blob of one alignment job (host builds it in pinned memory, one H2D copy).
  * All offsets are in bytes from the start of the blob; every section is 16 B aligned. */
@@ -31,7 +32,8 @@ typedef struct PoaJobHeader {
     int32_t off_live;       /* uint8  [n_rows]  sub-graph row mask, or -1 (all rows live)        */
     int32_t off_qs;         /* uint8  [qlen+1 padded] shifted query: qs[j] = query[j-1], qs[0]=0 */
     int32_t blob_bytes;
-    int32_t pad[3];
+    int32_t pn;             /* lanes of the reference's AVX2 vector for ITS score width (16 / 8): beg-clamp rule */
+    int32_t pad[2];
 } PoaJobHeader;
 
 /* one DP row's band and arg-max, 16 B: the adaptive band of a successor row is derived
@@ -48,6 +50,7 @@ typedef struct PoaResultDev {
     int64_t cells;                      /* sum over DP rows of (end - beg + 1)              */
     uint64_t plane_units_used;          /* 8-cell units of plane storage consumed           */
     int64_t fwd_clk, bt_clk;            /* SM clock cycles spent in the forward DP / the backtrace */
+    uint64_t t_start_ns, t_end_ns;      /* %globaltimer at entry / exit of the job's warp          */
 } PoaResultDev;
 
 /* device pointers of one job */
@@ -60,7 +63,9 @@ typedef struct PoaJobDesc {
     uint64_t *cigar;                    /* [cigar_cap]                                      */
     int32_t cigar_cap;
     int32_t pad;
-    PoaResultDev *result;
+    PoaResultDev *result;               /* may live in mapped pinned host memory            */
+    int32_t *done;                      /* unused (kept for layout)                                        */
+    int16_t *qprof;                     /* packed kernel: query profile scratch [m][qstride] in HBM         */
 } PoaJobDesc;
 
 /* alignment parameters, identical for all jobs of a launch */
@@ -73,8 +78,7 @@ typedef struct PoaParamsDev {
     int32_t put_gap_on_right, put_gap_at_end;
     int32_t ret_cigar;
     int32_t zero;                       /* always 0 (see poa_kernels.cu: LOCAL floors) */
-    int32_t pn;                         /* lanes of the reference's AVX2 vector for the chosen
-                                           score width (16 / 8): only used for its beg-clamp rule */
+    int32_t pn_unused;
     int32_t mat[POA_MAX_M * POA_MAX_M];
 } PoaParamsDev;
 

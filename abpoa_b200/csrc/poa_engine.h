@@ -17,7 +17,7 @@ typedef struct {
     int want_bands;                 /* copy the per-row (beg,end,left,right) back            */
     void *tag;                      /* caller's cookie                                        */
     /* out (valid inside the sink callback only) */
-    int status, bits;
+    int status, bits, ref_bits;     /* bits: kernel variant used (15 packed int16, 16, 32); ref_bits: the reference's width */
     int best_score, best_i, best_j, start_i, start_j, n_aln_bases, n_matched_bases, max_band;
     int64_t cells;
     int n_ops; const uint64_t *ops; /* graph-CIGAR words in backtrack (reversed) order        */

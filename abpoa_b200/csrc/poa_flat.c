@@ -57,6 +57,7 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
     size_t off = al16(sizeof *h);
     memset(h, 0, sizeof *h);
     h->n_rows = n_rows; h->qlen = qlen; h->w = pl->w; h->node_n = abg->node_n;
+    h->pn = poa_score_bits(abpt, qlen, n_rows) == 16 ? 16 : 8;
     h->off_base = (int32_t)off; off += al16(nr);
     h->off_remain = -1;
     if (pl->with_remain) { h->off_remain = (int32_t)off; off += al16(nr * 4); }
@@ -113,8 +114,26 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
         }
         predoff[r + 1] = np;
     }
-    (void)abpt;
     qs[0] = 0;
     memcpy(qs + 1, query, (size_t)qlen);
     memset(qs + 1 + qlen, 0, (size_t)h->blob_bytes - h->off_qs - 1 - (size_t)qlen);
+}
+
+/* May this alignment run on the packed int16x2 kernel?  Upper bounds are static; the lower side
+ * is additionally watched at run time (POA_ST_RANGE -> the job is redone in 32 bits). */
+int poa_p16_ok(const abpoa_para_t *abpt, int qlen, int n_rows) {
+    const int oe1 = abpt->gap_open1 + abpt->gap_ext1, oe2 = abpt->gap_open2 + abpt->gap_ext2;
+    const int emax = POA_MAX(abpt->gap_ext1, abpt->gap_ext2), oemax = POA_MAX(oe1, oe2);
+    if (abpt->max_mat <= 0 || (int64_t)qlen * abpt->max_mat > 28000) return 0;
+    if (abpt->min_mis > 1000 || abpt->max_mat > 1000 || oemax > 1000 || emax > 100) return 0;
+    if (abpt->wb < 0) {
+        if (abpt->align_mode != ABPOA_LOCAL_MODE) {          /* unbanded global / extend: column 0 sinks by e per row */
+            const int64_t len = qlen > n_rows ? qlen : n_rows;
+            if (len * abpt->gap_ext1 + abpt->gap_open1 > 26000) return 0;
+        }
+    } else {
+        const int64_t w = poa_band_halfwidth(abpt, qlen);
+        if (2 * w * emax + oemax > 12000) return 0;          /* worst in-band cell relative to the row maximum */
+    }
+    return 1;
 }

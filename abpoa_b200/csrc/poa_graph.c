@@ -232,6 +232,18 @@ void abpoa_reset(abpoa_t *ab, abpoa_para_t *abpt, int qlen) {
             for (int j = 0; j < nd->out_edge_n; ++j) memset(nd->read_ids[j], 0, (size_t)nd->read_ids_n * sizeof(uint64_t));
         nd->in_edge_n = nd->out_edge_n = nd->aligned_node_n = 0;
         nd->n_read = nd->n_span_read = 0;
+        /* invariant of the dense mirror: "degree <= POA_INL  <=>  edges live in the slabs".
+         * A node that spilled to the heap goes back to its inline slots for the next group. */
+        if (nd->in_edge_m > POA_INL) {
+            free(nd->in_id); free(nd->in_edge_weight);
+            nd->in_id = gx(abg)->in_id4 + (size_t)i * POA_INL; nd->in_edge_weight = gx(abg)->in_w4 + (size_t)i * POA_INL; nd->in_edge_m = POA_INL;
+        }
+        if (nd->out_edge_m > POA_INL) {
+            free(nd->out_id); free(nd->out_edge_weight);
+            if (nd->read_ids && nd->read_ids_n > 0)
+                for (int j = POA_INL; j < nd->out_edge_m; ++j) free(nd->read_ids[j]);
+            nd->out_id = gx(abg)->out_id4 + (size_t)i * POA_INL; nd->out_edge_weight = gx(abg)->out_w4 + (size_t)i * POA_INL; nd->out_edge_m = POA_INL;
+        }
     }
     {
         poa_graph_x *x = gx(abg);

@@ -83,6 +83,7 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
                    int beg_node_id, int end_node_id, const uint8_t *query);
 /* score width the reference would pick for this alignment (src/abpoa_align_simd.c:1293-1303) */
 int poa_score_bits(const abpoa_para_t *abpt, int qlen, int n_rows);
+int poa_p16_ok(const abpoa_para_t *abpt, int qlen, int n_rows);
 
 /* ---- CUDA backend (poa_cuda.cu) ---- */
 typedef struct poa_dev_ctx poa_dev_ctx;            /* per-handle stream + HBM arenas */

@@ -98,12 +98,12 @@ template <int GAP> struct Planes {
 /* ------------------------------------------------------------------ job view */
 struct JobView {
     const uint8_t *base; const int32_t *remain, *predoff, *pred, *predscore, *nodeid; const uint8_t *live, *qs;
-    int n_rows, qlen, w, node_n;
+    int n_rows, qlen, w, node_n, pn;
 };
 __device__ __forceinline__ JobView open_job(const uint8_t *blob) {
     const PoaJobHeader *h = reinterpret_cast<const PoaJobHeader *>(blob);
     JobView v;
-    v.n_rows = h->n_rows; v.qlen = h->qlen; v.w = h->w; v.node_n = h->node_n;
+    v.n_rows = h->n_rows; v.qlen = h->qlen; v.w = h->w; v.node_n = h->node_n; v.pn = h->pn;
     v.base = blob + h->off_base;
     v.remain = reinterpret_cast<const int32_t *>(blob + h->off_remain);
     v.predoff = reinterpret_cast<const int32_t *>(blob + h->off_predoff);
@@ -281,6 +281,16 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
 }
 
 /* ================================================================== forward DP + backtrace */
+/* Tell the host this job is finished: results (possibly in mapped host memory) are made
+ * visible system-wide, then its t_end_ns field turns non-zero (a plain store: no PCIe atomics
+ * needed).  The host sleeps on those fields instead of on a stream event, so nothing that waits for the kernel is ever
+ * queued behind it in a hardware channel shared with other streams. */
+__device__ __forceinline__ void signal_done(const PoaJobDesc &jd) {
+    uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    __threadfence_system();
+    *reinterpret_cast<volatile uint64_t *>(&jd.result->t_end_ns) = t | 1ull;      /* non-zero == finished */
+}
+
 /* planes a successor row reads from its predecessors: H (+E1 (+E2)) */
 template <int GAP> struct RingPlanes { static constexpr int N = GAP == LG ? 1 : (GAP == AG ? 2 : 3); };
 
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     const int job = blockIdx.x;
     if (job >= n_jobs) return;
     const long long clk0 = clock64();
+    uint64_t t_start_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
     const int m = prm->m;
     for (int t = lane; t < m * m; t += 32) mat_s[t] = prm->mat[t];
     __syncwarp();
@@ -315,13 +326,13 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     const bool banded = w >= 0;
     const bool use_remain = banded || (MODE == EXTEND && prm->zdrop > 0);
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
-    const int pnv = prm->pn;
+    const int pnv = jv.pn;
     const int zr = prm->zero;            /* run-time 0: keeps ptxas from fusing the LOCAL floors into VIMNMX.RELU */
 
     PoaResultDev res;
     res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
     res.start_i = res.start_j = 0; res.n_aln_bases = res.n_matched_bases = 0; res.max_band = 0; res.cells = 0; res.plane_units_used = 0;
-    res.fwd_clk = 0; res.bt_clk = 0;
+    res.fwd_clk = 0; res.bt_clk = 0; res.t_start_ns = t_start_ns; res.t_end_ns = 0;
 
     uint64_t cursor = 0;                 /* bump allocator over the job's plane slab, in 8-cell units */
     int64_t cells = 0; int max_band = 0;
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         int end0 = qlen;
         if (banded) end0 = min(qlen, max(0, qlen - __ldg(jv.remain)) + w);
         const int g1 = end0 >> 3, ngrp = g1 + 1;
-        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; } return; }
+        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
             const int g = gp + lane;
             if (g <= g1) {
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         }
         const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
         if (cursor + (uint64_t)ngrp * PL::N > jd.plane_cap_units || cursor + (uint64_t)ngrp * PL::N > 0xffffffffull) {
-            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; }
+            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; signal_done(jd); }
             return;
         }
         const uint32_t my_off = (uint32_t)cursor;
@@ -645,6 +656,458 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
         if (lane == 0) jd.result->bt_clk = clock64() - clk1;
     }
+    if (lane == 0) signal_done(jd);
+}
+
+/* ================================================================== packed int16x2 forward DP
+ * Same algorithm, same int16 plane layout and the same backtrace as poa_align_kernel<.., int16_t, ..>,
+ * but the row arithmetic works on PAIRS of cells with the DPX packed instructions
+ * (VIMNMX.S16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2 / VIADD.16x2): a lane's 8 cells are 4 registers
+ * per plane, loaded and stored as one 16-byte vector without unpacking.
+ *   - "minus infinity" is NEGP = -30000: far below any real score the launcher admits to this
+ *     kernel, and far enough from -32768 that adding one penalty cannot wrap; every addition that
+ *     can go down is a VIADDMNMX clamped at NEGP.
+ *   - substitution scores come from a per-job query profile qp[residue][j] (int16, built by the
+ *     warp itself at kernel start) as one 16-byte load per row.
+ *   - the lane-local part of the F prefix-max runs on packed values; the cross-lane scan runs on
+ *     32-bit lane aggregates, so e*jr never has to fit 16 bits.
+ *   - band edges are applied with two 16-byte mask vectors from shared-memory tables.
+ * The launcher uses this kernel whenever scores provably fit (see poa_p16_ok); a run-time guard
+ * (row maxima drifting towards the rails) makes the job fall back to the 32-bit kernel. */
+#define NEGP (-30000)
+#define NEGP2 0x8AD08AD0u
+
+__device__ __forceinline__ unsigned pk(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned v) { return ((int)v) >> 16; }
+__device__ __forceinline__ unsigned bc_hi(unsigned v) { return __byte_perm(v, v, 0x3232); }      /* [hi, hi] */
+/* cells shifted by one towards higher j: [prev.hi, cur.lo] */
+__device__ __forceinline__ unsigned sh1(unsigned prev, unsigned cur) { return __byte_perm(prev, cur, 0x5432); }
+
+/* lane-local exclusive prefix max: P[c] = max(x, a[0..c-1]) for the 8 packed cells a[0..3], x broadcast in xb */
+__device__ __forceinline__ void lane_excl_prefix(const unsigned a[4], unsigned xb, unsigned P[4]) {
+    unsigned inc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) inc[k] = __vmaxs2(a[k], __byte_perm(a[k], NEGP2, 0x1054));   /* [lo, max(lo,hi)] */
+    inc[1] = __vmaxs2(inc[1], bc_hi(inc[0]));
+    inc[2] = __vmaxs2(inc[2], bc_hi(inc[1]));
+    inc[3] = __vmaxs2(inc[3], bc_hi(inc[2]));
+    P[0] = __vmaxs2(sh1(xb, inc[0]), xb);
+    P[1] = __vmaxs2(sh1(inc[0], inc[1]), xb);
+    P[2] = __vmaxs2(sh1(inc[1], inc[2]), xb);
+    P[3] = __vmaxs2(sh1(inc[2], inc[3]), xb);
+}
+/* max over the 8 packed cells as a 32-bit int */
+__device__ __forceinline__ int lane_max8(const unsigned a[4]) {
+    const unsigned m = __vmaxs2(__vmaxs2(a[0], a[1]), __vmaxs2(a[2], a[3]));
+    return max(lo16(m), hi16(m));
+}
+
+template <int GAP, int MODE>
+__global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
+                                                           int n_jobs, int ring_rows, int ring_cells) {
+    typedef int16_t ST;
+    typedef Planes<GAP> PL;
+    constexpr int RN = RingPlanes<GAP>::N;
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    int *mat_s = reinterpret_cast<int *>(dyn_smem);
+    uint4 *cap_lo = reinterpret_cast<uint4 *>(dyn_smem + POA_MAX_M * POA_MAX_M * sizeof(int));   /* [9]: first n cells masked */
+    uint4 *cap_hi = cap_lo + 9;                                                                    /* [9]: last n cells masked  */
+    PoaRowInfo *ring_info = reinterpret_cast<PoaRowInfo *>(cap_hi + 9);
+    uint32_t *ring_off = reinterpret_cast<uint32_t *>(ring_info + ring_rows);
+    ST *ring_data = reinterpret_cast<ST *>(reinterpret_cast<uint8_t *>(ring_off) + (((size_t)ring_rows * 4 + 15) & ~(size_t)15));
+    const int rmask = ring_rows - 1, ring_groups = ring_cells >> 3;
+
+    const int lane = threadIdx.x;
+    const int job = blockIdx.x;
+    if (job >= n_jobs) return;
+    const long long clk0 = clock64();
+    uint64_t t_start_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+    const int m = prm->m;
+    for (int t = lane; t < m * m; t += 32) mat_s[t] = prm->mat[t];
+    if (lane < 9) {
+        unsigned lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lo[k] = pk(2 * k < lane ? NEGP : 32767, 2 * k + 1 < lane ? NEGP : 32767);
+            hi[k] = pk(2 * k >= 8 - lane ? NEGP : 32767, 2 * k + 1 >= 8 - lane ? NEGP : 32767);
+        }
+        cap_lo[lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        cap_hi[lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+    __syncwarp();
+
+    const PoaJobDesc jd = jobs[job];
+    const JobView jv = open_job(jd.blob);
+    ST *planes = reinterpret_cast<ST *>(jd.planes);
+    PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
+    const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
+    const bool banded = w >= 0;
+    const bool use_remain = banded || (MODE == EXTEND && prm->zdrop > 0);
+    const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
+    const int pnv = jv.pn;
+    const unsigned zr2 = (unsigned)prm->zero;     /* run-time packed zero (see the RELU note in poa_align_kernel) */
+
+    PoaResultDev res;
+    res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
+    res.start_i = res.start_j = 0; res.n_aln_bases = res.n_matched_bases = 0; res.max_band = 0; res.cells = 0; res.plane_units_used = 0;
+    res.fwd_clk = 0; res.bt_clk = 0; res.t_start_ns = t_start_ns; res.t_end_ns = 0;
+
+    /* ---- query profile: qp[r][j] = mat[r][query[j-1]], qp[r][0] = 0 (reference :533-539) ---- */
+    int16_t *qp = jd.qprof;
+    const int qstride = ((qlen + 1 + 7) & ~7) + 8;
+    for (int r = 0; r < m; ++r)
+        for (int j = lane; j < qstride; j += 32)
+            qp[(size_t)r * qstride + j] = (j == 0 || j > qlen) ? (int16_t)0 : (int16_t)mat_s[r * m + jv.qs[j]];
+    __syncwarp();
+
+    /* lane-independent packed constants */
+    unsigned K1[4], K2[4], KF1[4], KF2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        K1[k] = pk(e1 * (2 * k), e1 * (2 * k + 1));
+        K2[k] = pk(e2 * (2 * k), e2 * (2 * k + 1));
+        KF1[k] = pk(-(oe1 + e1 * (2 * k - 1)), -(oe1 + e1 * (2 * k)));
+        KF2[k] = pk(-(oe2 + e2 * (2 * k - 1)), -(oe2 + e2 * (2 * k)));
+    }
+    const unsigned NE1 = pk(-e1, -e1), NOE1 = pk(-oe1, -oe1), NE2 = pk(-e2, -e2), NOE2 = pk(-oe2, -oe2);
+
+    uint64_t cursor = 0;
+    int64_t cells = 0; int max_band = 0;
+    int best_score = NEG, best_i = 0, best_j = 0, best_row = 0;
+    int guard_lo = 0, guard_hi = 0;
+    bool stop = false;
+
+    /* ---------------- row 0 ---------------- */
+    {
+        int end0 = qlen;
+        if (banded) end0 = min(qlen, max(0, qlen - __ldg(jv.remain)) + w);
+        const int g1 = end0 >> 3, ngrp = g1 + 1;
+        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
+        for (int gp = 0; gp <= g1; gp += 32) {
+            const int g = gp + lane;
+            if (g <= g1) {
+                int h[8], ea[8], eb[8], fa[8], fb[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = g * 8 + c;
+                    if (MODE == LOCAL) { h[c] = ea[c] = eb[c] = fa[c] = fb[c] = (j <= end0) ? 0 : NEGP; }
+                    else if (j > end0) { h[c] = ea[c] = eb[c] = fa[c] = fb[c] = NEGP; }
+                    else if (GAP == LG) { h[c] = max(-e1 * j, NEGP); }
+                    else if (j == 0) { h[c] = 0; ea[c] = -oe1; eb[c] = -oe2; fa[c] = fb[c] = NEGP; }
+                    else {
+                        fa[c] = max(-o1 - e1 * j, NEGP); fb[c] = max(-o2 - e2 * j, NEGP); ea[c] = eb[c] = NEGP;
+                        h[c] = (GAP == CG) ? max(fa[c], fb[c]) : fa[c];
+                    }
+                }
+                ST *rp = planes + (size_t)g * POA_GROUP;
+                st8(rp, h);
+                if (GAP != LG) { st8(rp + (size_t)PL::E1 * ngrp * POA_GROUP, ea); st8(rp + (size_t)PL::F1 * ngrp * POA_GROUP, fa); }
+                if (GAP == CG) { st8(rp + (size_t)PL::E2 * ngrp * POA_GROUP, eb); st8(rp + (size_t)PL::F2 * ngrp * POA_GROUP, fb); }
+                if (g < ring_groups) {
+                    ST *rq = ring_data + (size_t)g * POA_GROUP;
+                    st8(rq, h);
+                    if (GAP != LG) st8(rq + ring_cells, ea);
+                    if (GAP == CG) st8(rq + 2 * ring_cells, eb);
+                }
+            }
+        }
+        if (lane == 0) {
+            PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0;
+            rowinfo[0] = r0; rowoff[0] = 0; ring_info[0] = r0; ring_off[0] = 0;
+        }
+        cursor = (uint64_t)ngrp * PL::N;
+        cells += end0 + 1; max_band = end0 + 1;
+        __syncwarp();
+    }
+
+    int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
+    if (n_rows > 2) {
+        pb = __ldg(jv.predoff + 1); pe = __ldg(jv.predoff + 2); rbase = __ldg(jv.base + 1);
+        if (use_remain) rem = __ldg(jv.remain + 1);
+        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
+    }
+    for (int i = 1; i < n_rows - 1 && !stop; ++i) {
+        int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
+        if (i + 1 < n_rows - 1) {
+            n_pe = __ldg(jv.predoff + i + 2); n_rbase = __ldg(jv.base + i + 1);
+            if (use_remain) n_rem = __ldg(jv.remain + i + 1);
+            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
+        }
+        const int np = pe - pb;
+        if (!(jv.live && !__ldg(jv.live + i))) {
+
+        int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
+        int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
+        for (int kb = 0; kb < np; kb += 32) {
+            const int k = kb + lane;
+            int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
+            if (k < np) {
+                const int prow = kb == 0 ? mypred : __ldg(jv.pred + pb + k);
+                const bool near = (i - prow) <= rmask;
+                const PoaRowInfo pi = near ? ring_info[prow & rmask] : rowinfo[prow];
+                l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
+                if (kb == 0) {
+                    pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_ps = myps;
+                    pk_off = near ? ring_off[prow & rmask] : rowoff[prow];
+                }
+            }
+            if (banded) {
+                ml = min(ml, __reduce_min_sync(FULL, l1));
+                mr = max(mr, __reduce_max_sync(FULL, r1));
+                min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b1));
+            }
+        }
+        int beg = 0, end = qlen;
+        if (banded) {
+            const int r = qlen - rem;
+            beg = max(0, min(ml, r) - w);
+            end = min(qlen, max(mr, r) + w);
+            if (np > 0 && beg / pnv < min_pre_beg / pnv) beg = min_pre_beg;
+        }
+        const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
+        if (cursor + (uint64_t)ngrp * PL::N > jd.plane_cap_units || cursor + (uint64_t)ngrp * PL::N > 0xffffffffull) {
+            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; signal_done(jd); }
+            return;
+        }
+        const uint32_t my_off = (uint32_t)cursor;
+        cursor += (uint64_t)ngrp * PL::N;
+        ST *rowp = planes + (size_t)my_off * POA_GROUP;
+        ST *ringp = ring_data + (size_t)(i & rmask) * RN * ring_cells;
+        cells += (end >= beg) ? (end - beg + 1) : 0;
+        max_band = max(max_band, end - beg + 1);
+        const int16_t *qrow = qp + (size_t)rbase * qstride;
+
+        int carry1 = 2 * NEG, carry2 = 2 * NEG;
+        int row_max = NEG, row_left = -1, row_right = -1;
+
+        for (int gp = g0; gp <= g1; gp += 32) {
+            const int g = gp + lane;
+            const bool active = g <= g1;
+            uint4 sv = make_uint4(0u, 0u, 0u, 0u);
+            if (active) sv = *reinterpret_cast<const uint4 *>(qrow + (size_t)g * 8);
+            unsigned M[4], X1[4], X2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { M[k] = NEGP2; X1[k] = NEGP2; X2[k] = NEGP2; }
+
+            for (int kb = 0; kb < np; kb += 32) {
+                int c_row = pk_row, c_beg = pk_beg, c_end = pk_end, c_ps = pk_ps; uint32_t c_off = pk_off;
+                if (kb > 0) {
+                    const int k = kb + lane; c_row = -1;
+                    if (k < np) {
+                        c_row = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
+                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? __ldg(jv.predscore + pb + k) : 0;
+                    }
+                }
+                const int nk = min(32, np - kb);
+                for (int k = 0; k < nk; ++k) {
+                    const int p_row = __shfl_sync(FULL, c_row, k);
+                    const int p_beg = __shfl_sync(FULL, c_beg, k), p_end = __shfl_sync(FULL, c_end, k);
+                    const uint32_t p_off = __shfl_sync(FULL, c_off, k);
+                    const int pg0 = p_beg >> 3, pg1 = p_end >> 3, png = pg1 - pg0 + 1;
+                    const bool near = (i - p_row) <= rmask;
+                    const ST *ph = planes + (size_t)p_off * POA_GROUP;
+                    const ST *rh = ring_data + (size_t)(p_row & rmask) * RN * ring_cells;
+                    uint4 hp = make_uint4(NEGP2, NEGP2, NEGP2, NEGP2), ep1 = hp, ep2 = hp;
+                    const bool inr = active && g >= pg0 && g <= pg1;
+                    const int rel = g - pg0;
+                    if (inr && near && rel < ring_groups) {
+                        const ST *q = rh + (size_t)rel * POA_GROUP;
+                        hp = *reinterpret_cast<const uint4 *>(q);
+                        if (GAP != LG) ep1 = *reinterpret_cast<const uint4 *>(q + ring_cells);
+                        if (GAP == CG) ep2 = *reinterpret_cast<const uint4 *>(q + 2 * ring_cells);
+                    } else if (inr) {
+                        const ST *q = ph + (size_t)rel * POA_GROUP;
+                        hp = *reinterpret_cast<const uint4 *>(q);
+                        if (GAP != LG) ep1 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E1 * png * POA_GROUP);
+                        if (GAP == CG) ep2 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E2 * png * POA_GROUP);
+                    }
+                    unsigned prev = __shfl_up_sync(FULL, hp.w, 1);
+                    if (lane == 0) {
+                        const int relm = rel - 1;
+                        int hm1 = NEGP;
+                        if (relm >= 0 && relm < png) hm1 = (near && relm < ring_groups) ? (int)rh[(size_t)relm * POA_GROUP + 7] : (int)ph[(size_t)relm * POA_GROUP + 7];
+                        if (MODE == LOCAL && g == 0) hm1 = 0;
+                        prev = (unsigned)hm1 << 16;
+                    }
+                    unsigned d0 = sh1(prev, hp.x), d1 = sh1(hp.x, hp.y), d2 = sh1(hp.y, hp.z), d3 = sh1(hp.z, hp.w);
+                    if (jv.predscore) {
+                        const int ps = __shfl_sync(FULL, c_ps, k);
+                        const unsigned ps2 = pk(ps, ps);
+                        d0 = __viaddmax_s16x2(d0, ps2, NEGP2); d1 = __viaddmax_s16x2(d1, ps2, NEGP2);
+                        d2 = __viaddmax_s16x2(d2, ps2, NEGP2); d3 = __viaddmax_s16x2(d3, ps2, NEGP2);
+                        if (GAP == LG) {
+                            hp.x = __viaddmax_s16x2(hp.x, ps2, NEGP2); hp.y = __viaddmax_s16x2(hp.y, ps2, NEGP2);
+                            hp.z = __viaddmax_s16x2(hp.z, ps2, NEGP2); hp.w = __viaddmax_s16x2(hp.w, ps2, NEGP2);
+                        } else {
+                            ep1.x = __viaddmax_s16x2(ep1.x, ps2, NEGP2); ep1.y = __viaddmax_s16x2(ep1.y, ps2, NEGP2);
+                            ep1.z = __viaddmax_s16x2(ep1.z, ps2, NEGP2); ep1.w = __viaddmax_s16x2(ep1.w, ps2, NEGP2);
+                            if (GAP == CG) {
+                                ep2.x = __viaddmax_s16x2(ep2.x, ps2, NEGP2); ep2.y = __viaddmax_s16x2(ep2.y, ps2, NEGP2);
+                                ep2.z = __viaddmax_s16x2(ep2.z, ps2, NEGP2); ep2.w = __viaddmax_s16x2(ep2.w, ps2, NEGP2);
+                            }
+                        }
+                    }
+                    M[0] = __vmaxs2(M[0], d0); M[1] = __vmaxs2(M[1], d1); M[2] = __vmaxs2(M[2], d2); M[3] = __vmaxs2(M[3], d3);
+                    if (GAP == LG) {        /* vertical term H[p][j] - e1 */
+                        X1[0] = __vmaxs2(X1[0], __viaddmax_s16x2(hp.x, NE1, NEGP2)); X1[1] = __vmaxs2(X1[1], __viaddmax_s16x2(hp.y, NE1, NEGP2));
+                        X1[2] = __vmaxs2(X1[2], __viaddmax_s16x2(hp.z, NE1, NEGP2)); X1[3] = __vmaxs2(X1[3], __viaddmax_s16x2(hp.w, NE1, NEGP2));
+                    } else {
+                        X1[0] = __vmaxs2(X1[0], ep1.x); X1[1] = __vmaxs2(X1[1], ep1.y); X1[2] = __vmaxs2(X1[2], ep1.z); X1[3] = __vmaxs2(X1[3], ep1.w);
+                        if (GAP == CG) { X2[0] = __vmaxs2(X2[0], ep2.x); X2[1] = __vmaxs2(X2[1], ep2.y); X2[2] = __vmaxs2(X2[2], ep2.z); X2[3] = __vmaxs2(X2[3], ep2.w); }
+                    }
+                }
+            }
+
+            /* band-edge masks of this lane's 8 cells */
+            const int nlo = min(max(beg - g * 8, 0), 8), nhi = min(max(g * 8 + 7 - end, 0), 8);
+            const uint4 clo = cap_lo[nlo], chi = cap_hi[nhi];
+            const unsigned CLO[4] = { clo.x, clo.y, clo.z, clo.w };
+            const unsigned CAP[4] = { __vmins2(clo.x, chi.x), __vmins2(clo.y, chi.y), __vmins2(clo.z, chi.z), __vmins2(clo.w, chi.w) };
+            const unsigned S[4] = { sv.x, sv.y, sv.z, sv.w };
+
+            unsigned T[4], H[4], F1[4], F2[4], E1o[4], E2o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned hm = __viaddmax_s16x2(M[k], S[k], NEGP2);
+                M[k] = __vmins2(hm, CLO[k]);                                 /* Hm, -inf left of the band */
+                if (GAP == LG) T[k] = __vmins2(__vmaxs2(hm, X1[k]), CLO[k]);
+                else if (GAP == AG) T[k] = M[k];                              /* affine F opens from the M-only value */
+                else T[k] = __vmins2(__vimax3_s16x2(hm, X1[k], X2[k]), CLO[k]);
+            }
+            /* lane-local A = T + e*c ; lane aggregate in 32 bits ; warp scan ; back to lane-local */
+            const int jr0 = (g - g0) * 8;
+            unsigned a1[4], a2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a1[k] = __vadd2(T[k], K1[k]); if (GAP == CG) a2[k] = __vadd2(T[k], K2[k]); }
+            const int off1 = e1 * jr0 - (GAP == LG ? 0 : oe1), off2 = e2 * jr0 - oe2;
+            int tot1, tot2 = 0;
+            int x1 = max(warp_excl_max(lane_max8(a1) + off1, lane, tot1), carry1);
+            carry1 = max(carry1, tot1);
+            const int xl1 = min(max(x1 - off1, NEGP), 32767);
+            unsigned P1[4], P2[4];
+            lane_excl_prefix(a1, pk(xl1, xl1), P1);
+            if (GAP == CG) {
+                int x2 = max(warp_excl_max(lane_max8(a2) + off2, lane, tot2), carry2);
+                carry2 = max(carry2, tot2);
+                const int xl2 = min(max(x2 - off2, NEGP), 32767);
+                lane_excl_prefix(a2, pk(xl2, xl2), P2);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (GAP == LG) {
+                    /* inclusive: H[c] = max(P[c], a[c]) - e1*c */
+                    unsigned h = __viaddmax_s16x2(__vmaxs2(P1[k], a1[k]), pk(-e1 * (2 * k), -e1 * (2 * k + 1)), NEGP2);
+                    if (MODE == LOCAL) h = __vmaxs2(h, zr2);
+                    H[k] = __vmins2(h, CAP[k]);
+                } else {
+                    F1[k] = __viaddmax_s16x2(P1[k], KF1[k], NEGP2);
+                    if (GAP == AG) {
+                        const unsigned t = __vmaxs2(M[k], X1[k]);
+                        unsigned fz = F1[k];
+                        if (MODE == LOCAL) fz = __vmaxs2(fz, zr2);
+                        const unsigned h = __vmaxs2(t, fz);
+                        const unsigned from_t = __vcmpges2(t, fz);            /* h == t, per cell */
+                        const unsigned ev = __viaddmax_s16x2(X1[k], NE1, __viaddmax_s16x2(h, NOE1, NEGP2));
+                        const unsigned alt = (MODE == LOCAL) ? zr2 : NEGP2;
+                        E1o[k] = __vmins2((ev & from_t) | (alt & ~from_t), CAP[k]);
+                        H[k] = __vmins2(h, CAP[k]);
+                    } else {
+                        F2[k] = __viaddmax_s16x2(P2[k], KF2[k], NEGP2);
+                        unsigned h = __vimax3_s16x2(T[k], F1[k], F2[k]);
+                        if (MODE == LOCAL) h = __vmaxs2(h, zr2);
+                        unsigned eo1 = __viaddmax_s16x2(X1[k], NE1, __viaddmax_s16x2(h, NOE1, NEGP2));
+                        unsigned eo2 = __viaddmax_s16x2(X2[k], NE2, __viaddmax_s16x2(h, NOE2, NEGP2));
+                        if (MODE == LOCAL) { eo1 = __vmaxs2(eo1, zr2); eo2 = __vmaxs2(eo2, zr2); }
+                        H[k] = __vmins2(h, CAP[k]); E1o[k] = __vmins2(eo1, CAP[k]); E2o[k] = __vmins2(eo2, CAP[k]);
+                    }
+                }
+            }
+
+            if (active) {
+                const int rel = g - g0;
+                const uint4 hv = make_uint4(H[0], H[1], H[2], H[3]);
+                if (rel < ring_groups) {
+                    ST *rq = ringp + (size_t)rel * POA_GROUP;
+                    *reinterpret_cast<uint4 *>(rq) = hv;
+                    if (GAP != LG) *reinterpret_cast<uint4 *>(rq + ring_cells) = make_uint4(E1o[0], E1o[1], E1o[2], E1o[3]);
+                    if (GAP == CG) *reinterpret_cast<uint4 *>(rq + 2 * ring_cells) = make_uint4(E2o[0], E2o[1], E2o[2], E2o[3]);
+                }
+                ST *q = rowp + (size_t)rel * POA_GROUP;
+                *reinterpret_cast<uint4 *>(q) = hv;
+                if (GAP != LG) {
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E1 * ngrp * POA_GROUP) = make_uint4(E1o[0], E1o[1], E1o[2], E1o[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F1 * ngrp * POA_GROUP) = make_uint4(F1[0], F1[1], F1[2], F1[3]);
+                }
+                if (GAP == CG) {
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E2 * ngrp * POA_GROUP) = make_uint4(E2o[0], E2o[1], E2o[2], E2o[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F2 * ngrp * POA_GROUP) = make_uint4(F2[0], F2[1], F2[2], F2[3]);
+                }
+            }
+
+            /* row maximum with first / last arg-max; masked cells hold NEGP and never win against a real cell */
+            {
+                const int lmax = active ? lane_max8(H) : NEGP;
+                const int pm = __reduce_max_sync(FULL, lmax);
+                const unsigned bm = __ballot_sync(FULL, lmax == pm && pm > NEGP);
+                if (bm) {
+                    int lfirst = -1, llast = -1;
+                    if (lmax == pm) {
+#pragma unroll
+                        for (int k = 3; k >= 0; --k) { if (hi16(H[k]) == pm) lfirst = g * 8 + 2 * k + 1; if (lo16(H[k]) == pm) lfirst = g * 8 + 2 * k; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { if (lo16(H[k]) == pm) llast = g * 8 + 2 * k; if (hi16(H[k]) == pm) llast = g * 8 + 2 * k + 1; }
+                    }
+                    const int pl = __shfl_sync(FULL, lfirst, __ffs(bm) - 1);
+                    const int pr = __shfl_sync(FULL, llast, 31 - __clz(bm));
+                    if (pm > row_max) { row_max = pm; row_left = pl; row_right = pr; }
+                    else if (pm == row_max) row_right = pr;
+                }
+            }
+        }
+        if (lane == 0) {
+            PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
+            ring_info[i & rmask] = ri; ring_off[i & rmask] = my_off;
+            rowinfo[i] = ri; rowoff[i] = my_off;
+        }
+        guard_lo |= (row_max < -14000); guard_hi |= (row_max > 29000);
+        if (MODE == LOCAL) {
+            if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_left; }
+        } else if (MODE == EXTEND) {
+            if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_right; best_row = i; }
+            else if (prm->zdrop > 0) {
+                const int delta = __ldg(jv.remain + best_row) - rem;
+                if (best_score - row_max > prm->zdrop + e1 * abs(delta - (row_right - best_j))) stop = true;
+            }
+        }
+        __syncwarp();
+        }   /* live row */
+        pb = pe; pe = n_pe; rbase = n_rbase; rem = n_rem; mypred = n_mypred; myps = n_myps;
+    }
+
+    if (MODE == GLOBAL) {
+        const int sb = jv.predoff[n_rows - 1], sn = jv.predoff[n_rows] - sb;
+        for (int k = 0; k < sn; ++k) {
+            const int prow = jv.pred[sb + k];
+            const PoaRowInfo pi = rowinfo[prow];
+            const int endc = qlen > pi.end ? pi.end : qlen;
+            const int pg0 = pi.beg >> 3;
+            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow] * POA_GROUP + (endc - pg0 * 8)] : NEG;
+            if (v > best_score) { best_score = v; best_i = prow; best_j = endc; }
+        }
+    }
+    res.best_score = best_score; res.best_i = best_i; res.best_j = best_j;
+    res.cells = cells; res.max_band = max_band; res.plane_units_used = cursor;
+    if (guard_lo || guard_hi || best_score <= NEGP + 2000) res.status = POA_ST_RANGE;    /* scores left the safe int16 window: redo in 32 bits */
+    const long long clk1 = clock64();
+    res.fwd_clk = clk1 - clk0;
+    if (lane == 0) *jd.result = res;
+    __syncwarp();
+    if (prm->ret_cigar && res.status == POA_ST_OK) {
+        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+        if (lane == 0) jd.result->bt_clk = clock64() - clk1;
+    }
+    if (lane == 0) signal_done(jd);
 }
 
 /* ------------------------------------------------------------------ launcher */
@@ -681,9 +1144,39 @@ static cudaError_t launch_mode(int mode, const PoaJobDesc *jobs, const PoaParams
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells) {
     int rc = band_cells < 64 ? 64 : band_cells;
     int rr = 64;
+    smem_budget = smem_budget > 512 ? smem_budget - 512 : smem_budget;      /* mask tables of the packed kernel */
     while (rr > 2 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rr >>= 1;
     while (rc > 64 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rc -= 64;   /* very wide rows: cache a prefix */
     *ring_rows = rr; *ring_cells = rc;
+}
+
+template <int GAP, int MODE>
+static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
+    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 227 * 1024;
+    }
+    poa_align_kernel_p16<GAP, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
+    return cudaGetLastError();
+}
+template <int GAP>
+static cudaError_t launch_p16_mode(int mode, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, cudaStream_t st) {
+    switch (mode) {
+    case GLOBAL: return launch_p16_one<GAP, GLOBAL>(jobs, prm, n_jobs, rr, rc, st);
+    case LOCAL:  return launch_p16_one<GAP, LOCAL>(jobs, prm, n_jobs, rr, rc, st);
+    default:     return launch_p16_one<GAP, EXTEND>(jobs, prm, n_jobs, rr, rc, st);
+    }
+}
+/* bits == 15 selects the packed int16x2 kernel (int16 planes, DPX pair arithmetic) */
+extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, const PoaJobDesc *jobs,
+                                            const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
+    if (n_jobs <= 0) return cudaSuccess;
+    if (gap_mode == LG) return launch_p16_mode<LG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    if (gap_mode == AG) return launch_p16_mode<AG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    return launch_p16_mode<CG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
 }
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,

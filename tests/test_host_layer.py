@@ -110,3 +110,26 @@ def test_product_has_no_cpu_fallback(tmp_path):
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert p.returncode != 0 and "ALIGNED" not in p.stdout
     assert "no CUDA device" in p.stderr or "CUDA" in p.stderr
+
+
+def test_handle_reuse_after_reset_with_high_degree_nodes(product_lib):
+    """A handle that held a bushy graph (nodes with more than 4 edges, spilled out of the inline
+    slots) must give the same result as a fresh handle after abpoa_reset()."""
+    from abpoa_b200 import synth
+    from helpers import run_group
+    from oracle_binding import oracle_align
+    cfg = PoaConfig(out_msa=True)
+    bushy = synth.make_group(77, 14, 120, 0.30)          # 30 % error: many alternative branches
+    plain = synth.make_group(78, 6, 300, 0.05)
+    fresh = run_group(product_lib, cfg, plain, use_oracle=True)
+    with PoaSession(cfg, product_lib) as s:
+        for reads in (bushy, plain):
+            s.reset(400)
+            for r in reads:
+                _, res = oracle_align(s, r)
+                s.add(r, res, len(reads))
+        g = s.ab.contents.abg.contents
+        assert max(g.node[i].in_edge_n for i in range(g.node_n)) >= 1
+        s.generate()
+        assert all(np.array_equal(x, y) for x, y in zip(s.consensus(), fresh["cons"]))
+        assert all(np.array_equal(x, y) for x, y in zip(s.msa_rows(), fresh["msa"]))
