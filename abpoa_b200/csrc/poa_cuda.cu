@@ -347,7 +347,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         if (c->capture && resv[t].status == POA_ST_OK) {
             poa_captured_job cj;
             cj.blob = c->h_in + blob_off[t]; cj.bytes = j.plan.bytes; cj.n_rows = j.plan.n_rows; cj.qlen = j.plan.qlen; cj.w = j.plan.w;
-            cj.n_pred = ((const int32_t *)(cj.blob + ((const PoaJobHeader *)cj.blob)->off_predoff))[j.plan.n_rows];
+            cj.n_pred = ((const int32_t *)(cj.blob + ((const PoaJobHeader *)cj.blob)->off_rowmeta))[2 * j.plan.n_rows];
             cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells;
             c->capture(c->capture_user, &cj);
         }
@@ -420,15 +420,21 @@ void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res
     if (!abpt->ret_cigar) return;
     const int n = j->n_ops;
     abpoa_cigar_t *cg = NULL;
+    const abpoa_graph_t *g = j->abg;
+    const int *id_of_row = g->index_to_node_id + j->plan.beg_index;
     if (n > 0) {
+        /* the device names graph positions by DP row; MATCH / DEL words carry node ids (abpoa.h:46-51) */
         cg = (abpoa_cigar_t *)poa_xmalloc((size_t)n * sizeof(abpoa_cigar_t));
-        if (abpt->rev_cigar) memcpy(cg, j->ops, (size_t)n * 8);
-        else for (int t = 0; t < n; ++t) cg[t] = j->ops[n - 1 - t];
+        const int rev = abpt->rev_cigar;
+        for (int t = 0; t < n; ++t) {
+            abpoa_cigar_t w = j->ops[rev ? t : n - 1 - t];
+            if ((w & 0xf) != ABPOA_CINS) w = ((abpoa_cigar_t)id_of_row[w >> 34] << 34) | (w & 0x3ffffffffull);
+            cg[t] = w;
+        }
     }
     res->graph_cigar = cg; res->n_cigar = n; res->m_cigar = n;
-    const abpoa_graph_t *g = j->abg;
-    res->node_e = g->index_to_node_id[j->plan.beg_index + j->best_i]; res->query_e = j->best_j - 1;
-    res->node_s = g->index_to_node_id[j->plan.beg_index + j->start_i]; res->query_s = j->start_j - 1;
+    res->node_e = id_of_row[j->best_i]; res->query_e = j->best_j - 1;
+    res->node_s = id_of_row[j->start_i]; res->query_s = j->start_j - 1;
     res->n_aln_bases += j->n_aln_bases; res->n_matched_bases += j->n_matched_bases;
 }
 

@@ -23,14 +23,13 @@ typedef struct PoaJobHeader {
     int32_t qlen;
     int32_t w;              /* band half width, < 0: unbanded                                   */
     int32_t node_n;         /* graph->node_n: initial max_pos_left of every row                 */
-    int32_t off_base;       /* uint8  [n_rows]  residue code of the row's node                  */
-    int32_t off_remain;     /* int32  [n_rows]  band centre term (only if w >= 0)               */
-    int32_t off_predoff;    /* int32  [n_rows+1]                                                */
-    int32_t off_pred;       /* int32  [n_pred]  predecessor rows, reference in_id order          */
-    int32_t off_predscore;  /* int32  [n_pred]  -G path scores, or -1                            */
-    int32_t off_nodeid;     /* int32  [n_rows]                                                   */
-    int32_t off_live;       /* uint8  [n_rows]  sub-graph row mask, or -1 (all rows live)        */
-    int32_t off_qs;         /* uint8  [qlen+1 padded] shifted query: qs[j] = query[j-1], qs[0]=0 */
+    int32_t off_rowmeta;    /* int2   [n_rows+1] x = start of the row's predecessor list in pred[]        */
+                            /*                   y = (band-centre term << 8) | residue code of the node   */
+    int32_t off_pred;       /* int32  [n_pred]  predecessor rows, reference in_id order                  */
+    int32_t off_predscore;  /* int32  [n_pred]  -G path scores, or -1                                    */
+    int32_t off_live;       /* uint8  [n_rows]  sub-graph row mask, or -1 (all rows live)                */
+    int32_t off_qs;         /* uint8  [qlen+1 padded] shifted query: qs[j] = query[j-1], qs[0]=0         */
+    int32_t rsv[4];
     int32_t blob_bytes;
     int32_t pn;             /* lanes of the reference's AVX2 vector for ITS score width (16 / 8): beg-clamp rule */
     int32_t pad[2];

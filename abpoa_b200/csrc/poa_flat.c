@@ -38,12 +38,9 @@ void poa_blob_plan_make(poa_blob_plan *pl, const abpoa_graph_t *abg, const abpoa
     pl->n_pred_max = n_pred;
     const size_t nr = (size_t)pl->n_rows;
     size_t b = al16(sizeof(struct PoaJobHeader));
-    b += al16(nr);                                   /* base      */
-    if (pl->with_remain) b += al16(nr * 4);          /* remain    */
-    b += al16((nr + 1) * 4);                         /* predoff   */
+    b += al16((nr + 1) * 8);                         /* rowmeta   */
     b += al16((size_t)n_pred * 4 + 4);               /* pred      */
     if (pl->with_score) b += al16((size_t)n_pred * 4 + 4);
-    b += al16(nr * 4);                               /* node ids  */
     if (!pl->whole_graph) b += al16(nr);             /* live mask */
     b += al16((size_t)qlen + 1) + 16;                /* shifted query + one spare vector */
     pl->bytes = b;
@@ -58,25 +55,18 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
     memset(h, 0, sizeof *h);
     h->n_rows = n_rows; h->qlen = qlen; h->w = pl->w; h->node_n = abg->node_n;
     h->pn = poa_score_bits(abpt, qlen, n_rows) == 16 ? 16 : 8;
-    h->off_base = (int32_t)off; off += al16(nr);
-    h->off_remain = -1;
-    if (pl->with_remain) { h->off_remain = (int32_t)off; off += al16(nr * 4); }
-    h->off_predoff = (int32_t)off; off += al16((nr + 1) * 4);
+    h->off_rowmeta = (int32_t)off; off += al16((nr + 1) * 8);
     h->off_pred = (int32_t)off; off += al16((size_t)pl->n_pred_max * 4 + 4);
     h->off_predscore = -1;
     if (pl->with_score) { h->off_predscore = (int32_t)off; off += al16((size_t)pl->n_pred_max * 4 + 4); }
-    h->off_nodeid = (int32_t)off; off += al16(nr * 4);
     h->off_live = -1;
     if (!pl->whole_graph) { h->off_live = (int32_t)off; off += al16(nr); }
     h->off_qs = (int32_t)off; off += al16((size_t)qlen + 1) + 16;
     h->blob_bytes = (int32_t)off;
     if (off != pl->bytes) poa_die(__func__, "blob size mismatch (%zu vs %zu)", off, pl->bytes);
 
-    uint8_t *base = dst + h->off_base;
-    int32_t *remain = pl->with_remain ? (int32_t *)(dst + h->off_remain) : NULL;
-    int32_t *predoff = (int32_t *)(dst + h->off_predoff), *pred = (int32_t *)(dst + h->off_pred);
+    int32_t *rowmeta = (int32_t *)(dst + h->off_rowmeta), *pred = (int32_t *)(dst + h->off_pred);
     int32_t *pscore = pl->with_score ? (int32_t *)(dst + h->off_predscore) : NULL;
-    int32_t *nodeid = (int32_t *)(dst + h->off_nodeid);
     uint8_t *live = pl->whole_graph ? NULL : dst + h->off_live;
     uint8_t *qs = dst + h->off_qs;
 
@@ -93,15 +83,16 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
             }
         }
     }
-    const int end_remain = remain ? abg->node_id_to_max_remain[end_node_id] : 0;
+    const int with_remain = pl->with_remain;
+    const int end_remain = with_remain ? abg->node_id_to_max_remain[end_node_id] : 0;
     const uint8_t *cbase = poa_graph_bases(abg); const int *cin = poa_graph_in_degrees(abg);
     const int *id_of_index = abg->index_to_node_id + beg_index, *index_of_id = abg->node_id_to_index, *max_remain = abg->node_id_to_max_remain;
     int np = 0;
-    predoff[0] = 0;
     for (int r = 0; r < n_rows; ++r) {
         const int id = id_of_index[r];
-        nodeid[r] = id; base[r] = cbase[id];
-        if (remain) remain[r] = max_remain[id] - end_remain - 1;
+        const int rem = with_remain ? max_remain[id] - end_remain - 1 : 0;
+        rowmeta[2 * r] = np;
+        rowmeta[2 * r + 1] = (int32_t)((uint32_t)rem << 8) | cbase[id];
         if (r > 0) {
             const int ni = cin[id]; const int *iid = poa_graph_in_ids(abg, id);
             for (int e = 0; e < ni; ++e) {
@@ -112,8 +103,8 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
                 pred[np++] = pr;
             }
         }
-        predoff[r + 1] = np;
     }
+    rowmeta[2 * n_rows] = np; rowmeta[2 * n_rows + 1] = 0;
     qs[0] = 0;
     memcpy(qs + 1, query, (size_t)qlen);
     memset(qs + 1 + qlen, 0, (size_t)h->blob_bytes - h->off_qs - 1 - (size_t)qlen);

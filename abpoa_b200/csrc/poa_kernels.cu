@@ -97,19 +97,19 @@ template <int GAP> struct Planes {
 
 /* ------------------------------------------------------------------ job view */
 struct JobView {
-    const uint8_t *base; const int32_t *remain, *predoff, *pred, *predscore, *nodeid; const uint8_t *live, *qs;
+    const int2 *rowmeta; const int32_t *pred, *predscore; const uint8_t *live, *qs;
     int n_rows, qlen, w, node_n, pn;
+    __device__ __forceinline__ int predoff(int i) const { return __ldg(&rowmeta[i].x); }
+    __device__ __forceinline__ int base(int i) const { return __ldg(&rowmeta[i].y) & 0xff; }
+    __device__ __forceinline__ int remain(int i) const { return __ldg(&rowmeta[i].y) >> 8; }
 };
 __device__ __forceinline__ JobView open_job(const uint8_t *blob) {
     const PoaJobHeader *h = reinterpret_cast<const PoaJobHeader *>(blob);
     JobView v;
     v.n_rows = h->n_rows; v.qlen = h->qlen; v.w = h->w; v.node_n = h->node_n; v.pn = h->pn;
-    v.base = blob + h->off_base;
-    v.remain = reinterpret_cast<const int32_t *>(blob + h->off_remain);
-    v.predoff = reinterpret_cast<const int32_t *>(blob + h->off_predoff);
+    v.rowmeta = reinterpret_cast<const int2 *>(blob + h->off_rowmeta);
     v.pred = reinterpret_cast<const int32_t *>(blob + h->off_pred);
     v.predscore = h->off_predscore >= 0 ? reinterpret_cast<const int32_t *>(blob + h->off_predscore) : nullptr;
-    v.nodeid = reinterpret_cast<const int32_t *>(blob + h->off_nodeid);
     v.live = h->off_live >= 0 ? blob + h->off_live : nullptr;
     v.qs = blob + h->off_qs;
     return v;
@@ -182,10 +182,10 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         const int h_ij = in_j ? (int)rp[j] : NEG;
         if (MODE == LOCAL && h_ij == 0) break;
         start_i = i; start_j = j;
-        const int id = jv.nodeid[i];
-        const int rb = jv.base[i], qc = jv.qs[j];
+        const int id = i;                       /* the host maps DP rows back to node ids */
+        const int rb = jv.base(i), qc = jv.qs[j];
         const int s = mat_s[rb * m + qc];
-        const int pb = jv.predoff[i], np = jv.predoff[i + 1] - pb;
+        const int pb = jv.predoff(i), np = jv.predoff(i + 1) - pb;
         const BtPred pc0 = bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, lane, j);
         int hit = 0;
 
@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
     const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
     const bool banded = w >= 0;
-    const bool use_remain = banded || (MODE == EXTEND && prm->zdrop > 0);
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
     const int pnv = jv.pn;
     const int zr = prm->zero;            /* run-time 0: keeps ptxas from fusing the LOCAL floors into VIMNMX.RELU */
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     /* ---------------- row 0 (the begin node): reference first_dp, :582-688 ---------------- */
     {
         int end0 = qlen;
-        if (banded) end0 = min(qlen, max(0, qlen - __ldg(jv.remain)) + w);
+        if (banded) end0 = min(qlen, max(0, qlen - jv.remain(0)) + w);
         const int g1 = end0 >> 3, ngrp = g1 + 1;
         if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
@@ -387,15 +386,14 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
      * one row ahead so that its latency never sits on the row-to-row dependency chain. */
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
-        pb = __ldg(jv.predoff + 1); pe = __ldg(jv.predoff + 2); rbase = __ldg(jv.base + 1);
-        if (use_remain) rem = __ldg(jv.remain + 1);
+        { const int2 m1 = __ldg(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
         if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
     }
+    int nx_y = n_rows > 3 ? __ldg(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
         if (i + 1 < n_rows - 1) {
-            n_pe = __ldg(jv.predoff + i + 2); n_rbase = __ldg(jv.base + i + 1);
-            if (use_remain) n_rem = __ldg(jv.remain + i + 1);
+            { const int2 m2 = __ldg(jv.rowmeta + i + 2); n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y; }
             if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
         }
         const int np = pe - pb;
@@ -625,7 +623,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         } else if (MODE == EXTEND) {
             if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_right; best_row = i; }
             else if (prm->zdrop > 0) {
-                const int delta = __ldg(jv.remain + best_row) - rem;
+                const int delta = jv.remain(best_row) - rem;
                 if (best_score - row_max > prm->zdrop + e1 * abs(delta - (row_right - best_j))) stop = true;
             }
         }
@@ -636,7 +634,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
 
     /* ---------------- global mode: best end cell among the SINK's predecessors ---------------- */
     if (MODE == GLOBAL) {
-        const int sb = jv.predoff[n_rows - 1], sn = jv.predoff[n_rows] - sb;
+        const int sb = jv.predoff(n_rows - 1), sn = jv.predoff(n_rows) - sb;
         for (int k = 0; k < sn; ++k) {
             const int prow = jv.pred[sb + k];
             const PoaRowInfo pi = rowinfo[prow];
@@ -743,7 +741,6 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
     PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
     const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
     const bool banded = w >= 0;
-    const bool use_remain = banded || (MODE == EXTEND && prm->zdrop > 0);
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
     const int pnv = jv.pn;
     const unsigned zr2 = (unsigned)prm->zero;     /* run-time packed zero (see the RELU note in poa_align_kernel) */
@@ -781,7 +778,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
     /* ---------------- row 0 ---------------- */
     {
         int end0 = qlen;
-        if (banded) end0 = min(qlen, max(0, qlen - __ldg(jv.remain)) + w);
+        if (banded) end0 = min(qlen, max(0, qlen - jv.remain(0)) + w);
         const int g1 = end0 >> 3, ngrp = g1 + 1;
         if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
@@ -823,15 +820,14 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
 
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
-        pb = __ldg(jv.predoff + 1); pe = __ldg(jv.predoff + 2); rbase = __ldg(jv.base + 1);
-        if (use_remain) rem = __ldg(jv.remain + 1);
+        { const int2 m1 = __ldg(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
         if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
     }
+    int nx_y = n_rows > 3 ? __ldg(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
         if (i + 1 < n_rows - 1) {
-            n_pe = __ldg(jv.predoff + i + 2); n_rbase = __ldg(jv.base + i + 1);
-            if (use_remain) n_rem = __ldg(jv.remain + i + 1);
+            { const int2 m2 = __ldg(jv.rowmeta + i + 2); n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y; }
             if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
         }
         const int np = pe - pb;
@@ -1076,7 +1072,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
         } else if (MODE == EXTEND) {
             if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_right; best_row = i; }
             else if (prm->zdrop > 0) {
-                const int delta = __ldg(jv.remain + best_row) - rem;
+                const int delta = jv.remain(best_row) - rem;
                 if (best_score - row_max > prm->zdrop + e1 * abs(delta - (row_right - best_j))) stop = true;
             }
         }
@@ -1086,7 +1082,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
     }
 
     if (MODE == GLOBAL) {
-        const int sb = jv.predoff[n_rows - 1], sn = jv.predoff[n_rows] - sb;
+        const int sb = jv.predoff(n_rows - 1), sn = jv.predoff(n_rows) - sb;
         for (int k = 0; k < sn; ++k) {
             const int prow = jv.pred[sb + k];
             const PoaRowInfo pi = rowinfo[prow];
