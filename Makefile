@@ -9,7 +9,7 @@ LIBDIR  := abpoa_b200/lib
 LIB     := $(LIBDIR)/libabpoa_b200.so
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 CFLAGS  := -O2 -g -Wall -Wextra -Wno-unused-parameter -fPIC -Iinclude -I$(CSRC) -std=gnu11 -pthread
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-pthread -Iinclude -I$(CSRC)
+NVFLAGS := $(KPROF) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-pthread -Iinclude -I$(CSRC)
 
 C_SRCS  := $(wildcard $(CSRC)/*.c)
 CU_SRCS := $(wildcard $(CSRC)/*.cu)

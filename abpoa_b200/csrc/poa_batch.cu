@@ -421,6 +421,10 @@ void worker_main(Worker wk) {
         const poa_engine_stats *st = poa_dev_ctx_stats(wk.ctx);
         fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f span %.0f ms\n",
                 poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3], poa_prof_ms[4]);
+        if (st->prof[0] + st->prof[1] > 0)
+            fprintf(stderr, "[kernel-phases, cycles/alignment] setup %.0fk pred %.0fk compute %.0fk store %.0fk rowmax %.0fk tail+prefetch %.0fk\n",
+                    st->prof[0] / 1e3 / st->alignments, st->prof[1] / 1e3 / st->alignments, st->prof[2] / 1e3 / st->alignments,
+                    st->prof[3] / 1e3 / st->alignments, st->prof[4] / 1e3 / st->alignments, st->prof[5] / 1e3 / st->alignments);
         fprintf(stderr, "[worker] setup %.0f plan %.0f run %.0f (kernel %.0f, fill %.0f, wait %.0f, copy %.0f) fuse %.0f finish %.0f ms\n",
                 pc.setup, pc.plan, pc.run, st->kernel_ms, st->fill_ms, st->wait_ms, st->copy_ms, pc.fuse, pc.finish);
     }

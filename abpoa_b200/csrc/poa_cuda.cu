@@ -351,7 +351,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
             cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells;
             c->capture(c->capture_user, &cj);
         }
-        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; }
+        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; for (int z = 0; z < 6; ++z) c->stats.prof[z] += resv[t].prof[z]; }
     }
 }
 

@@ -50,6 +50,7 @@ typedef struct PoaResultDev {
     uint64_t plane_units_used;          /* 8-cell units of plane storage consumed           */
     int64_t fwd_clk, bt_clk;            /* SM clock cycles spent in the forward DP / the backtrace */
     uint64_t t_start_ns, t_end_ns;      /* %globaltimer at entry / exit of the job's warp          */
+    int64_t prof[6];                    /* optional per-phase SM cycles (ABPOA kernel built with -DPOA_KPROF) */
 } PoaResultDev;
 
 /* device pointers of one job */

@@ -672,6 +672,15 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
  *   - band edges are applied with two 16-byte mask vectors from shared-memory tables.
  * The launcher uses this kernel whenever scores provably fit (see poa_p16_ok); a run-time guard
  * (row maxima drifting towards the rails) makes the job fall back to the 32-bit kernel. */
+#ifdef POA_KPROF
+#define KP_DECL long long kp[6] = {0,0,0,0,0,0}; long long kp_t = clock64();
+#define KP(n) { const long long t_ = clock64(); kp[n] += t_ - kp_t; kp_t = t_; }
+#define KP_OUT(res) { for (int z_ = 0; z_ < 6; ++z_) (res).prof[z_] = kp[z_]; }
+#else
+#define KP_DECL
+#define KP(n)
+#define KP_OUT(res)
+#endif
 #define NEGP (-30000)
 #define NEGP2 0x8AD08AD0u
 
@@ -711,9 +720,8 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
     int *mat_s = reinterpret_cast<int *>(dyn_smem);
     uint4 *cap_lo = reinterpret_cast<uint4 *>(dyn_smem + POA_MAX_M * POA_MAX_M * sizeof(int));   /* [9]: first n cells masked */
     uint4 *cap_hi = cap_lo + 9;                                                                    /* [9]: last n cells masked  */
-    PoaRowInfo *ring_info = reinterpret_cast<PoaRowInfo *>(cap_hi + 9);
-    uint32_t *ring_off = reinterpret_cast<uint32_t *>(ring_info + ring_rows);
-    ST *ring_data = reinterpret_cast<ST *>(reinterpret_cast<uint8_t *>(ring_off) + (((size_t)ring_rows * 4 + 15) & ~(size_t)15));
+    uint4 *ring_meta = cap_hi + 9;                       /* [ring_rows] {beg, end, (left+1)|(right+1)<<16, plane offset} */
+    ST *ring_data = reinterpret_cast<ST *>(ring_meta + ring_rows);
     const int rmask = ring_rows - 1, ring_groups = ring_cells >> 3;
 
     const int lane = threadIdx.x;
@@ -811,47 +819,66 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
         }
         if (lane == 0) {
             PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0;
-            rowinfo[0] = r0; rowoff[0] = 0; ring_info[0] = r0; ring_off[0] = 0;
+            rowinfo[0] = r0; rowoff[0] = 0; ring_meta[0] = make_uint4(0u, (unsigned)end0, 1u | (1u << 16), 0u);
         }
         cursor = (uint64_t)ngrp * PL::N;
         cells += end0 + 1; max_band = end0 + 1;
         __syncwarp();
     }
 
+    /* ---------------- rows 1 .. n_rows-2 ----------------
+     * Lean row loop: per-row graph metadata arrives one row ahead as a single 8-byte load; lane k
+     * owns predecessor k and publishes what the other lanes need about it in two packed words
+     * (two shuffles per predecessor); the ring is addressed with 32-bit shared-memory offsets. */
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_data);
+    const uint32_t ring_row_bytes = (uint32_t)(RN * ring_cells * 2), ring_plane_bytes = (uint32_t)(ring_cells * 2);
+    const int pn_shift = pnv == 16 ? 4 : 3;
+    const uint32_t cap32 = jd.plane_cap_units > 0xffffffffull ? 0xffffffffu : (uint32_t)jd.plane_cap_units;
+    uint32_t cur32 = (uint32_t)cursor;
+    const bool has_ps = jv.predscore != nullptr;
+
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
         { const int2 m1 = __ldg(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
-        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
+        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (has_ps) myps = __ldg(jv.predscore + pb + lane); }
     }
     int nx_y = n_rows > 3 ? __ldg(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
+    KP_DECL
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
+        KP(5)
         int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
         if (i + 1 < n_rows - 1) {
-            { const int2 m2 = __ldg(jv.rowmeta + i + 2); n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y; }
-            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
+            const int2 m2 = __ldg(jv.rowmeta + i + 2);
+            n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y;
+            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (has_ps) n_myps = __ldg(jv.predscore + pe + lane); }
         }
         const int np = pe - pb;
         if (!(jv.live && !__ldg(jv.live + i))) {
 
-        int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
+        /* ---- predecessor k on lane k: band hints + the two broadcast words ---- */
+        unsigned wA = 0, wB = 0;                      /* A: pg0 | png<<12 | near<<25 | slot<<26 ; B: plane offset (8-cell units) */
+        int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
+        if (lane < np) {
+            const int prow = mypred;
+            const bool near = (i - prow) <= rmask;
+            uint4 mi;
+            if (near) mi = ring_meta[prow & rmask];
+            else { const PoaRowInfo pi = rowinfo[prow]; mi = make_uint4((unsigned)pi.beg, (unsigned)pi.end, (unsigned)(pi.left + 1) | ((unsigned)(pi.right + 1) << 16), rowoff[prow]); }
+            l1 = (int)(mi.z & 0xffffu); r1 = (int)(mi.z >> 16); b1 = (int)mi.x;
+            const unsigned pg0 = mi.x >> 3, png = (mi.y >> 3) - pg0 + 1;
+            wA = pg0 | (png << 12) | ((unsigned)near << 25) | ((unsigned)(prow & rmask) << 26);
+            wB = mi.w;
+        }
         int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
-        for (int kb = 0; kb < np; kb += 32) {
-            const int k = kb + lane;
-            int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
-            if (k < np) {
-                const int prow = kb == 0 ? mypred : __ldg(jv.pred + pb + k);
-                const bool near = (i - prow) <= rmask;
-                const PoaRowInfo pi = near ? ring_info[prow & rmask] : rowinfo[prow];
-                l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
-                if (kb == 0) {
-                    pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_ps = myps;
-                    pk_off = near ? ring_off[prow & rmask] : rowoff[prow];
-                }
-            }
-            if (banded) {
-                ml = min(ml, __reduce_min_sync(FULL, l1));
-                mr = max(mr, __reduce_max_sync(FULL, r1));
-                min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b1));
+        if (banded) {
+            ml = min(ml, __reduce_min_sync(FULL, l1));
+            mr = max(mr, __reduce_max_sync(FULL, r1));
+            min_pre_beg = __reduce_min_sync(FULL, b1);
+            for (int kb = 32; kb < np; kb += 32) {          /* more than 32 predecessors: practically never */
+                const int k = kb + lane;
+                int l2 = INT32_MAX, r2 = INT32_MIN, b2 = INT32_MAX;
+                if (k < np) { const PoaRowInfo pi = rowinfo[__ldg(jv.pred + pb + k)]; l2 = pi.left + 1; r2 = pi.right + 1; b2 = pi.beg; }
+                ml = min(ml, __reduce_min_sync(FULL, l2)); mr = max(mr, __reduce_max_sync(FULL, r2)); min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b2));
             }
         }
         int beg = 0, end = qlen;
@@ -859,23 +886,26 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
             const int r = qlen - rem;
             beg = max(0, min(ml, r) - w);
             end = min(qlen, max(mr, r) + w);
-            if (np > 0 && beg / pnv < min_pre_beg / pnv) beg = min_pre_beg;
+            if (np > 0 && (beg >> pn_shift) < (min_pre_beg >> pn_shift)) beg = min_pre_beg;   /* reference's vector-granular clamp */
         }
         const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
-        if (cursor + (uint64_t)ngrp * PL::N > jd.plane_cap_units || cursor + (uint64_t)ngrp * PL::N > 0xffffffffull) {
-            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; signal_done(jd); }
+        const uint32_t need = (uint32_t)ngrp * PL::N;
+        if (need > cap32 - cur32) {
+            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cur32; *jd.result = res; signal_done(jd); }
             return;
         }
-        const uint32_t my_off = (uint32_t)cursor;
-        cursor += (uint64_t)ngrp * PL::N;
+        const uint32_t my_off = cur32;
+        cur32 += need;
         ST *rowp = planes + (size_t)my_off * POA_GROUP;
-        ST *ringp = ring_data + (size_t)(i & rmask) * RN * ring_cells;
+        const size_t gplane = (size_t)ngrp * POA_GROUP;                 /* elements between planes in HBM */
+        const uint32_t my_ring_s = ring_s + (uint32_t)(i & rmask) * ring_row_bytes;
         cells += (end >= beg) ? (end - beg + 1) : 0;
         max_band = max(max_band, end - beg + 1);
         const int16_t *qrow = qp + (size_t)rbase * qstride;
 
         int carry1 = 2 * NEG, carry2 = 2 * NEG;
         int row_max = NEG, row_left = -1, row_right = -1;
+        KP(0)
 
         for (int gp = g0; gp <= g1; gp += 32) {
             const int g = gp + lane;
@@ -885,49 +915,59 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
             unsigned M[4], X1[4], X2[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { M[k] = NEGP2; X1[k] = NEGP2; X2[k] = NEGP2; }
+            /* lane 0's left neighbour (cell 8g-1) lives in the previous group: only needed when that
+             * cell is inside the band, i.e. on later passes or when the band starts on a group boundary */
+            const bool fix_left = (gp > g0) || ((beg & 7) == 0);
 
             for (int kb = 0; kb < np; kb += 32) {
-                int c_row = pk_row, c_beg = pk_beg, c_end = pk_end, c_ps = pk_ps; uint32_t c_off = pk_off;
+                unsigned cA = wA, cB = wB; int c_ps = myps;
                 if (kb > 0) {
-                    const int k = kb + lane; c_row = -1;
+                    const int k = kb + lane; cA = 0; cB = 0; c_ps = 0;
                     if (k < np) {
-                        c_row = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
-                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? __ldg(jv.predscore + pb + k) : 0;
+                        const int prow = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[prow];
+                        const unsigned pg0 = (unsigned)pi.beg >> 3, png = ((unsigned)pi.end >> 3) - pg0 + 1;
+                        cA = pg0 | (png << 12); cB = rowoff[prow]; if (has_ps) c_ps = __ldg(jv.predscore + pb + k);
                     }
                 }
                 const int nk = min(32, np - kb);
                 for (int k = 0; k < nk; ++k) {
-                    const int p_row = __shfl_sync(FULL, c_row, k);
-                    const int p_beg = __shfl_sync(FULL, c_beg, k), p_end = __shfl_sync(FULL, c_end, k);
-                    const uint32_t p_off = __shfl_sync(FULL, c_off, k);
-                    const int pg0 = p_beg >> 3, pg1 = p_end >> 3, png = pg1 - pg0 + 1;
-                    const bool near = (i - p_row) <= rmask;
-                    const ST *ph = planes + (size_t)p_off * POA_GROUP;
-                    const ST *rh = ring_data + (size_t)(p_row & rmask) * RN * ring_cells;
-                    uint4 hp = make_uint4(NEGP2, NEGP2, NEGP2, NEGP2), ep1 = hp, ep2 = hp;
-                    const bool inr = active && g >= pg0 && g <= pg1;
+                    const unsigned A = __shfl_sync(FULL, cA, k), B = __shfl_sync(FULL, cB, k);
+                    const int pg0 = (int)(A & 0xfffu), png = (int)((A >> 12) & 0x1fffu);
+                    const bool near = (A >> 25) & 1u;
                     const int rel = g - pg0;
-                    if (inr && near && rel < ring_groups) {
-                        const ST *q = rh + (size_t)rel * POA_GROUP;
-                        hp = *reinterpret_cast<const uint4 *>(q);
-                        if (GAP != LG) ep1 = *reinterpret_cast<const uint4 *>(q + ring_cells);
-                        if (GAP == CG) ep2 = *reinterpret_cast<const uint4 *>(q + 2 * ring_cells);
-                    } else if (inr) {
-                        const ST *q = ph + (size_t)rel * POA_GROUP;
-                        hp = *reinterpret_cast<const uint4 *>(q);
-                        if (GAP != LG) ep1 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E1 * png * POA_GROUP);
-                        if (GAP == CG) ep2 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E2 * png * POA_GROUP);
+                    const bool inr = active && (unsigned)rel < (unsigned)png;
+                    uint4 hp = make_uint4(NEGP2, NEGP2, NEGP2, NEGP2), ep1 = hp, ep2 = hp;
+                    const uint32_t prs = ring_s + (A >> 26) * ring_row_bytes;        /* predecessor's ring row */
+                    const ST *ph = planes + (size_t)B * POA_GROUP;                     /* predecessor's HBM row  */
+                    if (inr) {
+                        if (near && rel < ring_groups) {
+                            const uint32_t a = prs + (uint32_t)rel * 16u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hp.x), "=r"(hp.y), "=r"(hp.z), "=r"(hp.w) : "r"(a));
+                            if (GAP != LG) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ep1.x), "=r"(ep1.y), "=r"(ep1.z), "=r"(ep1.w) : "r"(a + ring_plane_bytes));
+                            if (GAP == CG) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ep2.x), "=r"(ep2.y), "=r"(ep2.z), "=r"(ep2.w) : "r"(a + 2 * ring_plane_bytes));
+                        } else {
+                            const ST *q = ph + (size_t)rel * POA_GROUP;
+                            const size_t pp = (size_t)png * POA_GROUP;
+                            hp = *reinterpret_cast<const uint4 *>(q);
+                            if (GAP != LG) ep1 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E1 * pp);
+                            if (GAP == CG) ep2 = *reinterpret_cast<const uint4 *>(q + (size_t)PL::E2 * pp);
+                        }
                     }
                     unsigned prev = __shfl_up_sync(FULL, hp.w, 1);
                     if (lane == 0) {
-                        const int relm = rel - 1;
                         int hm1 = NEGP;
-                        if (relm >= 0 && relm < png) hm1 = (near && relm < ring_groups) ? (int)rh[(size_t)relm * POA_GROUP + 7] : (int)ph[(size_t)relm * POA_GROUP + 7];
+                        if (fix_left) {
+                            const int relm = rel - 1;
+                            if ((unsigned)relm < (unsigned)png) {
+                                if (near && relm < ring_groups) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(prs + (uint32_t)relm * 16u + 14u)); hm1 = (int)(short)v; }
+                                else hm1 = (int)ph[(size_t)relm * POA_GROUP + 7];
+                            }
+                        }
                         if (MODE == LOCAL && g == 0) hm1 = 0;
                         prev = (unsigned)hm1 << 16;
                     }
                     unsigned d0 = sh1(prev, hp.x), d1 = sh1(hp.x, hp.y), d2 = sh1(hp.y, hp.z), d3 = sh1(hp.z, hp.w);
-                    if (jv.predscore) {
+                    if (has_ps) {
                         const int ps = __shfl_sync(FULL, c_ps, k);
                         const unsigned ps2 = pk(ps, ps);
                         d0 = __viaddmax_s16x2(d0, ps2, NEGP2); d1 = __viaddmax_s16x2(d1, ps2, NEGP2);
@@ -955,6 +995,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
                 }
             }
 
+            KP(1)
             /* band-edge masks of this lane's 8 cells */
             const int nlo = min(max(beg - g * 8, 0), 8), nhi = min(max(g * 8 + 7 - end, 0), 8);
             const uint4 clo = cap_lo[nlo], chi = cap_hi[nhi];
@@ -1020,27 +1061,28 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
                 }
             }
 
+            KP(2)
             if (active) {
                 const int rel = g - g0;
-                const uint4 hv = make_uint4(H[0], H[1], H[2], H[3]);
                 if (rel < ring_groups) {
-                    ST *rq = ringp + (size_t)rel * POA_GROUP;
-                    *reinterpret_cast<uint4 *>(rq) = hv;
-                    if (GAP != LG) *reinterpret_cast<uint4 *>(rq + ring_cells) = make_uint4(E1o[0], E1o[1], E1o[2], E1o[3]);
-                    if (GAP == CG) *reinterpret_cast<uint4 *>(rq + 2 * ring_cells) = make_uint4(E2o[0], E2o[1], E2o[2], E2o[3]);
+                    const uint32_t a = my_ring_s + (uint32_t)rel * 16u;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]) : "memory");
+                    if (GAP != LG) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + ring_plane_bytes), "r"(E1o[0]), "r"(E1o[1]), "r"(E1o[2]), "r"(E1o[3]) : "memory");
+                    if (GAP == CG) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + 2 * ring_plane_bytes), "r"(E2o[0]), "r"(E2o[1]), "r"(E2o[2]), "r"(E2o[3]) : "memory");
                 }
                 ST *q = rowp + (size_t)rel * POA_GROUP;
-                *reinterpret_cast<uint4 *>(q) = hv;
+                *reinterpret_cast<uint4 *>(q) = make_uint4(H[0], H[1], H[2], H[3]);
                 if (GAP != LG) {
-                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E1 * ngrp * POA_GROUP) = make_uint4(E1o[0], E1o[1], E1o[2], E1o[3]);
-                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F1 * ngrp * POA_GROUP) = make_uint4(F1[0], F1[1], F1[2], F1[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E1 * gplane) = make_uint4(E1o[0], E1o[1], E1o[2], E1o[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F1 * gplane) = make_uint4(F1[0], F1[1], F1[2], F1[3]);
                 }
                 if (GAP == CG) {
-                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E2 * ngrp * POA_GROUP) = make_uint4(E2o[0], E2o[1], E2o[2], E2o[3]);
-                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F2 * ngrp * POA_GROUP) = make_uint4(F2[0], F2[1], F2[2], F2[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::E2 * gplane) = make_uint4(E2o[0], E2o[1], E2o[2], E2o[3]);
+                    *reinterpret_cast<uint4 *>(q + (size_t)PL::F2 * gplane) = make_uint4(F2[0], F2[1], F2[2], F2[3]);
                 }
             }
 
+            KP(3)
             /* row maximum with first / last arg-max; masked cells hold NEGP and never win against a real cell */
             {
                 const int lmax = active ? lane_max8(H) : NEGP;
@@ -1049,10 +1091,11 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
                 if (bm) {
                     int lfirst = -1, llast = -1;
                     if (lmax == pm) {
+                        /* one bit per cell that equals the row maximum */
+                        unsigned eq = 0;
 #pragma unroll
-                        for (int k = 3; k >= 0; --k) { if (hi16(H[k]) == pm) lfirst = g * 8 + 2 * k + 1; if (lo16(H[k]) == pm) lfirst = g * 8 + 2 * k; }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { if (lo16(H[k]) == pm) llast = g * 8 + 2 * k; if (hi16(H[k]) == pm) llast = g * 8 + 2 * k + 1; }
+                        for (int k = 0; k < 4; ++k) { eq |= (unsigned)(lo16(H[k]) == pm) << (2 * k); eq |= (unsigned)(hi16(H[k]) == pm) << (2 * k + 1); }
+                        lfirst = g * 8 + __ffs(eq) - 1; llast = g * 8 + 31 - __clz(eq);
                     }
                     const int pl = __shfl_sync(FULL, lfirst, __ffs(bm) - 1);
                     const int pr = __shfl_sync(FULL, llast, 31 - __clz(bm));
@@ -1061,9 +1104,10 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
                 }
             }
         }
+        KP(4)
         if (lane == 0) {
+            ring_meta[i & rmask] = make_uint4((unsigned)beg, (unsigned)end, (unsigned)(row_left + 1) | ((unsigned)(row_right + 1) << 16), my_off);
             PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
-            ring_info[i & rmask] = ri; ring_off[i & rmask] = my_off;
             rowinfo[i] = ri; rowoff[i] = my_off;
         }
         guard_lo |= (row_max < -14000); guard_hi |= (row_max > 29000);
@@ -1080,6 +1124,8 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
         }   /* live row */
         pb = pe; pe = n_pe; rbase = n_rbase; rem = n_rem; mypred = n_mypred; myps = n_myps;
     }
+    cursor = cur32;
+    KP_OUT(res)
 
     if (MODE == GLOBAL) {
         const int sb = jv.predoff(n_rows - 1), sn = jv.predoff(n_rows) - sb;
