@@ -32,7 +32,7 @@
 #include "poa_internal.h"
 #include "poa_engine.h"
 
-struct CapturedJob { uint8_t *blob; size_t bytes; int n_rows, qlen, w, n_pred, bits, best_score, n_ops; int64_t cells; };
+struct CapturedJob { uint8_t *blob; size_t bytes; int n_rows, qlen, w, n_pred, bits, best_score, n_ops; int64_t cells; uint64_t plane_units; };
 
 struct abpoa_gpu_batch {
     std::mutex cap_mu; std::vector<CapturedJob> captured;
@@ -92,7 +92,7 @@ static void capture_cb(void *user, const poa_captured_job *cj) {
     abpoa_gpu_batch *e = (abpoa_gpu_batch *)user;
     CapturedJob c; c.bytes = cj->bytes; c.blob = (uint8_t *)poa_xmalloc(cj->bytes); memcpy(c.blob, cj->blob, cj->bytes);
     c.n_rows = cj->n_rows; c.qlen = cj->qlen; c.w = cj->w; c.n_pred = cj->n_pred; c.bits = cj->bits;
-    c.best_score = cj->best_score; c.n_ops = cj->n_ops; c.cells = cj->cells;
+    c.best_score = cj->best_score; c.n_ops = cj->n_ops; c.cells = cj->cells; c.plane_units = cj->plane_units;
     std::lock_guard<std::mutex> lk(e->cap_mu);
     e->captured.push_back(c);
 }
@@ -125,7 +125,8 @@ extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int wa
         size_t end = pos, bytes = 0;
         while (end < jobs.size() && jobs[end].bits == jobs[pos].bits && end - pos < 4096) {
             const size_t per_row = jobs[end].w >= 0 ? (size_t)((2 * jobs[end].w + 1 + 32 + 7) / 8 + 2) : (size_t)((jobs[end].qlen + 8) / 8 + 1);
-            const size_t b = per_row * P * (size_t)jobs[end].n_rows * 8 * (jobs[end].bits / 8);
+            size_t b = per_row * P * (size_t)jobs[end].n_rows * 8 * (jobs[end].bits == 32 ? 4 : 2);
+            if (jobs[end].plane_units * 8 * (jobs[end].bits == 32 ? 4 : 2) > b) b = jobs[end].plane_units * 8 * (jobs[end].bits == 32 ? 4 : 2);
             if (end > pos && bytes + b > wave_bytes) break;
             bytes += b; ++end;
         }
@@ -139,7 +140,7 @@ extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int wa
         for (auto &wv : waves) {
             const size_t n = wv.second - wv.first;
             rj.resize(n); sc.resize(n); no.resize(n); ce.resize(n);
-            for (size_t t = 0; t < n; ++t) { const CapturedJob &cj = jobs[wv.first + t]; rj[t].d_blob = d_blobs + off[wv.first + t]; rj[t].n_rows = cj.n_rows; rj[t].qlen = cj.qlen; rj[t].w = cj.w; }
+            for (size_t t = 0; t < n; ++t) { const CapturedJob &cj = jobs[wv.first + t]; rj[t].d_blob = d_blobs + off[wv.first + t]; rj[t].n_rows = cj.n_rows; rj[t].qlen = cj.qlen; rj[t].w = cj.w; rj[t].plane_units = cj.plane_units; }
             ms += poa_dev_ctx_replay_launch(c, abpt, rj.data(), (int)n, jobs[wv.first].bits, sc.data(), no.data(), ce.data());
             for (size_t t = 0; t < n; ++t) { const CapturedJob &cj = jobs[wv.first + t]; if (sc[t] != cj.best_score || no[t] != cj.n_ops || ce[t] != cj.cells) ++mism; }
         }

@@ -348,7 +348,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
             poa_captured_job cj;
             cj.blob = c->h_in + blob_off[t]; cj.bytes = j.plan.bytes; cj.n_rows = j.plan.n_rows; cj.qlen = j.plan.qlen; cj.w = j.plan.w;
             cj.n_pred = ((const int32_t *)(cj.blob + ((const PoaJobHeader *)cj.blob)->off_rowmeta))[2 * j.plan.n_rows];
-            cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells;
+            cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells; cj.plane_units = resv[t].plane_units_used;
             c->capture(c->capture_user, &cj);
         }
         if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; for (int z = 0; z < 6; ++z) c->stats.prof[z] += resv[t].prof[z]; }
@@ -517,6 +517,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         if (bits == 15) work_bytes += al256((size_t)abpt->m * ((((size_t)rj[t].qlen + 1 + 7) & ~(size_t)7) + 8) * 2);
         poa_job tmp; memset(&tmp, 0, sizeof tmp); tmp.plan.n_rows = rj[t].n_rows; tmp.plan.qlen = rj[t].qlen; tmp.plan.w = rj[t].w;
         units[t] = plane_units_for(&tmp, abpt->gap_mode, 0);
+        if (rj[t].plane_units > units[t]) units[t] = rj[t].plane_units;          /* a job that needed the generous slab */
         plane_off[t] = tot_units; tot_units += units[t];
         const int bc = rj[t].w >= 0 ? (2 * rj[t].w + 1 + 40 + 7) / 8 * 8 : (rj[t].qlen + 1 + 7) / 8 * 8 + 8;
         if (bc > band_cells) band_cells = bc;

@@ -19,7 +19,7 @@ typedef struct {
     /* out (valid inside the sink callback only) */
     int status, bits, ref_bits;     /* bits: kernel variant used (15 packed int16, 16, 32); ref_bits: the reference's width */
     int best_score, best_i, best_j, start_i, start_j, n_aln_bases, n_matched_bases, max_band;
-    int64_t cells;
+    int64_t cells; uint64_t plane_units;
     int n_ops; const uint64_t *ops; /* graph-CIGAR words in backtrack (reversed) order        */
     const int32_t *bands;           /* [n_rows][4] when want_bands                            */
 } poa_job;
@@ -31,6 +31,7 @@ typedef struct {
     uint8_t *blob; size_t bytes;
     int n_rows, qlen, w, n_pred, bits;
     int best_score, n_ops; int64_t cells;
+    uint64_t plane_units;           /* 8-cell units of plane storage the job really used */
 } poa_captured_job;
 typedef void (*poa_capture_fn)(void *user, const poa_captured_job *cj);
 
@@ -53,7 +54,7 @@ poa_dev_ctx *poa_dev_ctx_new_on(int dev);
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a);
 void poa_dev_ctx_set_capture(poa_dev_ctx *c, poa_capture_fn fn, void *user);
 /* replay support: run pre-uploaded blobs (device pointers) as one launch on the context's stream */
-typedef struct { const uint8_t *d_blob; int n_rows, qlen, w; } poa_replay_job;
+typedef struct { const uint8_t *d_blob; int n_rows, qlen, w; uint64_t plane_units; } poa_replay_job;
 double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const poa_replay_job *jobs, int n, int bits,
                                  int32_t *out_score, int32_t *out_nops, int64_t *out_cells);
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint);

@@ -54,6 +54,9 @@ static const char POA_AA_ORDER[] = "ACGTNBDEFHIJKLMOPQRSUVWXYZ";
 
 static void __attribute__((constructor)) poa_build_alphabets(void) {
     int c, k;
+    /* the batch engine drives up to 32 CUDA streams: give each its own hardware work queue
+     * (read by the driver when the context is created; a user setting wins) */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     for (c = 0; c < 256; ++c) {
         ab_nt4_table[c] = 4; ab_nt256_table[c] = 'N';
         ab_aa26_table[c] = 26; ab_aa256_table[c] = '*';

@@ -34,6 +34,9 @@ import threading
 import time
 from pathlib import Path
 
+# one hardware work queue per stream of the batch engine (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -194,8 +197,9 @@ def main():
     packed = PackedGroups(groups)
     lib = capi.product()
     abpt = make_para(lib, w.cfg)
-    workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(64, (os.cpu_count() or 8) // max(world, 1)))
+    workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(32, (os.cpu_count() or 8) // 2 // max(world, 1)))
     gpl = int(os.environ.get("ABPOA_GPU_GROUPS_PER_LAUNCH", "0")) or max(1, min(32, (n_groups + workers - 1) // workers))
+    os.environ.setdefault("ABPOA_GPU_CPU_BASE", str(local_rank * workers))      # disjoint cores per rank
     eng = BatchEngine(device=local_rank, n_workers=workers, groups_per_launch=gpl)
 
     for _ in range(args.warmup):
