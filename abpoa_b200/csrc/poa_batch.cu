@@ -37,6 +37,8 @@ struct CapturedJob { uint8_t *blob; size_t bytes; int n_rows, qlen, w, n_pred, b
 struct abpoa_gpu_batch {
     std::mutex cap_mu; std::vector<CapturedJob> captured;
     int dev, n_workers, groups_per_launch;
+    int pipe_depth;                 /* sub-chunks (stream contexts) each worker keeps in flight */
+    int fast_order;                 /* spliced topological order in global mode (ABPOA_GPU_EXACT_ORDER=1 turns it off) */
     poa_arena *arena;
     std::vector<poa_dev_ctx *> ctx;
     double wall_ms;
@@ -54,6 +56,7 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     abpoa_gpu_batch *e = new abpoa_gpu_batch();
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     e->dev = device;
+    { const char *eo = getenv("ABPOA_GPU_EXACT_ORDER"); e->fast_order = !(eo && *eo == '1'); }
     if (cudaSetDevice(device) != cudaSuccess) poa_die("libabpoa_b200", "cannot select CUDA device %d", device);
     unsigned hc = std::thread::hardware_concurrency();
     if (n_workers <= 0) {
@@ -64,7 +67,7 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     }
     if (groups_per_launch <= 0) {
         const char *env = getenv("ABPOA_GPU_GROUPS_PER_LAUNCH");
-        groups_per_launch = env && *env ? atoi(env) : 32;
+        groups_per_launch = env && *env ? atoi(env) : 0;      /* 0: chosen per batch call from the number of groups */
     }
     e->n_workers = n_workers; e->groups_per_launch = groups_per_launch;
     size_t free_b = 0, total_b = 0;
@@ -74,7 +77,13 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     const char *env = getenv("ABPOA_GPU_ARENA_MB");
     if (env && *env) want = (size_t)atoll(env) << 20;
     e->arena = poa_arena_new(device, want);
-    for (int w = 0; w < n_workers; ++w) {
+    {
+        const char *pd = getenv("ABPOA_GPU_PIPE_DEPTH");
+        e->pipe_depth = pd && *pd ? atoi(pd) : 4;
+        if (e->pipe_depth < 1) e->pipe_depth = 1;
+        if (e->pipe_depth > 8) e->pipe_depth = 8;
+    }
+    for (int w = 0; w < e->pipe_depth * n_workers; ++w) {   /* pipe_depth per worker: sub-chunks in flight */
         poa_dev_ctx *c = poa_dev_ctx_new_on(device);
         poa_dev_ctx_use_arena(c, e->arena);
         e->ctx.push_back(c);
@@ -232,8 +241,8 @@ void pin_worker(int w) {
 
 struct Worker {
     int index;
-    abpoa_gpu_batch *eng; poa_dev_ctx *ctx; abpoa_para_t *abpt; int flags;
-    std::atomic<int> *next_chunk; int n_groups; const abpoa_gpu_group_t *groups; abpoa_gpu_group_result_t *results;
+    abpoa_gpu_batch *eng; poa_dev_ctx *ctx; poa_dev_ctx **ctxs; int n_ctx; abpoa_para_t *abpt; int flags;
+    std::atomic<int> *next_chunk; int G; int n_groups; const abpoa_gpu_group_t *groups; abpoa_gpu_group_result_t *results;
 };
 
 struct SinkCtx { abpoa_para_t *abpt; };
@@ -250,6 +259,9 @@ void sink_to_res(void *user, poa_job *j) {
 
 void finish_group(GroupState &gs, abpoa_para_t *abpt) {
     abpoa_t *ab = gs.ab;
+    /* consensus / MSA and the public index arrays use the reference's Kahn order */
+    poa_graph_set_fast_order(ab->abg, 0);
+    if (ab->abg->node_n > 2) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
     abpoa_gpu_group_result_t *o = gs.out;
     abpoa_output(ab, abpt, NULL);
     const abpoa_cons_t *abc = ab->abc;
@@ -289,7 +301,7 @@ void worker_main(Worker wk) {
     pin_worker(wk.index);
     if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
     abpoa_para_t *abpt = wk.abpt;
-    const int G = wk.eng->groups_per_launch;
+    const int G = wk.G;
     std::vector<abpoa_t *> handles;                     /* reused across chunks */
     SinkCtx sc = { abpt };
     for (;;) {
@@ -311,6 +323,7 @@ void worker_main(Worker wk) {
             int max_len = 1024;
             for (int i = 0; i < n; ++i) if (s.in->seq_lens[i] > max_len) max_len = s.in->seq_lens[i];
             abpoa_reset(s.ab, abpt, max_len);
+            poa_graph_set_fast_order(s.ab->abg, wk.eng->fast_order);
             abpoa_seq_t *abs = s.ab->abs;
             abs->n_seq = n; poa_seq_reserve(abs);
             for (int i = 0; i < n; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
@@ -431,6 +444,163 @@ void worker_main(Worker wk) {
     }
 }
 
+
+/* ------------------------------------------------------------------ pipelined worker
+ * Two half-chunks A and B, each with its own stream context.  While A's kernel runs on the GPU
+ * the thread fuses B's graph-CIGARs and stages B's next launch, and vice versa: host graph work
+ * and device DP overlap inside one thread, and each half's critical chain is
+ * (kernel + its own fusion), not (kernel + fusion of everything the worker owns). */
+struct HalfChunk {
+    poa_dev_ctx *ctx = NULL;
+    int g0 = 0, ng = 0, max_reads = 0;
+    std::vector<abpoa_t *> handles;
+    std::vector<GroupState> gs;
+    std::vector<Pending> pend;
+    std::vector<poa_job> jobs;
+    bool submitted = false;
+    int fused_rounds = 0;              /* reads 0 .. fused_rounds-1 are in the graphs */
+};
+
+void half_setup(HalfChunk &h, const Worker &wk, int g0, int g1) {
+    abpoa_para_t *abpt = wk.abpt;
+    h.g0 = g0; h.ng = g1 - g0; h.max_reads = 0; h.submitted = false; h.fused_rounds = 0;
+    while ((int)h.handles.size() < h.ng) h.handles.push_back(abpoa_init());
+    h.gs.assign(h.ng, GroupState()); h.pend.assign(h.ng, Pending());
+    int qmax = 0;
+    for (int t = 0; t < h.ng; ++t) {
+        GroupState &s = h.gs[t];
+        s.in = &wk.groups[g0 + t]; s.out = &wk.results[g0 + t]; s.ab = h.handles[t]; s.next_read = 0;
+        memset(s.out, 0, sizeof *s.out);
+        const int n = s.in->n_seq;
+        if (n > h.max_reads) h.max_reads = n;
+        int max_len = 1024;
+        for (int i = 0; i < n; ++i) { if (s.in->seq_lens[i] > max_len) max_len = s.in->seq_lens[i]; if (s.in->seq_lens[i] > qmax) qmax = s.in->seq_lens[i]; }
+        abpoa_reset(s.ab, abpt, max_len);
+        poa_graph_set_fast_order(s.ab->abg, wk.eng->fast_order);
+        abpoa_seq_t *abs = s.ab->abs;
+        abs->n_seq = n; poa_seq_reserve(abs);
+        for (int i = 0; i < n; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
+        s.weights = (int **)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int *));
+        for (int i = 0; i < n; ++i) {
+            const int l = s.in->seq_lens[i];
+            const int *qw = (abpt->use_qv && s.in->qual_weights && s.in->qual_weights[i]) ? s.in->qual_weights[i] : NULL;
+            if (qw) { s.weights[i] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1)); memcpy(s.weights[i], qw, sizeof(int) * (size_t)l); }
+        }
+        if (wk.flags & ABPOA_GPU_RECORD_READS) {
+            s.out->read_best_score = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+            s.out->read_n_cigar = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+            s.out->read_cigar_hash = (uint64_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(uint64_t));
+        }
+    }
+    if (h.ng > 0) poa_dev_ctx_reserve(h.ctx, h.ng, 3 * qmax + 64, qmax);
+}
+
+/* flatten the graphs for read r of every group of the half and launch (asynchronously when possible) */
+void half_start_round(HalfChunk &h, const Worker &wk, int r, SinkCtx *sc) {
+    abpoa_para_t *abpt = wk.abpt;
+    h.jobs.clear(); h.submitted = false;
+    for (int t = 0; t < h.ng; ++t) {
+        GroupState &s = h.gs[t];
+        h.pend[t].gs = &s; h.pend[t].have = false; memset(&h.pend[t].res, 0, sizeof(abpoa_res_t));
+        if (r >= s.in->n_seq) continue;
+        abpoa_graph_t *abg = s.ab->abg;
+        if (abg->node_n <= 2) continue;
+        if (!abg->is_topological_sorted) abpoa_topological_sort(abg, abpt);
+        poa_job j; memset(&j, 0, sizeof j);
+        j.abg = abg; j.beg_node_id = ABPOA_SRC_NODE_ID; j.end_node_id = ABPOA_SINK_NODE_ID;
+        j.query = s.in->seqs[r]; j.tag = &h.pend[t];
+        poa_blob_plan_make(&j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, s.in->seq_lens[r]);
+        h.jobs.push_back(j);
+    }
+    if (h.jobs.empty()) return;
+    if (poa_engine_submit(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size())) h.submitted = true;
+    else poa_engine_run(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size(), sink_to_res, sc);      /* mixed kinds / too big: blocking */
+}
+
+/* wait for the half's launch, then fuse read r into every group that has one */
+void half_finish_round(HalfChunk &h, const Worker &wk, int r, SinkCtx *sc) {
+    abpoa_para_t *abpt = wk.abpt;
+    if (h.submitted) { poa_engine_collect(h.ctx, sink_to_res, sc); h.submitted = false; }
+    for (int t = 0; t < h.ng; ++t) {
+        GroupState &s = h.gs[t];
+        if (r >= s.in->n_seq) continue;
+        Pending &pd = h.pend[t];
+        if (wk.flags & ABPOA_GPU_RECORD_READS) {
+            s.out->read_best_score[r] = pd.have ? pd.res.best_score : 0;
+            s.out->read_n_cigar[r] = pd.res.n_cigar;
+            s.out->read_cigar_hash[r] = fnv1a(pd.res.graph_cigar, pd.res.n_cigar);
+        }
+        poa_add_alignment_nosync(s.ab, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, (uint8_t *)s.in->seqs[r], s.weights[r], s.in->seq_lens[r],
+                                 NULL, pd.res, r, s.in->n_seq, 1);
+        if (pd.res.n_cigar) free(pd.res.graph_cigar);
+        memset(&pd.res, 0, sizeof pd.res); pd.have = false;
+    }
+    h.fused_rounds = r + 1;
+}
+
+void worker_pipelined(Worker wk) {
+    const bool prof = getenv("ABPOA_GPU_PROFILE") != NULL;
+    pin_worker(wk.index);
+    if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
+    abpoa_para_t *abpt = wk.abpt;
+    const int G = wk.G;
+    SinkCtx sc = { abpt };
+    /* sub-chunks in flight per worker: all contexts when there is enough work, fewer for small batches
+     * (so that a few chunks spread over the workers instead of piling onto the first one) */
+    int K = wk.n_ctx;
+    {
+        const int n_chunks = (wk.n_groups + G - 1) / G, nw = wk.eng->n_workers < n_chunks ? wk.eng->n_workers : n_chunks;
+        const int per_worker = (n_chunks + nw - 1) / nw;
+        if (K > per_worker) K = per_worker < 1 ? 1 : per_worker;
+    }
+    std::vector<HalfChunk> half((size_t)K);
+    for (int k = 0; k < K; ++k) half[k].ctx = wk.ctxs[k];
+    PhaseClock pc; double t_start = 0, t_finish = 0;
+    for (;;) {
+        int got = 0, rounds = 0;
+        for (int k = 0; k < K; ++k) {
+            const int chunk = wk.next_chunk->fetch_add(1);
+            const int g0 = chunk * G;
+            if (g0 >= wk.n_groups) { half[k].ng = 0; half[k].max_reads = 0; continue; }
+            half_setup(half[k], wk, g0, g0 + G < wk.n_groups ? g0 + G : wk.n_groups);
+            if (half[k].max_reads > rounds) rounds = half[k].max_reads;
+            ++got;
+        }
+        if (!got) break;
+        for (int r = 0; r < rounds; ++r)
+            for (int k = 0; k < K; ++k) {
+                HalfChunk &h = half[k];
+                if (h.ng == 0) continue;
+                pc.tic();
+                if (r > 0 && r - 1 < h.max_reads) half_finish_round(h, wk, r - 1, &sc);
+                t_finish += pc.toc();
+                if (r < h.max_reads) half_start_round(h, wk, r, &sc);
+                t_start += pc.toc();
+            }
+        for (int k = 0; k < K; ++k) {
+            HalfChunk &h = half[k];
+            if (h.ng == 0) continue;
+            pc.tic();
+            if (h.fused_rounds < h.max_reads) half_finish_round(h, wk, h.max_reads - 1, &sc);
+            for (int t = 0; t < h.ng; ++t) {
+                finish_group(h.gs[t], abpt);
+                for (int i = 0; i < h.gs[t].in->n_seq; ++i) free(h.gs[t].weights[i]);
+                free(h.gs[t].weights);
+            }
+            t_finish += pc.toc();
+        }
+    }
+
+    for (int k = 0; k < K; ++k) for (abpoa_t *ab : half[k].handles) abpoa_free(ab);
+    if (prof) {
+        double wait = 0, fill = 0, copy = 0, kern = 0;
+        for (int k = 0; k < K; ++k) { const poa_engine_stats *st = poa_dev_ctx_stats(wk.ctxs[k]); wait += st->wait_ms; fill += st->fill_ms; copy += st->copy_ms; kern += st->kernel_ms; }
+        fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f ms\n", poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3]);
+        fprintf(stderr, "[worker-pipe x%d] start(plan+fill+launch) %.0f finish(wait+copy+fuse) %.0f ms; launch-to-done %.0f fill %.0f copy %.0f kernel %.0f ms\n",
+                K, t_start, t_finish, wait, fill, copy, kern);
+    }
+}
+
 }  // namespace
 
 extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
@@ -442,12 +612,17 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     if (flags & ABPOA_GPU_CAPTURE_JOBS) abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_set_capture(c, (flags & ABPOA_GPU_CAPTURE_JOBS) ? capture_cb : NULL, e);
     std::atomic<int> next_chunk(0);
-    const int n_chunks = (n_groups + e->groups_per_launch - 1) / e->groups_per_launch;
+    /* groups per launch: as given, else spread the batch evenly over every sub-chunk slot (workers x pipe depth) */
+    int G = e->groups_per_launch;
+    if (G <= 0) { const int slots = e->n_workers * e->pipe_depth; G = (n_groups + slots - 1) / slots; if (G > 32) G = 32; if (G < 1) G = 1; }
+    const int n_chunks = (n_groups + G - 1) / G;
     const int nw = e->n_workers < n_chunks ? e->n_workers : n_chunks;
+    static const bool no_pipe = getenv("ABPOA_GPU_NO_PIPELINE") != NULL;
+    const bool pipelined = !abpt->amb_strand && !no_pipe && e->pipe_depth > 1;
     std::vector<std::thread> th;
     for (int w = 0; w < nw; ++w) {
-        Worker wk = { w, e, e->ctx[w], abpt, flags, &next_chunk, n_groups, groups, results };
-        th.emplace_back(worker_main, wk);
+        Worker wk = { w, e, e->ctx[(size_t)e->pipe_depth * w], &e->ctx[(size_t)e->pipe_depth * w], e->pipe_depth, abpt, flags, &next_chunk, G, n_groups, groups, results };
+        th.emplace_back(pipelined ? worker_pipelined : worker_main, wk);
     }
     for (auto &t : th) t.join();
     e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

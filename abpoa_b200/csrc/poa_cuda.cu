@@ -83,7 +83,16 @@ static void arena_give(poa_arena *a, uint8_t *p, size_t bytes) {
     a->cv.notify_all();
 }
 
+struct LaunchState {
+    bool active = false;
+    const abpoa_para_t *abpt = NULL; poa_job *jobs = NULL; std::vector<int> idx; int n = 0, bits = 0;
+    std::vector<size_t> blob_off, work_off, cig_off;
+    uint8_t *planes_base = NULL; size_t plane_bytes = 0, in_bytes = 0;
+    double t_begin = 0, t_filled = 0;
+};
+
 struct poa_dev_ctx {
+    LaunchState ls;
     int dev;
     poa_arena *arena;
     cudaStream_t st;
@@ -107,7 +116,11 @@ static void require_gpu(void) {
 
 poa_dev_ctx *poa_dev_ctx_new_on(int dev) {
     require_gpu();
-    poa_dev_ctx *c = (poa_dev_ctx *)poa_xcalloc(1, sizeof(poa_dev_ctx));
+    poa_dev_ctx *c = new poa_dev_ctx();
+    c->arena = NULL; c->st = NULL; c->h_in = c->h_out = c->d_in = c->d_work = c->d_planes = c->h_res = NULL;
+    c->h_in_cap = c->h_out_cap = c->d_in_cap = c->d_work_cap = c->d_planes_cap = c->h_res_cap = c->planes_limit = 0;
+    memset(&c->stats, 0, sizeof c->stats); c->capture = NULL; c->capture_user = NULL; memset(&c->last_desc, 0, sizeof c->last_desc);
+    c->last_bits = c->last_gap = c->last_rows = 0;
     if (dev >= 0) { c->dev = dev; CK(cudaSetDevice(c->dev)); }
     else CK(cudaGetDevice(&c->dev));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -135,7 +148,7 @@ void poa_dev_ctx_free(poa_dev_ctx *c) {
     if (c->d_planes) cudaFree(c->d_planes);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); cudaEventDestroy(c->ev_done);
     cudaStreamDestroy(c->st);
-    free(c);
+    delete c;
 }
 
 void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes) { c->planes_limit = bytes; }
@@ -214,14 +227,22 @@ static inline double now_ms(void) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
+/* One launch = begin (stage + H2D + kernel, returns at once) and finish (sleep until the jobs
+ * report, copy CIGARs back, publish results).  A context has at most one launch outstanding;
+ * a worker that owns two contexts overlaps the fusion of one half-chunk with the kernel of the other. */
+static void run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx_in, int n, int bits, int generous) {
     CK(cudaSetDevice(c->dev));
+    LaunchState &L = c->ls;
+    L.abpt = abpt; L.jobs = jobs; L.idx.assign(idx_in, idx_in + n); L.n = n; L.bits = bits; L.active = true;
+    const int *idx = L.idx.data();
     const double t_begin = now_ms();
     const int S = bits == 32 ? 4 : 2;          /* bits: 15 = packed int16x2 kernel, 16 / 32 = generic kernel */
     /* ---- layout of the input arena: params | descs | blobs ---- */
     size_t in_bytes = al256(sizeof(PoaParamsDev)) + al256((size_t)n * sizeof(PoaJobDesc));
     const size_t off_desc = al256(sizeof(PoaParamsDev));
-    std::vector<size_t> blob_off(n), work_off(n), cig_off(n), qp_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    std::vector<size_t> &blob_off = L.blob_off, &work_off = L.work_off, &cig_off = L.cig_off; std::vector<size_t> qp_off(n);
+    blob_off.assign(n, 0); work_off.assign(n, 0); cig_off.assign(n, 0);
+    std::vector<uint64_t> units(n), plane_off(n);
     for (int t = 0; t < n; ++t) { blob_off[t] = in_bytes; in_bytes += al256(jobs[idx[t]].plan.bytes); }
     /* ---- work arena: results | per job (rowinfo, rowoff, cigar) ---- */
     size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
@@ -240,6 +261,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
         plane_off[t] = tot_units; tot_units += units[t];
     }
     const size_t plane_bytes = (size_t)tot_units * POA_GROUP * S;
+    L.plane_bytes = plane_bytes; L.in_bytes = 0;
     grow_host(&c->h_in, &c->h_in_cap, in_bytes);
     grow_host(&c->h_res, &c->h_res_cap, 256 + (size_t)n * sizeof(PoaResultDev));
     grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
@@ -247,6 +269,7 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
     uint8_t *planes_base;
     if (c->arena) planes_base = arena_take(c->arena, plane_bytes);
     else { grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1); planes_base = c->d_planes; }
+    L.planes_base = planes_base; L.in_bytes = in_bytes;
 
     poa_fill_params((PoaParamsDev *)c->h_in, abpt, bits);
     PoaJobDesc *desc = (PoaJobDesc *)(c->h_in + off_desc);
@@ -284,6 +307,18 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
                                             (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
                              (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
+    L.t_begin = t_begin; L.t_filled = t_filled;
+}
+
+static void run_finish(poa_dev_ctx *c) {
+    LaunchState &L = c->ls;
+    if (!L.active) return;
+    L.active = false;
+    CK(cudaSetDevice(c->dev));
+    poa_job *jobs = L.jobs; const int *idx = L.idx.data(); const int n = L.n, bits = L.bits;
+    std::vector<size_t> &blob_off = L.blob_off, &work_off = L.work_off, &cig_off = L.cig_off;
+    uint8_t *planes_base = L.planes_base; const size_t plane_bytes = L.plane_bytes, in_bytes = L.in_bytes;
+    const double t_begin = L.t_begin, t_filled = L.t_filled;
     /* ---- wait for the launch: every job bumps the counter in mapped host memory when its results
      *      (also written there) are complete.  No event / copy is queued behind the kernel, so
      *      streams that share a hardware channel never serialise on it. ---- */
@@ -352,6 +387,57 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
             c->capture(c->capture_user, &cj);
         }
         if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; for (int z = 0; z < 6; ++z) c->stats.prof[z] += resv[t].prof[z]; }
+    }
+}
+
+static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
+    run_begin(c, abpt, jobs, idx, n, bits, generous);
+    run_finish(c);
+}
+
+/* Asynchronous variant for pipelined callers: submit() stages and launches the jobs when they can
+ * all go into ONE launch of one kernel variant (the normal case) and returns 1; otherwise it does
+ * nothing and returns 0 (the caller uses poa_engine_run).  collect() finishes the outstanding launch,
+ * redoes the rare overflow / range jobs synchronously and delivers every job to the sink. */
+int poa_engine_submit(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n) {
+    if (n <= 0 || c->ls.active) return 0;
+    static const int use_p16 = [] { const char *e = getenv("ABPOA_GPU_NO_P16"); return !(e && *e == '1'); }();
+    int kind = -1; size_t bytes = 0;
+    const size_t limit = c->arena ? poa_arena_capacity(c->arena) / 4 : c->planes_limit;
+    for (int t = 0; t < n; ++t) {
+        const int rb = poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows);
+        jobs[t].ref_bits = rb;
+        const int k = (use_p16 && poa_p16_ok(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows)) ? 15 : rb;
+        if (kind < 0) kind = k; else if (k != kind) return 0;
+        bytes += (size_t)plane_units_for(&jobs[t], abpt->gap_mode, 0) * POA_GROUP * (k == 32 ? 4 : 2);
+    }
+    if (limit && bytes > limit) return 0;
+    std::vector<int> idx(n);
+    for (int t = 0; t < n; ++t) idx[t] = t;
+    run_begin(c, abpt, jobs, idx.data(), n, kind, 0);
+    return 1;
+}
+
+void poa_engine_collect(poa_dev_ctx *c, poa_job_sink sink, void *user) {
+    if (!c->ls.active) return;
+    const abpoa_para_t *abpt = c->ls.abpt; poa_job *jobs = c->ls.jobs; const int n = c->ls.n, bits = c->ls.bits;
+    run_finish(c);
+    /* results live in the context's pinned buffers: deliver the good ones before any re-run reuses them */
+    std::vector<int> redo;
+    for (int t = 0; t < n; ++t) {
+        if (jobs[t].status == POA_ST_PLANE_OVF || jobs[t].status == POA_ST_RANGE) redo.push_back(t);
+        else sink(user, &jobs[t]);
+    }
+    for (int t : redo) {
+        c->stats.retries += 1;
+        int b2 = bits;
+        if (jobs[t].status == POA_ST_PLANE_OVF) run_same_width(c, abpt, jobs, &t, 1, b2, 1);
+        if (jobs[t].status == POA_ST_RANGE) {
+            b2 = jobs[t].ref_bits == 16 ? 16 : 32;
+            run_same_width(c, abpt, jobs, &t, 1, b2, 0);
+            if (jobs[t].status == POA_ST_PLANE_OVF) run_same_width(c, abpt, jobs, &t, 1, b2, 1);
+        }
+        sink(user, &jobs[t]);
     }
 }
 

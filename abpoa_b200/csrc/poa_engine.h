@@ -60,6 +60,8 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint);
 
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);
+int poa_engine_submit(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n);
+void poa_engine_collect(poa_dev_ctx *c, poa_job_sink sink, void *user);
 void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res);
 void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes);
 const poa_engine_stats *poa_dev_ctx_stats(const poa_dev_ctx *c);

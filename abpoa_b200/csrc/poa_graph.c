@@ -43,6 +43,7 @@ typedef struct {
      * residues / aligned-set sizes are mirrored in dense arrays, so a pass touches ~40 B per node. */
     int slab_m;
     int *in_id4, *in_w4, *out_id4, *out_w4;     /* [slab_m][POA_INL] */
+    int *aln4;                                  /* [slab_m][POA_INL] first aligned-group members (copy of node[].aligned_node_id) */
     int *cin, *cout;                            /* == node[].in_edge_n / out_edge_n */
     int *caln;                                  /* == node[].aligned_node_n          */
     uint8_t *cbase;                             /* == node[].base                    */
@@ -52,6 +53,20 @@ typedef struct {
     int has_read_ids;                           /* some out-edge carries a read-id bitset */
     int *touched; int n_touched, touched_m; uint8_t *touch_mark;   /* nodes whose edge lists changed since the last ordering */
     int64_t n_edges;                            /* total in-edges in the graph        */
+    /* nodes the Kahn passes must COUNT for: in-degree >= 2 or member of an aligned group (forward
+     * pass), out-degree >= 2 (reverse pass).  Everything else is a plain chain link and is pushed
+     * the moment its only neighbour is dequeued, without touching a counter. */
+    int *fwd_list, n_fwd, fwd_m; uint8_t *fwd_mark;
+    int *rev_list, n_rev, rev_m; uint8_t *rev_mark;
+    /* Spliced topological order (poa_graph_set_fast_order).  The DP result does not depend on
+     * WHICH topological order the rows follow in global mode, so instead of a full Kahn pass
+     * after every read the previous order is kept and the nodes the read created are spliced in
+     * behind their anchors (see splice_order).  Recorded while a read is threaded: */
+    int fast_order;                             /* enabled by the batch engine for this handle      */
+    int tracking, old_n;                        /* a fusion onto a sorted graph is being recorded    */
+    int *new_ids, *new_anchor; int n_new, new_m;
+    int *new_edges; int n_new_edges, new_edges_m;   /* (from,to) pairs of new edges between old nodes */
+    int64_t n_spliced, n_splice_fallback;
 } poa_graph_x;
 
 static inline poa_graph_x *gx(abpoa_graph_t *abg) { return (poa_graph_x *)abg; }
@@ -96,6 +111,7 @@ static void nodes_reserve(abpoa_graph_t *abg, int want) {
     x->in_w4 = (int *)poa_xrealloc(x->in_w4, (size_t)m * POA_INL * sizeof(int));
     x->out_id4 = (int *)poa_xrealloc(x->out_id4, (size_t)m * POA_INL * sizeof(int));
     x->out_w4 = (int *)poa_xrealloc(x->out_w4, (size_t)m * POA_INL * sizeof(int));
+    x->aln4 = (int *)poa_xrealloc(x->aln4, (size_t)m * POA_INL * sizeof(int));
     x->cin = (int *)poa_xrealloc(x->cin, (size_t)m * sizeof(int));
     x->cout = (int *)poa_xrealloc(x->cout, (size_t)m * sizeof(int));
     x->caln = (int *)poa_xrealloc(x->caln, (size_t)m * sizeof(int));
@@ -103,6 +119,8 @@ static void nodes_reserve(abpoa_graph_t *abg, int want) {
     x->cnread = (int *)poa_xrealloc(x->cnread, (size_t)m * sizeof(int)); x->cspan = (int *)poa_xrealloc(x->cspan, (size_t)m * sizeof(int));
     memset(x->cnread + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cspan + old, 0, (size_t)(m - old) * sizeof(int));
     x->touch_mark = (uint8_t *)poa_xrealloc(x->touch_mark, (size_t)m);
+    x->fwd_mark = (uint8_t *)poa_xrealloc(x->fwd_mark, (size_t)m); x->rev_mark = (uint8_t *)poa_xrealloc(x->rev_mark, (size_t)m);
+    memset(x->fwd_mark + old, 0, (size_t)(m - old)); memset(x->rev_mark + old, 0, (size_t)(m - old));
     memset(x->cin + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cout + old, 0, (size_t)(m - old) * sizeof(int));
     memset(x->caln + old, 0, (size_t)(m - old) * sizeof(int)); memset(x->cbase + old, 0, (size_t)(m - old));
     memset(x->touch_mark + old, 0, (size_t)(m - old));
@@ -113,6 +131,13 @@ static void nodes_reserve(abpoa_graph_t *abg, int want) {
         if (nd->out_edge_m == POA_INL) { nd->out_id = x->out_id4 + (size_t)i * POA_INL; nd->out_edge_weight = x->out_w4 + (size_t)i * POA_INL; }
     }
 }
+
+static inline void list_push(int **list, int *n, int *m, int id) {
+    if (*n == *m) { *m = *m ? *m << 1 : 1024; *list = (int *)poa_xrealloc(*list, (size_t)*m * sizeof(int)); }
+    (*list)[(*n)++] = id;
+}
+static inline void mark_fwd_counted(poa_graph_x *x, int id) { if (!x->fwd_mark[id]) { x->fwd_mark[id] = 1; list_push(&x->fwd_list, &x->n_fwd, &x->fwd_m, id); } }
+static inline void mark_rev_counted(poa_graph_x *x, int id) { if (!x->rev_mark[id]) { x->rev_mark[id] = 1; list_push(&x->rev_list, &x->n_rev, &x->rev_m, id); } }
 
 static inline void touch(poa_graph_x *x, int id) {
     if (x->touch_mark[id]) return;
@@ -141,8 +166,8 @@ void poa_graph_free(abpoa_graph_t *abg) {
     free(abg->index_to_node_id); free(abg->node_id_to_index); free(abg->node_id_to_msa_rank);
     free(abg->node_id_to_max_pos_left); free(abg->node_id_to_max_pos_right); free(abg->node_id_to_max_remain);
     free(x->deg); free(x->queue);
-    free(x->in_id4); free(x->in_w4); free(x->out_id4); free(x->out_w4);
-    free(x->cin); free(x->cout); free(x->caln); free(x->cbase); free(x->cnread); free(x->cspan); free(x->touched); free(x->touch_mark);
+    free(x->in_id4); free(x->in_w4); free(x->out_id4); free(x->out_w4); free(x->aln4);
+    free(x->cin); free(x->cout); free(x->caln); free(x->cbase); free(x->cnread); free(x->cspan); free(x->touched); free(x->touch_mark); free(x->fwd_list); free(x->fwd_mark); free(x->rev_list); free(x->rev_mark); free(x->new_ids); free(x->new_anchor); free(x->new_edges);
     free(x);
 }
 
@@ -253,6 +278,10 @@ void abpoa_reset(abpoa_t *ab, abpoa_para_t *abpt, int qlen) {
         x->span_pending = 0; x->public_stale = 0; x->has_read_ids = 0;
         for (int t = 0; t < x->n_touched; ++t) x->touch_mark[x->touched[t]] = 0;
         x->n_touched = 0; x->n_edges = 0;
+        for (int t = 0; t < x->n_fwd; ++t) x->fwd_mark[x->fwd_list[t]] = 0;
+        for (int t = 0; t < x->n_rev; ++t) x->rev_mark[x->rev_list[t]] = 0;
+        x->n_fwd = x->n_rev = 0;
+        x->tracking = 0; x->n_new = x->n_new_edges = 0;
     }
     abg->node_n = 2;
     nodes_reserve(abg, qlen + 2);
@@ -364,20 +393,28 @@ static int edge_add(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, 
         int *iw = nin <= POA_INL ? x->in_w4 + (size_t)to_id * POA_INL : to->in_edge_weight;
         int *oid = nout <= POA_INL ? x->out_id4 + (size_t)from_id * POA_INL : from->out_id;
         int *ow = nout <= POA_INL ? x->out_w4 + (size_t)from_id * POA_INL : from->out_edge_weight;
+        /* A list in non-increasing weight order is a fixed point of the exchange pass, so a node
+         * needs re-ordering only when a bump (or an append) breaks that order. */
         for (int i = 0; i < nin; ++i)
-            if (iid[i] == from_id) { iw[i] += w; break; }
+            if (iid[i] == from_id) { iw[i] += w; if (i > 0 && iw[i - 1] < iw[i]) touch(x, to_id); break; }
         for (int i = 0; i < nout; ++i)
-            if (oid[i] == to_id) { ow[i] += w; slot = i; break; }
+            if (oid[i] == to_id) { ow[i] += w; slot = i; if (i > 0 && ow[i - 1] < ow[i]) touch(x, from_id); break; }
     }
     if (slot < 0) {              /* new edge, appended after the existing ones */
         in_edges_reserve(x, to_id, to->in_edge_n + 1);
         to->in_id[to->in_edge_n] = from_id; to->in_edge_weight[to->in_edge_n] = w; x->cin[to_id] = ++to->in_edge_n;
+        if (to->in_edge_n == 2) mark_fwd_counted(x, to_id);
         out_edges_reserve(x, from_id, from->out_edge_n + 1, add_read_id);
         slot = from->out_edge_n;
         from->out_id[slot] = to_id; from->out_edge_weight[slot] = w; x->cout[from_id] = ++from->out_edge_n;
         x->n_edges += 1;
+        if (x->tracking && from_id < x->old_n && to_id < x->old_n) {
+            if (x->n_new_edges + 2 > x->new_edges_m) { x->new_edges_m = x->new_edges_m ? x->new_edges_m << 1 : 256; x->new_edges = (int *)poa_xrealloc(x->new_edges, (size_t)x->new_edges_m * sizeof(int)); }
+            x->new_edges[x->n_new_edges++] = from_id; x->new_edges[x->n_new_edges++] = to_id;
+        }
+        if (to->in_edge_n > 1 && to->in_edge_weight[to->in_edge_n - 2] < w) touch(x, to_id);
+        if (slot > 0 && from->out_edge_weight[slot - 1] < w) touch(x, from_id);
     }
-    touch(x, from_id); touch(x, to_id);
     if (add_read_id) {           /* which reads run through this edge: feeds the RC-MSA */
         if (read_ids_n <= 0) poa_die(__func__, "Unexpected read_ids_n: %d.", read_ids_n);
         out_edges_reserve(x, from_id, from->out_edge_n, 1);
@@ -398,7 +435,13 @@ static int edge_add(abpoa_graph_t *abg, int from_id, int to_id, int check_edge, 
 }
 
 /* nodes that occupy the same MSA column ("aligned" = mismatch alternatives) */
-static void aligned_push(abpoa_node_t *nd, int id) {
+static void aligned_push_raw(abpoa_node_t *nd, int id);
+static inline void aligned_push(abpoa_graph_t *abg, int owner, int id) {
+    abpoa_node_t *nd = &abg->node[owner];
+    if (nd->aligned_node_n < POA_INL) gx(abg)->aln4[(size_t)owner * POA_INL + nd->aligned_node_n] = id;
+    aligned_push_raw(nd, id);
+}
+static void aligned_push_raw(abpoa_node_t *nd, int id) {
     if (nd->aligned_node_n == nd->aligned_node_m) {
         int m = nd->aligned_node_m ? nd->aligned_node_m << 1 : 2;
         nd->aligned_node_id = (int *)(nd->aligned_node_m ? poa_xrealloc(nd->aligned_node_id, (size_t)m * sizeof(int)) : poa_xmalloc((size_t)m * sizeof(int)));
@@ -409,20 +452,22 @@ static void aligned_push(abpoa_node_t *nd, int id) {
 
 static void aligned_join(abpoa_graph_t *abg, int node_id, int new_id) {
     abpoa_node_t *node = abg->node; int *caln = gx(abg)->caln;
+    mark_fwd_counted(gx(abg), node_id); mark_fwd_counted(gx(abg), new_id);
     for (int i = 0; i < node[node_id].aligned_node_n; ++i) {
         int sib = node[node_id].aligned_node_id[i];
-        aligned_push(&node[sib], new_id); caln[sib] = node[sib].aligned_node_n;
-        aligned_push(&node[new_id], sib);
+        mark_fwd_counted(gx(abg), sib);
+        aligned_push(abg, sib, new_id); caln[sib] = node[sib].aligned_node_n;
+        aligned_push(abg, new_id, sib);
     }
-    aligned_push(&node[node_id], new_id); caln[node_id] = node[node_id].aligned_node_n;
-    aligned_push(&node[new_id], node_id); caln[new_id] = node[new_id].aligned_node_n;
+    aligned_push(abg, node_id, new_id); caln[node_id] = node[node_id].aligned_node_n;
+    aligned_push(abg, new_id, node_id); caln[new_id] = node[new_id].aligned_node_n;
 }
 
 static int aligned_with_base(const abpoa_graph_t *abg, int node_id, uint8_t base) {
     const poa_graph_x *x = cgx(abg);
     const int na = x->caln[node_id];
     if (na == 0) return -1;
-    const int *al = abg->node[node_id].aligned_node_id;
+    const int *al = na <= POA_INL ? x->aln4 + (size_t)node_id * POA_INL : abg->node[node_id].aligned_node_id;
     for (int i = 0; i < na; ++i)
         if (x->cbase[al[i]] == base) return al[i];
     return -1;
@@ -443,7 +488,9 @@ void abpoa_BFS_set_node_index(abpoa_graph_t *abg, int src_id, int sink_id) {
     const poa_graph_x *x = gx(abg);
     int *deg = gx(abg)->deg, *q = gx(abg)->queue;
     const abpoa_node_t *node = abg->node;
-    memcpy(deg, x->cin, (size_t)n * sizeof(int));
+    const int *cin = x->cin, *cout = x->cout, *caln = x->caln;
+    /* only "counted" nodes (in-degree >= 2 or in an aligned group) need an in-degree counter */
+    for (int t = 0; t < x->n_fwd; ++t) { const int v = x->fwd_list[t]; deg[v] = cin[v]; }
     int *index_to_node_id = abg->index_to_node_id, *node_id_to_index = abg->node_id_to_index;
     int head = 0, tail = 0, index = 0;
     q[tail++] = src_id;
@@ -452,13 +499,14 @@ void abpoa_BFS_set_node_index(abpoa_graph_t *abg, int src_id, int sink_id) {
         index_to_node_id[index] = cur;
         node_id_to_index[cur] = index++;
         if (cur == sink_id) return;
-        const int ne = x->cout[cur]; const int *oid = out_ids_of(x, cur);
+        const int ne = cout[cur]; const int *oid = out_ids_of(x, cur);
         for (int e = 0; e < ne; ++e) {
             const int v = oid[e];
+            const int na = caln[v];
+            if (cin[v] == 1 && na == 0) { q[tail++] = v; continue; }       /* chain link: ready at once */
             if (--deg[v] != 0) continue;
-            const int na = x->caln[v];
             if (na) {                                   /* ready only together with its whole aligned group */
-                const int *al = node[v].aligned_node_id;
+                const int *al = na <= POA_INL ? x->aln4 + (size_t)v * POA_INL : node[v].aligned_node_id;
                 int ready = 1;
                 for (int a = 0; a < na; ++a) if (deg[al[a]] != 0) { ready = 0; break; }
                 if (!ready) continue;
@@ -512,33 +560,78 @@ static void order_edges_by_weight(abpoa_graph_t *abg) {
     x->n_touched = 0;
 }
 
-/* max_remain[v] = 1 + max_remain[heaviest out-neighbour, first on ties]; SINK = -1.
- * Reverse Kahn from the sink; it is the centre line of the adaptive band. */
+/* max_remain[v] = 1 + max_remain[heaviest out-neighbour, first on ties]; SINK = -1: the centre
+ * line of the adaptive band.  The reference runs a reverse Kahn traversal from the sink
+ * (src/abpoa_graph.c:333-389); the values depend only on the out-neighbours, so one backward sweep
+ * over the topological order just computed gives the same numbers without queue or counters. */
 void abpoa_BFS_set_node_remain(abpoa_graph_t *abg, int src_id, int sink_id) {
-    const int n = abg->node_n;
-    scratch_reserve(abg, n);
     const poa_graph_x *x = gx(abg);
-    int *deg = gx(abg)->deg, *q = gx(abg)->queue, *remain = abg->node_id_to_max_remain;
-    memcpy(deg, x->cout, (size_t)n * sizeof(int));
-    memset(remain, 0, (size_t)n * sizeof(int));
-    int head = 0, tail = 0;
-    q[tail++] = sink_id; remain[sink_id] = -1;
-    while (head < tail) {
-        const int cur = q[head++];
-        if (cur != sink_id) {
-            const int ne = x->cout[cur]; const int *oid = out_ids_of(x, cur), *ow = out_ws_of(x, cur);
-            int best_w = -1, best = -1;
+    int *remain = abg->node_id_to_max_remain;
+    const int *cout = x->cout, *order = abg->index_to_node_id;
+    const int lo = abg->node_id_to_index[src_id], hi = abg->node_id_to_index[sink_id];
+    if (lo < 0 || hi >= abg->node_n || lo > hi) poa_die(__func__, "Failed to set node remain.");
+    remain[sink_id] = -1;
+    for (int i = hi - 1; i >= lo; --i) {
+        const int cur = order[i];
+        const int ne = cout[cur]; const int *oid = out_ids_of(x, cur);
+        if (ne == 1) remain[cur] = remain[oid[0]] + 1;
+        else {
+            const int *ow = out_ws_of(x, cur);
+            int best_w = -1, best = sink_id;
             for (int e = 0; e < ne; ++e) if (ow[e] > best_w) { best_w = ow[e]; best = oid[e]; }
             remain[cur] = remain[best] + 1;
         }
-        if (cur == src_id) return;
-        const int ni = x->cin[cur]; const int *iid = in_ids_of(x, cur);
-        for (int e = 0; e < ni; ++e) {
-            const int u = iid[e];
-            if (--deg[u] == 0) q[tail++] = u;
-        }
     }
-    poa_die(__func__, "Failed to set node remain.");
+}
+
+/* ------------------------------------------------------------------ spliced order
+ * Invariant shared with the Kahn order above: the members of an aligned group occupy consecutive
+ * rows.  A read's path is monotone in the rows of the order it was aligned in, so
+ *   - a new node aligned to x goes right behind x's group,
+ *   - a new unaligned (inserted) node goes right behind the group of the previous path node
+ *     (or inherits the anchor of the previous node if that one is new as well),
+ * which keeps every old and every new edge pointing forward and the groups consecutive.  Anchors
+ * come out in non-decreasing order along the path, so the splice is one backward merge.  New
+ * edges between OLD nodes are re-checked; a violation falls back to the full Kahn pass. */
+void poa_graph_set_fast_order(abpoa_graph_t *abg, int on) { gx(abg)->fast_order = on; }
+void poa_graph_order_stats(const abpoa_graph_t *abg, int64_t *spliced, int64_t *fallback) { *spliced = cgx(abg)->n_spliced; *fallback = cgx(abg)->n_splice_fallback; }
+
+static inline int group_last_row(const abpoa_graph_t *abg, int v) {
+    const poa_graph_x *x = cgx(abg);
+    int r = abg->node_id_to_index[v];
+    const int na = x->caln[v];
+    if (na == 0) return r;
+    const int *al = na <= POA_INL ? x->aln4 + (size_t)v * POA_INL : abg->node[v].aligned_node_id;
+    for (; r + 1 < x->old_n; ++r) {
+        const int u = abg->index_to_node_id[r + 1];
+        int member = 0;
+        for (int a = 0; a < na; ++a) if (al[a] == u) { member = 1; break; }
+        if (!member) break;
+    }
+    return r;
+}
+static inline void record_new_node(poa_graph_x *x, int id, int anchor) {
+    if (x->n_new == x->new_m) {
+        x->new_m = x->new_m ? x->new_m << 1 : 256;
+        x->new_ids = (int *)poa_xrealloc(x->new_ids, (size_t)x->new_m * sizeof(int));
+        x->new_anchor = (int *)poa_xrealloc(x->new_anchor, (size_t)x->new_m * sizeof(int));
+    }
+    x->new_ids[x->n_new] = id; x->new_anchor[x->n_new++] = anchor;
+}
+static int splice_order(abpoa_graph_t *abg) {
+    poa_graph_x *x = gx(abg);
+    const int old_n = x->old_n, n = abg->node_n;
+    if (old_n + x->n_new != n) return 0;              /* nodes were created behind our back */
+    int *order = abg->index_to_node_id, *idx = abg->node_id_to_index;
+    int w = n - 1, k = x->n_new - 1;
+    for (int i = old_n - 1; i >= 0 && k >= 0; --i) {  /* rows in front of the first anchor keep their index */
+        while (k >= 0 && x->new_anchor[k] == i) { const int v = x->new_ids[k--]; order[w] = v; idx[v] = w--; }
+        const int v = order[i]; order[w] = v; idx[v] = w--;
+    }
+    if (k >= 0) return 0;
+    for (int e = 0; e < x->n_new_edges; e += 2)
+        if (idx[x->new_edges[e]] >= idx[x->new_edges[e + 1]]) return 0;
+    return 1;
 }
 
 void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
@@ -546,7 +639,16 @@ void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
     const int n = abg->node_n;
     index_arrays_reserve(abg, abpt, n);
     double t0 = prof_now();
-    abpoa_BFS_set_node_index(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    {
+        poa_graph_x *x = gx(abg);
+        int spliced = 0;
+        if (x->tracking) {
+            spliced = splice_order(abg);
+            if (spliced) x->n_spliced += 1; else x->n_splice_fallback += 1;
+            x->tracking = 0;
+        }
+        if (!spliced) abpoa_BFS_set_node_index(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);
+    }
     double t1 = prof_now(); poa_prof_ms[0] += t1 - t0;
     order_edges_by_weight(abg);
     double t2 = prof_now(); poa_prof_ms[1] += t2 - t1;
@@ -663,7 +765,10 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
         seed_graph_with_sequence(abg, abpt, seq, weight, seq_l, qpos_to_node_id, add_read_id, add_read_weight, read_id, read_ids_n, tot_read_n);
     } else if (res.n_cigar > 0) {
         const double tf0 = prof_now();
-        int qi = -1, last_id = beg_node_id, last_is_new = 0;
+        int qi = -1, last_id = beg_node_id, last_is_new = 0, last_anchor = -1;
+        x->tracking = x->fast_order && abg->is_topological_sorted && abpt->align_mode == ABPOA_GLOBAL_MODE &&
+                      beg_node_id == ABPOA_SRC_NODE_ID && end_node_id == ABPOA_SINK_NODE_ID;
+        x->old_n = abg->node_n; x->n_new = 0; x->n_new_edges = 0;
         for (int c = 0; c < res.n_cigar; ++c) {
             const abpoa_cigar_t cg = res.graph_cigar[c];
             const int op = (int)(cg & 0xf);
@@ -675,6 +780,7 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
                 if (gx(abg)->cbase[node_id] == seq[qi]) target = node_id;
                 else if ((target = aligned_with_base(abg, node_id, seq[qi])) < 0) {
                     target = abpoa_add_graph_node(abg, seq[qi]); target_is_new = 1;
+                    if (x->tracking) { last_anchor = group_last_row(abg, node_id); record_new_node(x, target, last_anchor); }
                 }
                 edge_add(abg, last_id, target, target_is_new ? 0 : 1 - last_is_new, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
                 if (target_is_new) x->cspan[target] = x->cspan[last_id];
@@ -688,6 +794,7 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
                     ++qi;
                     const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
                     int nid = abpoa_add_graph_node(abg, seq[qi]);
+                    if (x->tracking) { if (!last_is_new) last_anchor = group_last_row(abg, last_id); record_new_node(x, nid, last_anchor); }
                     edge_add(abg, last_id, nid, 0, weight[qi], add_read_id & add, add_read_weight, read_id, read_ids_n, tot_read_n);
                     x->cspan[nid] = x->cspan[last_id];
                     if (!add) x->cnread[last_id]--;

@@ -53,6 +53,10 @@ void poa_set_msa_rank(abpoa_graph_t *abg, int src_id, int sink_id);
 int poa_edge_path_score(const abpoa_graph_t *abg, int node_id, int in_idx);  /* -G scores */
 /* dense, node-id-indexed views kept by poa_graph.c (see poa_graph_x) */
 void poa_graph_sync_public(abpoa_graph_t *abg);        /* fold dense n_read / n_span_read into node[] */
+/* batch engine, global mode: keep the previous topological order and splice new nodes in instead of
+ * a full Kahn pass per read (poa_graph.c, "spliced order"); counters for diagnostics */
+void poa_graph_set_fast_order(abpoa_graph_t *abg, int on);
+void poa_graph_order_stats(const abpoa_graph_t *abg, int64_t *spliced, int64_t *fallback);
 int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *weight,
                              int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends);
 int64_t poa_graph_edge_count(const abpoa_graph_t *abg);

@@ -116,32 +116,43 @@ __device__ __forceinline__ JobView open_job(const uint8_t *blob) {
 }
 
 /* ================================================================== backtrace */
-struct BtPred {            /* what lane k knows about predecessor k of the current row */
-    int row;               /* predecessor row, -1 if lane has none                       */
+/* What lane k holds about candidate predecessor k of the current row.  The row-level part (band,
+ * slab offset, its own predecessor list start and its first two predecessors) is LOOK-AHEAD: when
+ * the walk moves to this candidate, the next step already knows everything but the cells, so a
+ * step costs two dependent memory levels (candidate row record -> its cells) instead of four. */
+struct BtCand {
+    int row;                      /* candidate row, -1 if the lane has none                 */
+    int beg, end; uint32_t off;   /* its band and slab offset                               */
+    int pb, np, base;             /* its predecessor list (start, count) and residue        */
+    int p0, p1;                   /* its first two predecessors (rows), -1 if absent        */
     int h_jm1, h_j, e1_j, e2_j, ps;
-    bool in_m, in_e;       /* j-1 / j inside the predecessor's band                      */
+    bool in_m, in_e;              /* j-1 / j inside the candidate's band                    */
 };
 
 template <int GAP, typename ST>
-__device__ __forceinline__ BtPred bt_load_pred(const JobView &jv, const PoaRowInfo *rowinfo, const uint32_t *rowoff,
-                                               const ST *planes, int pb, int np, int k, int j) {
-    BtPred r; r.row = -1; r.h_jm1 = r.h_j = r.e1_j = r.e2_j = NEG; r.ps = 0; r.in_m = r.in_e = false;
-    if (k < np) {
-        r.row = jv.pred[pb + k];
-        if (jv.predscore) r.ps = jv.predscore[pb + k];
-        const PoaRowInfo pi = rowinfo[r.row];
-        const int g0 = pi.beg >> 3, ng = (pi.end >> 3) - g0 + 1;
-        const ST *rp = planes + (size_t)rowoff[r.row] * POA_GROUP - (size_t)g0 * POA_GROUP;
-        r.in_m = (j - 1 >= pi.beg && j - 1 <= pi.end);
-        r.in_e = (j >= pi.beg && j <= pi.end);
-        if (r.in_m) r.h_jm1 = (int)rp[j - 1];
-        if (r.in_e) {
-            r.h_j = (int)rp[j];
-            if (GAP != LG) r.e1_j = (int)rp[(size_t)ng * POA_GROUP + j];
-            if (GAP == CG) r.e2_j = (int)rp[(size_t)2 * ng * POA_GROUP + j];
-        }
+__device__ __forceinline__ void bt_load_row(BtCand &r, const JobView &jv, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row) {
+    r.row = row;
+    const PoaRowInfo pi = rowinfo[row];
+    r.beg = pi.beg; r.end = pi.end; r.off = rowoff[row];
+    const int2 m0 = __ldg(jv.rowmeta + row);
+    r.pb = m0.x; r.np = __ldg(&jv.rowmeta[row + 1].x) - m0.x; r.base = m0.y & 0xff;
+    r.p0 = r.np > 0 ? __ldg(jv.pred + r.pb) : -1;
+    r.p1 = r.np > 1 ? __ldg(jv.pred + r.pb + 1) : -1;
+}
+template <int GAP, typename ST>
+__device__ __forceinline__ void bt_load_cells(BtCand &r, const ST *planes, int j) {
+    r.h_jm1 = r.h_j = r.e1_j = r.e2_j = NEG; r.in_m = r.in_e = false;
+    if (r.row < 0) return;
+    const int g0 = r.beg >> 3, ng = (r.end >> 3) - g0 + 1;
+    const ST *rp = planes + (size_t)r.off * POA_GROUP - (size_t)g0 * POA_GROUP;
+    r.in_m = (j - 1 >= r.beg && j - 1 <= r.end);
+    r.in_e = (j >= r.beg && j <= r.end);
+    if (r.in_m) r.h_jm1 = (int)rp[j - 1];
+    if (r.in_e) {
+        r.h_j = (int)rp[j];
+        if (GAP != LG) r.e1_j = (int)rp[(size_t)ng * POA_GROUP + j];
+        if (GAP == CG) r.e2_j = (int)rp[(size_t)2 * ng * POA_GROUP + j];
     }
-    return r;
 }
 
 struct CigarSink {
@@ -174,32 +185,59 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     int gap_at_end = prm->put_gap_at_end; const int gap_on_right = prm->put_gap_on_right;
     if (best_j < qlen) cg.ins(qlen - best_j, qlen - 1);
 
+    /* the current row (uniform) and, on lane k, its candidate predecessor k */
+    BtCand me; bt_load_row<GAP, ST>(me, jv, rowinfo, rowoff, i);
+    BtCand pc0; pc0.row = -1; pc0.ps = 0;
+    bool cand_rows_loaded = false;
+
     while (i > 0 && j > 0) {
-        const PoaRowInfo ri = rowinfo[i];
-        const int gi0 = ri.beg >> 3, ngi = (ri.end >> 3) - gi0 + 1;
-        const ST *rp = planes + (size_t)rowoff[i] * POA_GROUP - (size_t)gi0 * POA_GROUP;
-        const bool in_j = (j >= ri.beg && j <= ri.end), in_jm1 = (j - 1 >= ri.beg && j - 1 <= ri.end);
+        const int gi0 = me.beg >> 3, ngi = (me.end >> 3) - gi0 + 1;
+        const ST *rp = planes + (size_t)me.off * POA_GROUP - (size_t)gi0 * POA_GROUP;
+        const bool in_j = (j >= me.beg && j <= me.end), in_jm1 = (j - 1 >= me.beg && j - 1 <= me.end);
         const int h_ij = in_j ? (int)rp[j] : NEG;
         if (MODE == LOCAL && h_ij == 0) break;
         start_i = i; start_j = j;
         const int id = i;                       /* the host maps DP rows back to node ids */
-        const int rb = jv.base(i), qc = jv.qs[j];
+        const int rb = me.base, qc = jv.qs[j];
         const int s = mat_s[rb * m + qc];
-        const int pb = jv.predoff(i), np = jv.predoff(i + 1) - pb;
-        const BtPred pc0 = bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, lane, j);
+        const int pb = me.pb, np = me.np;
+        if (!cand_rows_loaded) {                /* new row: lane k learns about candidate k (lanes 0/1 know which row already) */
+            pc0.row = -1; pc0.ps = 0;
+            if (lane < np) {
+                const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : __ldg(jv.pred + pb + lane));
+                bt_load_row<GAP, ST>(pc0, jv, rowinfo, rowoff, prow);
+                if (jv.predscore) pc0.ps = __ldg(jv.predscore + pb + lane);
+            }
+            cand_rows_loaded = true;
+        }
+        bt_load_cells<GAP, ST>(pc0, planes, j);
         int hit = 0;
+
+        /* move to the candidate held by lane `sel` of chunk `kb` */
+        auto move_to = [&](const BtCand &pc, int sel) {
+            me.row = __shfl_sync(FULL, pc.row, sel); me.beg = __shfl_sync(FULL, pc.beg, sel); me.end = __shfl_sync(FULL, pc.end, sel);
+            me.off = __shfl_sync(FULL, pc.off, sel); me.pb = __shfl_sync(FULL, pc.pb, sel); me.np = __shfl_sync(FULL, pc.np, sel);
+            me.base = __shfl_sync(FULL, pc.base, sel); me.p0 = __shfl_sync(FULL, pc.p0, sel); me.p1 = __shfl_sync(FULL, pc.p1, sel);
+            i = me.row; cand_rows_loaded = false;
+        };
+        auto chunk = [&](int kb) -> BtCand {   /* candidates kb .. kb+31 (kb > 0 is the rare > 32 predecessor case) */
+            if (kb == 0) return pc0;
+            BtCand pc; pc.row = -1; pc.ps = 0;
+            if (kb + lane < np) { bt_load_row<GAP, ST>(pc, jv, rowinfo, rowoff, __ldg(jv.pred + pb + kb + lane)); if (jv.predscore) pc.ps = __ldg(jv.predscore + pb + kb + lane); }
+            bt_load_cells<GAP, ST>(pc, planes, j);
+            return pc;
+        };
 
         /* first predecessor (reference order) whose diagonal cell explains H[i][j] */
         auto try_match = [&]() {
             for (int kb = 0; kb < np; kb += 32) {
-                const BtPred pc = kb == 0 ? pc0 : bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, kb + lane, j);
+                const BtCand pc = chunk(kb);
                 const bool ok = pc.row >= 0 && pc.in_m && (pc.h_jm1 + s + pc.ps == h_ij);
                 const unsigned b = __ballot_sync(FULL, ok);
                 if (b) {
-                    const int sel = __ffs(b) - 1;
-                    const int prow = __shfl_sync(FULL, pc.row, sel);
                     cg.match(id, j - 1);
-                    i = prow; --j; cur = OP_ALL; hit = 1;
+                    move_to(pc, __ffs(b) - 1);
+                    --j; cur = OP_ALL; hit = 1;
                     ++n_aln; n_match += (rb == qc);
                     return;
                 }
@@ -215,7 +253,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 if (GAP == CG) e2_ij = (int)rp[(size_t)PL::E2 * ngi * POA_GROUP + j];
             }
             for (int kb = 0; kb < np && !hit; kb += 32) {
-                const BtPred pc = kb == 0 ? pc0 : bt_load_pred<GAP, ST>(jv, rowinfo, rowoff, planes, pb, np, kb + lane, j);
+                const BtCand pc = chunk(kb);
                 int code = 0;                                           /* 1: via E1, 2: via E2; +4: gap opened at p */
                 if (pc.row >= 0 && pc.in_e) {
                     if (GAP == LG) {
@@ -234,11 +272,11 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 const unsigned b = __ballot_sync(FULL, code != 0);
                 if (b) {
                     const int sel = __ffs(b) - 1;
-                    const int prow = __shfl_sync(FULL, pc.row, sel);
                     const int c = __shfl_sync(FULL, code, sel);
                     if (GAP != LG) cur = (c & 4) ? (OP_M | OP_F) : ((c & 3) == 1 ? OP_E1 : OP_E2);
                     cg.del(id);
-                    i = prow; hit = 1; gap_at_end = 0;
+                    move_to(pc, sel);
+                    hit = 1; gap_at_end = 0;
                 }
             }
         }
@@ -265,7 +303,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                     }
                 }
             }
-            if (hit) { cg.ins(1, j - 1); --j; gap_at_end = 0; ++n_aln; }
+            if (hit) { cg.ins(1, j - 1); --j; gap_at_end = 0; ++n_aln; }     /* same row: candidate rows stay valid */
         }
 
         if (!hit && (GAP == LG || (cur & OP_M))) { try_match(); if (hit) gap_at_end = 0; }

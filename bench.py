@@ -198,7 +198,7 @@ def main():
     lib = capi.product()
     abpt = make_para(lib, w.cfg)
     workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(32, (os.cpu_count() or 8) // 2 // max(world, 1)))
-    gpl = int(os.environ.get("ABPOA_GPU_GROUPS_PER_LAUNCH", "0")) or max(1, min(32, (n_groups + workers - 1) // workers))
+    gpl = int(os.environ.get("ABPOA_GPU_GROUPS_PER_LAUNCH", "0"))      # 0: the engine spreads the groups over workers x pipe depth
     os.environ.setdefault("ABPOA_GPU_CPU_BASE", str(local_rank * workers))      # disjoint cores per rank
     eng = BatchEngine(device=local_rank, n_workers=workers, groups_per_launch=gpl)
 
@@ -280,7 +280,7 @@ def main():
         "dtype": "int16/int32 planes, int32 registers", "data": "synthetic", "config": cfgdesc,
         "clocks": clocks, "reads_per_s": tot_reads / elapsed,
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
-                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl},
+                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl or "auto"},
         "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"]},

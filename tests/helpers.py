@@ -28,7 +28,7 @@ def read_fasta(path: Path, m: int = 5) -> list[np.ndarray]:
     return seqs
 
 
-def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: bool = False):
+def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: bool = False, fast_order: bool = False):
     """Progressive POA of one group through `lib`; returns per-read records + consensus (+ MSA).
 
     use_oracle=True: the graph / consensus / MSA code of `lib` is driven, but every
@@ -40,15 +40,28 @@ def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: boo
         if use_oracle:
             from oracle_binding import oracle_align
             s.reset(max((len(r) for r in reads), default=1024))
+            if fast_order:      # what the batch engine does per handle: spliced topological order between reads
+                s.lib.dll.poa_graph_set_fast_order(s.ab.contents.abg, 1)
             alns = []
             for r in reads:
                 a, res = oracle_align(s, r)
                 alns.append(a)
                 s.add(r, res, len(reads))
+            if fast_order:      # ... and the reference's Kahn order again before consensus / MSA
+                import ctypes as C
+                spl, fb = C.c_int64(0), C.c_int64(0)
+                s.lib.dll.poa_graph_order_stats(s.ab.contents.abg, C.byref(spl), C.byref(fb))
+                s.order_stats = (spl.value, fb.value)
+                s.lib.dll.poa_graph_set_fast_order(s.ab.contents.abg, 0)
+                g = s.ab.contents.abg.contents
+                if g.node_n > 2:
+                    g.is_topological_sorted = 0
+                    s.lib.abpoa_topological_sort(s.ab.contents.abg, s.abpt)
         else:
             alns = s.run_reads(reads)
         s.generate()
         return {
+            "order_stats": getattr(s, "order_stats", None),
             "alns": alns,
             "cons": s.consensus(),
             "cov": s.consensus_cov(),

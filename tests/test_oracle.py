@@ -33,3 +33,19 @@ def test_oracle_matches_live_reference(product_lib, reference_lib, name):
     cfg = PoaConfig(**case["cfg"])
     reads = case_reads(case)
     assert_group_equal(run_group(product_lib, cfg, reads, use_oracle=True), run_group(reference_lib, cfg, reads), name)
+
+
+GLOBAL_CASES = [n for n, c in CASES.items() if c["cfg"].get("align_mode", 0) == 0]
+
+
+@pytest.mark.parametrize("name", GLOBAL_CASES)
+def test_spliced_order_matches_golden(product_lib, name):
+    """Global mode: the batch engine keeps the previous topological order and splices the new nodes
+    in instead of re-running the Kahn pass per read (poa_graph.c "spliced order").  Every alignment
+    (score, graph-CIGAR in node ids, end points, DP cells), consensus and RC-MSA must be unchanged."""
+    case = CASES[name]
+    cfg = PoaConfig(**case["cfg"])
+    r = run_group(product_lib, cfg, case_reads(case), use_oracle=True, fast_order=True)
+    spliced, fallback = r["order_stats"]
+    assert spliced > 0 and fallback == 0, (spliced, fallback)
+    assert_digest_equal(group_digest(r, cfg.m), GOLDEN["cases"][name], name)
