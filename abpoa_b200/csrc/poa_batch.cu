@@ -222,21 +222,48 @@ uint64_t fnv1a(const abpoa_cigar_t *a, int n) {
 /* One worker per physical core: pin worker `w` to the (base + w)-th CPU the process may use.
  * Linux numbers the first hardware thread of every core first, so consecutive workers land on
  * distinct cores; ranks of a multi-GPU job pass disjoint bases (ABPOA_GPU_CPU_BASE). */
+/* CPUs the process may use, ordered so that consecutive workers land on DISTINCT physical cores
+ * (one hardware thread per core first, sockets interleaved, SMT siblings only after every core has
+ * a worker).  Linux numbers CPUs differently from box to box, so the order is read from sysfs. */
+static std::vector<int> worker_cpu_order() {
+    std::vector<int> cpus;
+    cpu_set_t allowed; CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return cpus;
+    struct Cpu { int cpu, pkg, core, smt; };
+    std::vector<Cpu> v;
+    for (int c = 0; c < CPU_SETSIZE; ++c) {
+        if (!CPU_ISSET(c, &allowed)) continue;
+        Cpu x = { c, 0, c, 0 };
+        char path[128]; FILE *f;
+        snprintf(path, sizeof path, "/sys/devices/system/cpu/cpu%d/topology/physical_package_id", c);
+        if ((f = fopen(path, "r"))) { if (fscanf(f, "%d", &x.pkg) != 1) x.pkg = 0; fclose(f); }
+        snprintf(path, sizeof path, "/sys/devices/system/cpu/cpu%d/topology/core_id", c);
+        if ((f = fopen(path, "r"))) { if (fscanf(f, "%d", &x.core) != 1) x.core = c; fclose(f); }
+        v.push_back(x);
+    }
+    /* smt rank = position among the allowed CPUs sharing (pkg, core) */
+    for (size_t i = 0; i < v.size(); ++i) { int r = 0; for (size_t k = 0; k < i; ++k) if (v[k].pkg == v[i].pkg && v[k].core == v[i].core) ++r; v[i].smt = r; }
+    /* rank of the core inside its package, to interleave the packages */
+    std::vector<int> core_rank(v.size(), 0);
+    for (size_t i = 0; i < v.size(); ++i) { int r = 0; for (size_t k = 0; k < v.size(); ++k) if (v[k].pkg == v[i].pkg && v[k].smt == v[i].smt && (v[k].core < v[i].core)) ++r; core_rank[i] = r; }
+    std::vector<size_t> idx(v.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+        if (v[a].smt != v[b].smt) return v[a].smt < v[b].smt;
+        if (core_rank[a] != core_rank[b]) return core_rank[a] < core_rank[b];
+        return v[a].pkg < v[b].pkg; });
+    for (size_t i : idx) cpus.push_back(v[i].cpu);
+    return cpus;
+}
+
 void pin_worker(int w) {
     const char *pin = getenv("ABPOA_GPU_PIN");
     if (pin && *pin == '0') return;
-    cpu_set_t allowed; CPU_ZERO(&allowed);
-    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
-    const int n = CPU_COUNT(&allowed);
-    if (n <= 0) return;
+    static const std::vector<int> order = worker_cpu_order();
+    if (order.empty()) return;
     const char *b = getenv("ABPOA_GPU_CPU_BASE");
-    int want = ((b && *b ? atoi(b) : 0) + w) % n;
-    for (int c = 0; c < CPU_SETSIZE; ++c)
-        if (CPU_ISSET(c, &allowed) && want-- == 0) {
-            cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one);
-            pthread_setaffinity_np(pthread_self(), sizeof one, &one);
-            return;
-        }
+    const int c = order[(size_t)((b && *b ? atoi(b) : 0) + w) % order.size()];
+    cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one);
+    pthread_setaffinity_np(pthread_self(), sizeof one, &one);
 }
 
 struct Worker {

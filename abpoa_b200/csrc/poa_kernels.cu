@@ -116,43 +116,38 @@ __device__ __forceinline__ JobView open_job(const uint8_t *blob) {
 }
 
 /* ================================================================== backtrace */
-/* What lane k holds about candidate predecessor k of the current row.  The row-level part (band,
- * slab offset, its own predecessor list start and its first two predecessors) is LOOK-AHEAD: when
- * the walk moves to this candidate, the next step already knows everything but the cells, so a
- * step costs two dependent memory levels (candidate row record -> its cells) instead of four. */
-struct BtCand {
-    int row;                      /* candidate row, -1 if the lane has none                 */
-    int beg, end; uint32_t off;   /* its band and slab offset                               */
-    int pb, np, base;             /* its predecessor list (start, count) and residue        */
-    int p0, p1;                   /* its first two predecessors (rows), -1 if absent        */
-    int h_jm1, h_j, e1_j, e2_j, ps;
-    bool in_m, in_e;              /* j-1 / j inside the candidate's band                    */
+/* Row record of the backtrace: band, virtual cell-0 pointer of the H plane, predecessor list and the
+ * first two predecessors.  `me` (uniform) describes the current row; on lane k a second record
+ * describes candidate predecessor k, loaded once per row and valid across insertion steps.  It is
+ * LOOK-AHEAD: when the walk moves to a candidate the new row needs no loads at all (its record is
+ * broadcast from the winning lane and H[i][j] is the cell that was just compared), so the common
+ * diagonal step costs: candidate record (mostly L1/L2 hits) -> one cell -> ballot. */
+template <typename ST> struct BtRow {
+    int row;                      /* -1: the lane holds no candidate                         */
+    int beg, end; uint32_t off;   /* band and slab offset                                    */
+    int pb, np, base;             /* predecessor list (start, count) and residue              */
+    int p0, p1;                   /* first two predecessors (rows), -1 if absent              */
+    const ST *ptr;                /* &H[row][0] (virtual: only cells beg..end exist)          */
+    int pstride;                  /* elements between planes of the row                      */
+    __device__ __forceinline__ bool has(int j) const { return j >= beg && j <= end; }      /* empty for end < beg (no candidate) */
+    __device__ __forceinline__ void locate(const ST *planes) {
+        const int g0 = beg >> 3;
+        pstride = ((end >> 3) - g0 + 1) * POA_GROUP;
+        ptr = planes + ((ptrdiff_t)off - g0) * POA_GROUP;
+    }
 };
-
-template <int GAP, typename ST>
-__device__ __forceinline__ void bt_load_row(BtCand &r, const JobView &jv, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row) {
+template <typename ST>
+__device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, const ST *planes, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row) {
     r.row = row;
     const PoaRowInfo pi = rowinfo[row];
-    r.beg = pi.beg; r.end = pi.end; r.off = rowoff[row];
+    const uint32_t off = rowoff[row];
     const int2 m0 = __ldg(jv.rowmeta + row);
-    r.pb = m0.x; r.np = __ldg(&jv.rowmeta[row + 1].x) - m0.x; r.base = m0.y & 0xff;
+    const int nx = __ldg(&jv.rowmeta[row + 1].x);
+    r.beg = pi.beg; r.end = pi.end; r.off = off;
+    r.pb = m0.x; r.np = nx - m0.x; r.base = m0.y & 0xff;
     r.p0 = r.np > 0 ? __ldg(jv.pred + r.pb) : -1;
     r.p1 = r.np > 1 ? __ldg(jv.pred + r.pb + 1) : -1;
-}
-template <int GAP, typename ST>
-__device__ __forceinline__ void bt_load_cells(BtCand &r, const ST *planes, int j) {
-    r.h_jm1 = r.h_j = r.e1_j = r.e2_j = NEG; r.in_m = r.in_e = false;
-    if (r.row < 0) return;
-    const int g0 = r.beg >> 3, ng = (r.end >> 3) - g0 + 1;
-    const ST *rp = planes + (size_t)r.off * POA_GROUP - (size_t)g0 * POA_GROUP;
-    r.in_m = (j - 1 >= r.beg && j - 1 <= r.end);
-    r.in_e = (j >= r.beg && j <= r.end);
-    if (r.in_m) r.h_jm1 = (int)rp[j - 1];
-    if (r.in_e) {
-        r.h_j = (int)rp[j];
-        if (GAP != LG) r.e1_j = (int)rp[(size_t)ng * POA_GROUP + j];
-        if (GAP == CG) r.e2_j = (int)rp[(size_t)2 * ng * POA_GROUP + j];
-    }
+    r.locate(planes);
 }
 
 struct CigarSink {
@@ -178,6 +173,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     const PoaRowInfo *rowinfo = jd.rowinfo; const uint32_t *rowoff = jd.rowoff;
     const int m = prm->m, e1 = prm->e1, oe1 = prm->oe1, e2 = prm->e2, oe2 = prm->oe2;
     const int qlen = jv.qlen;
+    const bool has_ps = jv.predscore != nullptr;
     CigarSink cg; cg.out = jd.cigar; cg.cap = jd.cigar_cap; cg.n = 0; cg.pending = 0; cg.lane = lane; cg.ovf = 0;
 
     int i = best_i, j = best_j, start_i = best_i, start_j = best_j, cur = OP_ALL;
@@ -185,87 +181,131 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     int gap_at_end = prm->put_gap_at_end; const int gap_on_right = prm->put_gap_on_right;
     if (best_j < qlen) cg.ins(qlen - best_j, qlen - 1);
 
-    /* the current row (uniform) and, on lane k, its candidate predecessor k */
-    BtCand me; bt_load_row<GAP, ST>(me, jv, rowinfo, rowoff, i);
-    BtCand pc0; pc0.row = -1; pc0.ps = 0;
-    bool cand_rows_loaded = false;
+    BtRow<ST> me; bt_load_row<ST>(me, jv, planes, rowinfo, rowoff, i);
+    BtRow<ST> pc; pc.row = -1; pc.beg = 0; pc.end = -1; pc.ptr = planes; pc.pstride = 0;
+    int pc_ps = 0;
+    bool cand_loaded = false;
+    int h_ij = (j > 0 && me.has(j)) ? (int)me.ptr[j] : NEG;       /* carried from step to step afterwards */
+    int qc = j > 0 ? (int)jv.qs[j] : 0;
+
+    /* Scout: the planes were written long ago, so every cell the walk touches is an HBM miss, and
+     * the walk is one dependent miss per step.  A scout runs BT_LEAD rows ahead along the
+     * first-predecessor chain (heaviest edges first = the path most reads take) and prefetches the
+     * H cells the walk will compare there, assuming diagonal moves (a 128-byte line holds 64 cells,
+     * so a few indels do not matter).  Lane L remembers the row the scout visited L steps ago; when
+     * the walk takes another branch it usually rejoins that chain a row or two later and the scout
+     * simply carries on, otherwise (the walk overtook it) it restarts at the walk's row. */
+    constexpr int BT_LEAD = 6;
+    int s_row = i, s_p0 = me.p0, s_ahead = 0, s_hist = (lane == 0) ? i : -1;
+    auto scout_sync = [&](int new_row) {               /* the walk moved to new_row */
+        const unsigned on_chain = __ballot_sync(FULL, s_hist == new_row);
+        if (on_chain) s_ahead = __ffs(on_chain) - 1;
+        else if (new_row <= s_row) { s_row = new_row; s_p0 = me.p0; s_ahead = 0; s_hist = (lane == 0) ? new_row : -1; }
+        else if (s_ahead > 1) --s_ahead;
+    };
+
+    /* the walk moves to the candidate row held by lane `sel` */
+    auto move_to = [&](const BtRow<ST> &src, int sel) {
+        me.row = __shfl_sync(FULL, src.row, sel); me.beg = __shfl_sync(FULL, src.beg, sel); me.end = __shfl_sync(FULL, src.end, sel);
+        me.off = __shfl_sync(FULL, src.off, sel); me.pb = __shfl_sync(FULL, src.pb, sel);
+        const int nb = __shfl_sync(FULL, (src.np << 8) | src.base, sel); me.np = nb >> 8; me.base = nb & 0xff;
+        me.p0 = __shfl_sync(FULL, src.p0, sel); me.p1 = __shfl_sync(FULL, src.p1, sel);
+        me.locate(planes);
+        i = me.row; cand_loaded = false;
+        scout_sync(i);
+    };
+    /* candidates 32.. of a row with more than 32 predecessors (practically never) */
+    auto load_chunk = [&](BtRow<ST> &px, int &px_ps, int kb) {
+        px.row = -1; px.beg = 0; px.end = -1; px.ptr = planes; px.pstride = 0; px_ps = 0;
+        if (kb + lane < me.np) {
+            bt_load_row<ST>(px, jv, planes, rowinfo, rowoff, __ldg(jv.pred + me.pb + kb + lane));
+            if (has_ps) px_ps = __ldg(jv.predscore + me.pb + kb + lane);
+        }
+    };
 
     while (i > 0 && j > 0) {
-        const int gi0 = me.beg >> 3, ngi = (me.end >> 3) - gi0 + 1;
-        const ST *rp = planes + (size_t)me.off * POA_GROUP - (size_t)gi0 * POA_GROUP;
-        const bool in_j = (j >= me.beg && j <= me.end), in_jm1 = (j - 1 >= me.beg && j - 1 <= me.end);
-        const int h_ij = in_j ? (int)rp[j] : NEG;
         if (MODE == LOCAL && h_ij == 0) break;
         start_i = i; start_j = j;
         const int id = i;                       /* the host maps DP rows back to node ids */
-        const int rb = me.base, qc = jv.qs[j];
+        const int rb = me.base, np = me.np;
+        const int qprev = (int)jv.qs[j - 1];    /* next column's residue: off the critical path */
         const int s = mat_s[rb * m + qc];
-        const int pb = me.pb, np = me.np;
-        if (!cand_rows_loaded) {                /* new row: lane k learns about candidate k (lanes 0/1 know which row already) */
-            pc0.row = -1; pc0.ps = 0;
+        if (!cand_loaded) {                     /* new row: lane k learns about candidate k (lanes 0/1 already know which row) */
+            pc.row = -1; pc.beg = 0; pc.end = -1; pc_ps = 0;
             if (lane < np) {
-                const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : __ldg(jv.pred + pb + lane));
-                bt_load_row<GAP, ST>(pc0, jv, rowinfo, rowoff, prow);
-                if (jv.predscore) pc0.ps = __ldg(jv.predscore + pb + lane);
+                const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : __ldg(jv.pred + me.pb + lane));
+                bt_load_row<ST>(pc, jv, planes, rowinfo, rowoff, prow);
+                if (has_ps) pc_ps = __ldg(jv.predscore + me.pb + lane);
             }
-            cand_rows_loaded = true;
+            cand_loaded = true;
         }
-        bt_load_cells<GAP, ST>(pc0, planes, j);
+        const bool c_in_m = pc.has(j - 1);
+        const int c_hm1 = c_in_m ? (int)pc.ptr[j - 1] : NEG;
         int hit = 0;
-
-        /* move to the candidate held by lane `sel` of chunk `kb` */
-        auto move_to = [&](const BtCand &pc, int sel) {
-            me.row = __shfl_sync(FULL, pc.row, sel); me.beg = __shfl_sync(FULL, pc.beg, sel); me.end = __shfl_sync(FULL, pc.end, sel);
-            me.off = __shfl_sync(FULL, pc.off, sel); me.pb = __shfl_sync(FULL, pc.pb, sel); me.np = __shfl_sync(FULL, pc.np, sel);
-            me.base = __shfl_sync(FULL, pc.base, sel); me.p0 = __shfl_sync(FULL, pc.p0, sel); me.p1 = __shfl_sync(FULL, pc.p1, sel);
-            i = me.row; cand_rows_loaded = false;
-        };
-        auto chunk = [&](int kb) -> BtCand {   /* candidates kb .. kb+31 (kb > 0 is the rare > 32 predecessor case) */
-            if (kb == 0) return pc0;
-            BtCand pc; pc.row = -1; pc.ps = 0;
-            if (kb + lane < np) { bt_load_row<GAP, ST>(pc, jv, rowinfo, rowoff, __ldg(jv.pred + pb + kb + lane)); if (jv.predscore) pc.ps = __ldg(jv.predscore + pb + kb + lane); }
-            bt_load_cells<GAP, ST>(pc, planes, j);
-            return pc;
-        };
+        if (s_ahead < BT_LEAD && s_p0 > 0) {   /* one scout row per step (loads issued here are consumed after the walk's own cell load) */
+            s_row = s_p0; ++s_ahead;
+            const int up = __shfl_up_sync(FULL, s_hist, 1); s_hist = lane == 0 ? s_row : up;
+            const int2 sm = __ldg(jv.rowmeta + s_row);
+            const int snx = __ldg(&jv.rowmeta[s_row + 1].x);
+            const PoaRowInfo si = rowinfo[s_row];
+            const uint32_t so = rowoff[s_row];
+            s_p0 = snx > sm.x ? __ldg(jv.pred + sm.x) : 0;
+            const int jp = j - s_ahead - 1;
+            if (si.end >= si.beg) {
+                const ST *sp = planes + ((ptrdiff_t)so - (si.beg >> 3)) * POA_GROUP;
+                const int ja = min(max(jp - 16, si.beg), si.end), jb = min(max(jp + 8, si.beg), si.end);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + ja));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + jb));
+            }
+        }
 
         /* first predecessor (reference order) whose diagonal cell explains H[i][j] */
         auto try_match = [&]() {
-            for (int kb = 0; kb < np; kb += 32) {
-                const BtCand pc = chunk(kb);
-                const bool ok = pc.row >= 0 && pc.in_m && (pc.h_jm1 + s + pc.ps == h_ij);
-                const unsigned b = __ballot_sync(FULL, ok);
-                if (b) {
-                    cg.match(id, j - 1);
-                    move_to(pc, __ffs(b) - 1);
-                    --j; cur = OP_ALL; hit = 1;
-                    ++n_aln; n_match += (rb == qc);
-                    return;
+            unsigned b = __ballot_sync(FULL, c_in_m && (c_hm1 + s + pc_ps == h_ij));
+            BtRow<ST> sx = pc; int hv = c_hm1;
+            if (!b && np > 32) {
+                for (int kb = 32; kb < np && !b; kb += 32) {
+                    int x_ps; load_chunk(sx, x_ps, kb);
+                    const bool in = sx.has(j - 1);
+                    hv = in ? (int)sx.ptr[j - 1] : NEG;
+                    b = __ballot_sync(FULL, in && (hv + s + x_ps == h_ij));
                 }
             }
+            if (!b) return;
+            const int sel = __ffs(b) - 1;
+            cg.match(id, j - 1);
+            h_ij = __shfl_sync(FULL, hv, sel);
+            move_to(sx, sel);
+            ++n_aln; n_match += (rb == qc);
+            --j; qc = qprev; cur = OP_ALL; hit = 1;
         };
 
         if (!gap_on_right && !gap_at_end && (GAP == LG || (cur & OP_M))) try_match();
 
         if (!hit && (GAP == LG || (cur & OP_E))) {                      /* deletion: come from (p, j) */
             int e1_ij = NEG, e2_ij = NEG;
-            if (GAP != LG && in_j) {
-                e1_ij = (int)rp[(size_t)PL::E1 * ngi * POA_GROUP + j];
-                if (GAP == CG) e2_ij = (int)rp[(size_t)PL::E2 * ngi * POA_GROUP + j];
+            if (GAP != LG && me.has(j)) {
+                e1_ij = (int)me.ptr[PL::E1 * me.pstride + j];
+                if (GAP == CG) e2_ij = (int)me.ptr[PL::E2 * me.pstride + j];
             }
+            BtRow<ST> sx = pc; int x_ps = pc_ps;
             for (int kb = 0; kb < np && !hit; kb += 32) {
-                const BtCand pc = chunk(kb);
-                int code = 0;                                           /* 1: via E1, 2: via E2; +4: gap opened at p */
-                if (pc.row >= 0 && pc.in_e) {
+                if (kb > 0) load_chunk(sx, x_ps, kb);
+                int code = 0, c_hj = NEG;                               /* 1: via E1, 2: via E2; +4: gap opened at p */
+                if (sx.has(j)) {
+                    c_hj = (int)sx.ptr[j];
                     if (GAP == LG) {
-                        if (pc.h_j - e1 + pc.ps == h_ij) code = 1;
+                        if (c_hj - e1 + x_ps == h_ij) code = 1;
                     } else {
+                        const int c_e1 = (int)sx.ptr[PL::E1 * sx.pstride + j];
                         if (cur & OP_E1) {
-                            const bool ok = (cur & OP_M) ? (h_ij == pc.e1_j + pc.ps) : (e1_ij == pc.e1_j - e1 + pc.ps);
-                            if (ok) code = 1 | ((pc.h_j - oe1 == pc.e1_j) ? 4 : 0);
+                            const bool ok = (cur & OP_M) ? (h_ij == c_e1 + x_ps) : (e1_ij == c_e1 - e1 + x_ps);
+                            if (ok) code = 1 | ((c_hj - oe1 == c_e1) ? 4 : 0);
                         }
                         if (GAP == CG && code == 0 && (cur & OP_E2)) {
-                            const bool ok = (cur & OP_M) ? (h_ij == pc.e2_j + pc.ps) : (e2_ij == pc.e2_j - e2 + pc.ps);
-                            if (ok) code = 2 | ((pc.h_j - oe2 == pc.e2_j) ? 4 : 0);
+                            const int c_e2 = (int)sx.ptr[PL::E2 * sx.pstride + j];
+                            const bool ok = (cur & OP_M) ? (h_ij == c_e2 + x_ps) : (e2_ij == c_e2 - e2 + x_ps);
+                            if (ok) code = 2 | ((c_hj - oe2 == c_e2) ? 4 : 0);
                         }
                     }
                 }
@@ -275,35 +315,37 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                     const int c = __shfl_sync(FULL, code, sel);
                     if (GAP != LG) cur = (c & 4) ? (OP_M | OP_F) : ((c & 3) == 1 ? OP_E1 : OP_E2);
                     cg.del(id);
-                    move_to(pc, sel);
+                    h_ij = __shfl_sync(FULL, c_hj, sel);
+                    move_to(sx, sel);
                     hit = 1; gap_at_end = 0;
                 }
             }
         }
 
         if (!hit && (GAP == LG || (cur & OP_F))) {                      /* insertion: come from (i, j-1) */
-            const int h_jm1 = in_jm1 ? (int)rp[j - 1] : NEG;
+            const bool in_j = me.has(j), in_jm1 = me.has(j - 1);
+            const int h_jm1 = in_jm1 ? (int)me.ptr[j - 1] : NEG;
             if (GAP == LG) {
                 if (h_jm1 - e1 == h_ij) hit = 1;
             } else {
                 if (GAP == AG || (cur & OP_F1)) {
-                    const int f_ij = in_j ? (int)rp[(size_t)PL::F1 * ngi * POA_GROUP + j] : NEG;
-                    const int f_jm1 = in_jm1 ? (int)rp[(size_t)PL::F1 * ngi * POA_GROUP + j - 1] : NEG;
+                    const int f_ij = in_j ? (int)me.ptr[PL::F1 * me.pstride + j] : NEG;
+                    const int f_jm1 = in_jm1 ? (int)me.ptr[PL::F1 * me.pstride + j - 1] : NEG;
                     if (!(cur & OP_M) || h_ij == f_ij) {
                         if (h_jm1 - oe1 == f_ij) { cur = OP_M | OP_E; hit = 1; }
                         else if (f_jm1 - e1 == f_ij) { cur = OP_F1; hit = 1; }
                     }
                 }
                 if (GAP == CG && !hit && (cur & OP_F2)) {
-                    const int f_ij = in_j ? (int)rp[(size_t)PL::F2 * ngi * POA_GROUP + j] : NEG;
-                    const int f_jm1 = in_jm1 ? (int)rp[(size_t)PL::F2 * ngi * POA_GROUP + j - 1] : NEG;
+                    const int f_ij = in_j ? (int)me.ptr[PL::F2 * me.pstride + j] : NEG;
+                    const int f_jm1 = in_jm1 ? (int)me.ptr[PL::F2 * me.pstride + j - 1] : NEG;
                     if (!(cur & OP_M) || h_ij == f_ij) {
                         if (h_jm1 - oe2 == f_ij) { cur = OP_M | OP_E; hit = 1; }
                         else if (f_jm1 - e2 == f_ij) { cur = OP_F2; hit = 1; }
                     }
                 }
             }
-            if (hit) { cg.ins(1, j - 1); --j; gap_at_end = 0; ++n_aln; }     /* same row: candidate rows stay valid */
+            if (hit) { cg.ins(1, j - 1); h_ij = h_jm1; --j; qc = qprev; gap_at_end = 0; ++n_aln; }   /* same row: candidates stay valid */
         }
 
         if (!hit && (GAP == LG || (cur & OP_M))) { try_match(); if (hit) gap_at_end = 0; }
@@ -1204,6 +1246,8 @@ static cudaError_t launch_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, i
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
+        const char *cv = getenv("ABPOA_GPU_CARVEOUT");
+        if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
         configured = 227 * 1024;
     }
     poa_align_kernel<GAP, ST, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
@@ -1237,6 +1281,8 @@ static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *pr
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
+        const char *cv = getenv("ABPOA_GPU_CARVEOUT");          /* shared-memory share of the L1/shared array, percent */
+        if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
         configured = 227 * 1024;
     }
     poa_align_kernel_p16<GAP, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
