@@ -11,6 +11,7 @@
  * point uses a batch of one; abpoa_gpu.h drives many contexts from worker threads.
  */
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -82,6 +83,22 @@ static void arena_give(poa_arena *a, uint8_t *p, size_t bytes) {
     }
     a->cv.notify_all();
 }
+
+uint8_t *poa_arena_borrow(poa_arena *a, size_t bytes) { return arena_take(a, bytes); }
+/* non-blocking: NULL when no free range is large enough right now */
+uint8_t *poa_arena_try_borrow(poa_arena *a, size_t bytes) {
+    bytes = al256(bytes);
+    std::lock_guard<std::mutex> lk(a->mu);
+    for (size_t i = 0; i < a->free_list.size(); ++i)
+        if (a->free_list[i].second >= bytes) {
+            const size_t off = a->free_list[i].first;
+            a->free_list[i].first += bytes; a->free_list[i].second -= bytes;
+            if (a->free_list[i].second == 0) a->free_list.erase(a->free_list.begin() + i);
+            return a->base + off;
+        }
+    return NULL;
+}
+void poa_arena_return(poa_arena *a, uint8_t *p, size_t bytes) { arena_give(a, p, bytes); }
 
 struct LaunchState {
     bool active = false;
@@ -162,17 +179,40 @@ static void stream_wait(poa_dev_ctx *c) {
     CK(cudaEventSynchronize(c->ev_done));
 }
 
+/* cudaFree / cudaFreeHost wait for every kernel on the device -- including the resident kernel,
+ * which only ends when its batch call does.  While one is running, buffers that are outgrown are
+ * parked here and released when it has stopped. */
+static std::atomic<int> g_hold_frees(0);
+static std::mutex g_parked_mu;
+static std::vector<void *> g_parked_dev, g_parked_host;
+static void release_dev(void *p) {
+    if (g_hold_frees.load()) { std::lock_guard<std::mutex> lk(g_parked_mu); g_parked_dev.push_back(p); }
+    else CK(cudaFree(p));
+}
+static void release_host(void *p) {
+    if (g_hold_frees.load()) { std::lock_guard<std::mutex> lk(g_parked_mu); g_parked_host.push_back(p); }
+    else CK(cudaFreeHost(p));
+}
+void poa_hold_frees(int on) {
+    g_hold_frees.store(on);
+    if (on) return;
+    std::lock_guard<std::mutex> lk(g_parked_mu);
+    for (void *p : g_parked_dev) cudaFree(p);
+    for (void *p : g_parked_host) cudaFreeHost(p);
+    g_parked_dev.clear(); g_parked_host.clear();
+}
+
 static void grow_host(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return;
     size_t n = al256(need * 2);
-    if (*p) CK(cudaFreeHost(*p));
+    if (*p) release_host(*p);
     CK(cudaHostAlloc((void **)p, n, cudaHostAllocDefault));
     *cap = n;
 }
 static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
     if (need <= *cap) return;
     size_t n = al256(slack ? need * 2 : need);
-    if (*p) CK(cudaFree(*p));
+    if (*p) release_dev(*p);
     cudaError_t e = cudaMalloc((void **)p, n);
     if (e != cudaSuccess && slack) { cudaGetLastError(); n = al256(need); e = cudaMalloc((void **)p, n); }
     if (e != cudaSuccess) poa_die("libabpoa_b200/cuda", "cudaMalloc of %zu bytes failed: %s", n, cudaGetErrorString(e));

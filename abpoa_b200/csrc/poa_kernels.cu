@@ -95,13 +95,19 @@ template <int GAP> struct Planes {
     static constexpr int H = 0, E1 = 1, E2 = 2, F1 = (GAP == AG ? 2 : 3), F2 = 4;
 };
 
+/* Blob loads.  NOT ld.global.nc (__ldg): the resident kernel rewrites a slot's blob buffer between
+ * jobs, and the read-only path is not kept coherent with stores of the same kernel -- a line left
+ * over from the previous job's backtrace (its last steps read the first rows' metadata) would be
+ * served to the next job.  Plain loads go through L1 coherently for same-SM writers. */
+template <typename T> __device__ __forceinline__ T ldb(const T *p) { return *p; }
+
 /* ------------------------------------------------------------------ job view */
 struct JobView {
     const int2 *rowmeta; const int32_t *pred, *predscore; const uint8_t *live, *qs;
     int n_rows, qlen, w, node_n, pn;
-    __device__ __forceinline__ int predoff(int i) const { return __ldg(&rowmeta[i].x); }
-    __device__ __forceinline__ int base(int i) const { return __ldg(&rowmeta[i].y) & 0xff; }
-    __device__ __forceinline__ int remain(int i) const { return __ldg(&rowmeta[i].y) >> 8; }
+    __device__ __forceinline__ int predoff(int i) const { return ldb(&rowmeta[i].x); }
+    __device__ __forceinline__ int base(int i) const { return ldb(&rowmeta[i].y) & 0xff; }
+    __device__ __forceinline__ int remain(int i) const { return ldb(&rowmeta[i].y) >> 8; }
 };
 __device__ __forceinline__ JobView open_job(const uint8_t *blob) {
     const PoaJobHeader *h = reinterpret_cast<const PoaJobHeader *>(blob);
@@ -141,12 +147,12 @@ __device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, con
     r.row = row;
     const PoaRowInfo pi = rowinfo[row];
     const uint32_t off = rowoff[row];
-    const int2 m0 = __ldg(jv.rowmeta + row);
-    const int nx = __ldg(&jv.rowmeta[row + 1].x);
+    const int2 m0 = ldb(jv.rowmeta + row);
+    const int nx = ldb(&jv.rowmeta[row + 1].x);
     r.beg = pi.beg; r.end = pi.end; r.off = off;
     r.pb = m0.x; r.np = nx - m0.x; r.base = m0.y & 0xff;
-    r.p0 = r.np > 0 ? __ldg(jv.pred + r.pb) : -1;
-    r.p1 = r.np > 1 ? __ldg(jv.pred + r.pb + 1) : -1;
+    r.p0 = r.np > 0 ? ldb(jv.pred + r.pb) : -1;
+    r.p1 = r.np > 1 ? ldb(jv.pred + r.pb + 1) : -1;
     r.locate(planes);
 }
 
@@ -218,8 +224,8 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     auto load_chunk = [&](BtRow<ST> &px, int &px_ps, int kb) {
         px.row = -1; px.beg = 0; px.end = -1; px.ptr = planes; px.pstride = 0; px_ps = 0;
         if (kb + lane < me.np) {
-            bt_load_row<ST>(px, jv, planes, rowinfo, rowoff, __ldg(jv.pred + me.pb + kb + lane));
-            if (has_ps) px_ps = __ldg(jv.predscore + me.pb + kb + lane);
+            bt_load_row<ST>(px, jv, planes, rowinfo, rowoff, ldb(jv.pred + me.pb + kb + lane));
+            if (has_ps) px_ps = ldb(jv.predscore + me.pb + kb + lane);
         }
     };
 
@@ -233,9 +239,9 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         if (!cand_loaded) {                     /* new row: lane k learns about candidate k (lanes 0/1 already know which row) */
             pc.row = -1; pc.beg = 0; pc.end = -1; pc_ps = 0;
             if (lane < np) {
-                const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : __ldg(jv.pred + me.pb + lane));
+                const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : ldb(jv.pred + me.pb + lane));
                 bt_load_row<ST>(pc, jv, planes, rowinfo, rowoff, prow);
-                if (has_ps) pc_ps = __ldg(jv.predscore + me.pb + lane);
+                if (has_ps) pc_ps = ldb(jv.predscore + me.pb + lane);
             }
             cand_loaded = true;
         }
@@ -245,11 +251,11 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         if (s_ahead < BT_LEAD && s_p0 > 0) {   /* one scout row per step (loads issued here are consumed after the walk's own cell load) */
             s_row = s_p0; ++s_ahead;
             const int up = __shfl_up_sync(FULL, s_hist, 1); s_hist = lane == 0 ? s_row : up;
-            const int2 sm = __ldg(jv.rowmeta + s_row);
-            const int snx = __ldg(&jv.rowmeta[s_row + 1].x);
+            const int2 sm = ldb(jv.rowmeta + s_row);
+            const int snx = ldb(&jv.rowmeta[s_row + 1].x);
             const PoaRowInfo si = rowinfo[s_row];
             const uint32_t so = rowoff[s_row];
-            s_p0 = snx > sm.x ? __ldg(jv.pred + sm.x) : 0;
+            s_p0 = snx > sm.x ? ldb(jv.pred + sm.x) : 0;
             const int jp = j - s_ahead - 1;
             if (si.end >= si.beg) {
                 const ST *sp = planes + ((ptrdiff_t)so - (si.beg >> 3)) * POA_GROUP;
@@ -466,18 +472,18 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
      * one row ahead so that its latency never sits on the row-to-row dependency chain. */
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
-        { const int2 m1 = __ldg(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
-        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (jv.predscore) myps = __ldg(jv.predscore + pb + lane); }
+        { const int2 m1 = ldb(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
+        if (lane < pe - pb) { mypred = ldb(jv.pred + pb + lane); if (jv.predscore) myps = ldb(jv.predscore + pb + lane); }
     }
-    int nx_y = n_rows > 3 ? __ldg(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
+    int nx_y = n_rows > 3 ? ldb(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
         if (i + 1 < n_rows - 1) {
-            { const int2 m2 = __ldg(jv.rowmeta + i + 2); n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y; }
-            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (jv.predscore) n_myps = __ldg(jv.predscore + pe + lane); }
+            { const int2 m2 = ldb(jv.rowmeta + i + 2); n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y; }
+            if (lane < n_pe - pe) { n_mypred = ldb(jv.pred + pe + lane); if (jv.predscore) n_myps = ldb(jv.predscore + pe + lane); }
         }
         const int np = pe - pb;
-        if (!(jv.live && !__ldg(jv.live + i))) {
+        if (!(jv.live && !ldb(jv.live + i))) {
 
         /* lane k holds predecessor k (chunk 0); band hints are reductions over all of them */
         int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             const int k = kb + lane;
             int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
             if (k < np) {
-                const int prow = kb == 0 ? mypred : __ldg(jv.pred + pb + k);
+                const int prow = kb == 0 ? mypred : ldb(jv.pred + pb + k);
                 const bool near = (i - prow) <= rmask;
                 const PoaRowInfo pi = near ? ring_info[prow & rmask] : rowinfo[prow];
                 l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
@@ -529,7 +535,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             const bool active = g <= g1;
             /* this lane's 8 query residues; independent of the predecessors, so issued first */
             uint2 qv = make_uint2(0u, 0u);
-            if (active) qv = __ldg(reinterpret_cast<const uint2 *>(jv.qs + (size_t)g * 8));
+            if (active) qv = ldb(reinterpret_cast<const uint2 *>(jv.qs + (size_t)g * 8));
             int M[8], X1[8], X2[8];                         /* M: diagonal term; X1/X2: E1/E2 inputs (LG: X1 = vertical term) */
             fill8(M, NEG); fill8(X1, NEG); if (GAP == CG) fill8(X2, NEG);
 
@@ -538,8 +544,8 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 if (kb > 0) {                               /* rare: more than 32 predecessors */
                     const int k = kb + lane; c_row = -1;
                     if (k < np) {
-                        c_row = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
-                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? __ldg(jv.predscore + pb + k) : 0;
+                        c_row = ldb(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
+                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? ldb(jv.predscore + pb + k) : 0;
                     }
                 }
                 const int nk = min(32, np - kb);
@@ -790,27 +796,19 @@ __device__ __forceinline__ int lane_max8(const unsigned a[4]) {
     return max(lo16(m), hi16(m));
 }
 
-template <int GAP, int MODE>
-__global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
-                                                           int n_jobs, int ring_rows, int ring_cells) {
-    typedef int16_t ST;
-    typedef Planes<GAP> PL;
-    constexpr int RN = RingPlanes<GAP>::N;
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    int *mat_s = reinterpret_cast<int *>(dyn_smem);
-    uint4 *cap_lo = reinterpret_cast<uint4 *>(dyn_smem + POA_MAX_M * POA_MAX_M * sizeof(int));   /* [9]: first n cells masked */
-    uint4 *cap_hi = cap_lo + 9;                                                                    /* [9]: last n cells masked  */
-    uint4 *ring_meta = cap_hi + 9;                       /* [ring_rows] {beg, end, (left+1)|(right+1)<<16, plane offset} */
-    ST *ring_data = reinterpret_cast<ST *>(ring_meta + ring_rows);
-    const int rmask = ring_rows - 1, ring_groups = ring_cells >> 3;
-
-    const int lane = threadIdx.x;
-    const int job = blockIdx.x;
-    if (job >= n_jobs) return;
-    const long long clk0 = clock64();
-    uint64_t t_start_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+/* shared-memory layout of one packed-kernel CTA (one warp) */
+struct P16Smem {
+    int *mat_s; uint4 *cap_lo, *cap_hi, *ring_meta; int16_t *ring_data;
+};
+__device__ __forceinline__ P16Smem p16_smem_init(uint8_t *dyn_smem, const PoaParamsDev *prm, int ring_rows, int lane) {
+    P16Smem sm;
+    sm.mat_s = reinterpret_cast<int *>(dyn_smem);
+    sm.cap_lo = reinterpret_cast<uint4 *>(dyn_smem + POA_MAX_M * POA_MAX_M * sizeof(int));   /* [9]: first n cells masked */
+    sm.cap_hi = sm.cap_lo + 9;                                                                 /* [9]: last n cells masked  */
+    sm.ring_meta = sm.cap_hi + 9;                    /* [ring_rows] {beg, end, (left+1)|(right+1)<<16, plane offset} */
+    sm.ring_data = reinterpret_cast<int16_t *>(sm.ring_meta + ring_rows);
     const int m = prm->m;
-    for (int t = lane; t < m * m; t += 32) mat_s[t] = prm->mat[t];
+    for (int t = lane; t < m * m; t += 32) sm.mat_s[t] = prm->mat[t];
     if (lane < 9) {
         unsigned lo[4], hi[4];
 #pragma unroll
@@ -818,12 +816,26 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
             lo[k] = pk(2 * k < lane ? NEGP : 32767, 2 * k + 1 < lane ? NEGP : 32767);
             hi[k] = pk(2 * k >= 8 - lane ? NEGP : 32767, 2 * k + 1 >= 8 - lane ? NEGP : 32767);
         }
-        cap_lo[lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        cap_hi[lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        sm.cap_lo[lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        sm.cap_hi[lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
     __syncwarp();
+    return sm;
+}
 
-    const PoaJobDesc jd = jobs[job];
+/* One alignment job on one warp: forward DP + backtrace.  Writes *jd.result (every status) but does
+ * NOT publish completion -- the caller does (signal_done), after whatever it still has to move. */
+template <int GAP, int MODE>
+__device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParamsDev *__restrict__ prm, const P16Smem &sm,
+                                            int ring_rows, int ring_cells, int lane) {
+    typedef int16_t ST;
+    typedef Planes<GAP> PL;
+    constexpr int RN = RingPlanes<GAP>::N;
+    int *mat_s = sm.mat_s; uint4 *cap_lo = sm.cap_lo, *cap_hi = sm.cap_hi, *ring_meta = sm.ring_meta; ST *ring_data = sm.ring_data;
+    const int rmask = ring_rows - 1, ring_groups = ring_cells >> 3;
+    const long long clk0 = clock64();
+    uint64_t t_start_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+    const int m = prm->m;
     const JobView jv = open_job(jd.blob);
     ST *planes = reinterpret_cast<ST *>(jd.planes);
     PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
@@ -868,7 +880,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
         int end0 = qlen;
         if (banded) end0 = min(qlen, max(0, qlen - jv.remain(0)) + w);
         const int g1 = end0 >> 3, ngrp = g1 + 1;
-        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
+        if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
             const int g = gp + lane;
             if (g <= g1) {
@@ -919,21 +931,21 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
 
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
-        { const int2 m1 = __ldg(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
-        if (lane < pe - pb) { mypred = __ldg(jv.pred + pb + lane); if (has_ps) myps = __ldg(jv.predscore + pb + lane); }
+        { const int2 m1 = ldb(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
+        if (lane < pe - pb) { mypred = ldb(jv.pred + pb + lane); if (has_ps) myps = ldb(jv.predscore + pb + lane); }
     }
-    int nx_y = n_rows > 3 ? __ldg(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
+    int nx_y = n_rows > 3 ? ldb(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     KP_DECL
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         KP(5)
         int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
         if (i + 1 < n_rows - 1) {
-            const int2 m2 = __ldg(jv.rowmeta + i + 2);
+            const int2 m2 = ldb(jv.rowmeta + i + 2);
             n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y;
-            if (lane < n_pe - pe) { n_mypred = __ldg(jv.pred + pe + lane); if (has_ps) n_myps = __ldg(jv.predscore + pe + lane); }
+            if (lane < n_pe - pe) { n_mypred = ldb(jv.pred + pe + lane); if (has_ps) n_myps = ldb(jv.predscore + pe + lane); }
         }
         const int np = pe - pb;
-        if (!(jv.live && !__ldg(jv.live + i))) {
+        if (!(jv.live && !ldb(jv.live + i))) {
 
         /* ---- predecessor k on lane k: band hints + the two broadcast words ---- */
         unsigned wA = 0, wB = 0;                      /* A: pg0 | png<<12 | near<<25 | slot<<26 ; B: plane offset (8-cell units) */
@@ -957,7 +969,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
             for (int kb = 32; kb < np; kb += 32) {          /* more than 32 predecessors: practically never */
                 const int k = kb + lane;
                 int l2 = INT32_MAX, r2 = INT32_MIN, b2 = INT32_MAX;
-                if (k < np) { const PoaRowInfo pi = rowinfo[__ldg(jv.pred + pb + k)]; l2 = pi.left + 1; r2 = pi.right + 1; b2 = pi.beg; }
+                if (k < np) { const PoaRowInfo pi = rowinfo[ldb(jv.pred + pb + k)]; l2 = pi.left + 1; r2 = pi.right + 1; b2 = pi.beg; }
                 ml = min(ml, __reduce_min_sync(FULL, l2)); mr = max(mr, __reduce_max_sync(FULL, r2)); min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b2));
             }
         }
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
         const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
         const uint32_t need = (uint32_t)ngrp * PL::N;
         if (need > cap32 - cur32) {
-            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cur32; *jd.result = res; signal_done(jd); }
+            if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cur32; *jd.result = res; }
             return;
         }
         const uint32_t my_off = cur32;
@@ -1004,9 +1016,9 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
                 if (kb > 0) {
                     const int k = kb + lane; cA = 0; cB = 0; c_ps = 0;
                     if (k < np) {
-                        const int prow = __ldg(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[prow];
+                        const int prow = ldb(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[prow];
                         const unsigned pg0 = (unsigned)pi.beg >> 3, png = ((unsigned)pi.end >> 3) - pg0 + 1;
-                        cA = pg0 | (png << 12); cB = rowoff[prow]; if (has_ps) c_ps = __ldg(jv.predscore + pb + k);
+                        cA = pg0 | (png << 12); cB = rowoff[prow]; if (has_ps) c_ps = ldb(jv.predscore + pb + k);
                     }
                 }
                 const int nk = min(32, np - kb);
@@ -1223,13 +1235,119 @@ __global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__r
     if (guard_lo || guard_hi || best_score <= NEGP + 2000) res.status = POA_ST_RANGE;    /* scores left the safe int16 window: redo in 32 bits */
     const long long clk1 = clock64();
     res.fwd_clk = clk1 - clk0;
+#ifndef POA_KPROF
+    { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); res.prof[5] = (int64_t)smid; }   /* which SM served the job (diagnostics) */
+#endif
     if (lane == 0) *jd.result = res;
     __syncwarp();
     if (prm->ret_cigar && res.status == POA_ST_OK) {
         poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
         if (lane == 0) jd.result->bt_clk = clock64() - clk1;
     }
+}
+
+
+template <int GAP, int MODE>
+__global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
+                                                           int n_jobs, int ring_rows, int ring_cells) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const int lane = threadIdx.x;
+    const int job = blockIdx.x;
+    if (job >= n_jobs) return;
+    const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
+    const PoaJobDesc jd = jobs[job];
+    p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
+    __syncwarp();
     if (lane == 0) signal_done(jd);
+}
+
+/* ------------------------------------------------------------------ resident kernel
+ * One launch for a whole batch call: CTA s serves slot s for as long as the call lasts.  A slot is
+ * one read group's private workspace in HBM plus a mailbox in mapped pinned host memory.  The host
+ * thread that owns the group writes the flattened graph + read into the slot's staging buffer
+ * (pinned host memory) and bumps mail->seq; the warp sees it, pulls the blob over PCIe/C2C into
+ * HBM itself, aligns, pushes the graph-CIGAR back into pinned host memory and stamps the result.
+ * No stream, launch, memcpy or event per alignment: the ~1000 sequential chains of a batch advance
+ * independently, each limited only by its own (kernel + fusion) latency. */
+__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t *p) {
+    uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+template <int GAP, int MODE>
+__global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *__restrict__ slots, const PoaParamsDev *__restrict__ prm,
+                                                              int n_slots, int ring_rows, int ring_cells,
+                                                              const volatile PoaResidentCtl *ctl, uint64_t budget_ns) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_slots) return;
+    const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
+    const PoaSlotDev sl = slots[blockIdx.x];
+    uint64_t t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const uint64_t deadline = t0 + budget_ns;             /* backstop: a resident CTA never outlives its budget */
+    uint32_t last = 0;
+    for (;;) {
+        /* ---- wait for the next job of this slot ---- */
+        uint32_t seq = 0, polls = 0; bool quit = false;
+        for (;;) {
+            if (lane == 0) {
+                seq = ld_sys_u32(&sl.mail->seq);
+                if (seq == last) {
+                    uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (ld_sys_u32(&ctl->quit) != 0 || now > deadline) quit = true;
+                }
+            }
+            seq = __shfl_sync(FULL, seq, 0); quit = __shfl_sync(FULL, (int)quit, 0) != 0;
+            if (seq != last || quit) break;
+            __nanosleep(polls < 64 ? 2000 : 20000); ++polls;
+        }
+        if (seq == last) return;                         /* quit (or deadline) with no job pending */
+        __threadfence_system();
+        /* ---- the job's description: lanes 0..7 each fetch 16 bytes of the 128-byte mailbox ---- */
+        PoaJobDesc jd; uint32_t bytes;
+        {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (lane < 8) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                       : "l"(reinterpret_cast<const uint4 *>(sl.mail) + lane) : "memory");
+            auto word = [&](int w) { return __shfl_sync(FULL, w & 3 ? (w & 2 ? ((w & 1) ? v.w : v.z) : v.y) : v.x, w >> 2); };
+            auto ptr64 = [&](int w) { return (uint64_t)word(w) | ((uint64_t)word(w + 1) << 32); };
+            bytes = word(1);
+            jd.cigar_cap = (int32_t)word(2); jd.pad = 0;
+            jd.plane_cap_units = ptr64(4);
+            jd.blob = reinterpret_cast<const uint8_t *>(ptr64(6)); jd.planes = reinterpret_cast<void *>(ptr64(8));
+            jd.rowinfo = reinterpret_cast<PoaRowInfo *>(ptr64(10)); jd.rowoff = reinterpret_cast<uint32_t *>(ptr64(12));
+            jd.cigar = reinterpret_cast<uint64_t *>(ptr64(14)); jd.qprof = reinterpret_cast<int16_t *>(ptr64(16));
+            jd.result = sl.result; jd.done = nullptr;
+        }
+        /* ---- pull the blob into HBM (uncached system-memory reads: the staging buffer is rewritten per job) ---- */
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(sl.host_blob); uint4 *dst = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(jd.blob));
+            const uint32_t n16 = (bytes + 15) >> 4;
+            for (uint32_t t = lane; t < n16; t += 32 * 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t k = t + 32 * u;
+                    if (k < n16) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + k) : "memory");
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const uint32_t k = t + 32 * u; if (k < n16) dst[k] = v[u]; }
+            }
+            __threadfence_block(); __syncwarp();
+        }
+        p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
+        __syncwarp();
+        /* ---- graph-CIGAR back to the host, then publish ---- */
+        {
+            int st = 0, n_ops = 0;
+            if (lane == 0) { st = sl.result->status; n_ops = sl.result->n_ops; }
+            st = __shfl_sync(FULL, st, 0); n_ops = __shfl_sync(FULL, n_ops, 0);
+            if (st == POA_ST_OK) for (int t = lane; t < n_ops; t += 32) sl.host_cigar[t] = jd.cigar[t];
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) signal_done(jd);
+        last = seq;
+        __syncwarp();
+    }
 }
 
 /* ------------------------------------------------------------------ launcher */
@@ -1316,4 +1434,38 @@ extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, 
     if (gap_mode == LG) return launch_mode<LG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
     if (gap_mode == AG) return launch_mode<AG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
     return launch_mode<CG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+}
+
+/* ------------------------------------------------------------------ resident kernel launcher */
+/* query_only carries, when launching, the dynamic shared memory to ASK for if that is more than the ring
+ * needs: it caps how many CTAs fit an SM, so the hardware spreads the slots over all SMs evenly. */
+template <int GAP, int MODE>
+static cudaError_t resident_one(int query_only, int *max_ctas_per_sm, const PoaSlotDev *slots, const PoaParamsDev *prm, int n_slots,
+                                int ring_rows, int ring_cells, const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
+    size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
+    if (!query_only && max_ctas_per_sm && (size_t)*max_ctas_per_sm > smem) smem = (size_t)*max_ctas_per_sm;
+    cudaError_t e = cudaFuncSetAttribute(poa_resident_kernel_p16<GAP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    if (query_only) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, poa_resident_kernel_p16<GAP, MODE>, 32, smem);
+    poa_resident_kernel_p16<GAP, MODE><<<n_slots, 32, smem, st>>>(slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns);
+    return cudaGetLastError();
+}
+template <int GAP>
+static cudaError_t resident_mode(int mode, int q, int *o, const PoaSlotDev *slots, const PoaParamsDev *prm, int n, int rr, int rc,
+                                 const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
+    switch (mode) {
+    case GLOBAL: return resident_one<GAP, GLOBAL>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
+    case LOCAL:  return resident_one<GAP, LOCAL>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
+    default:     return resident_one<GAP, EXTEND>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
+    }
+}
+/* query_only: report how many resident CTAs fit one SM (nothing is launched) */
+extern "C" cudaError_t poa_launch_resident_p16(int gap_mode, int align_mode, int query_only, int *max_ctas_per_sm, const PoaSlotDev *slots,
+                                               const PoaParamsDev *prm, int n_slots, int ring_rows, int ring_cells,
+                                               const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
+    switch (gap_mode) {
+    case LG: return resident_mode<LG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
+    case AG: return resident_mode<AG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
+    default: return resident_mode<CG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
+    }
 }

@@ -57,6 +57,9 @@ static void __attribute__((constructor)) poa_build_alphabets(void) {
     /* the batch engine drives up to 32 CUDA streams: give each its own hardware work queue
      * (read by the driver when the context is created; a user setting wins) */
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    /* Load every kernel when the module loads: with lazy loading the FIRST launch of a kernel has to
+     * synchronise the context, which can never complete while the resident kernel is running. */
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     for (c = 0; c < 256; ++c) {
         ab_nt4_table[c] = 4; ab_nt256_table[c] = 'N';
         ab_aa26_table[c] = 26; ab_aa256_table[c] = '*';

@@ -36,6 +36,7 @@ from pathlib import Path
 
 # one hardware work queue per stream of the batch engine (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
