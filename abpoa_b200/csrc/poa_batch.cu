@@ -653,6 +653,7 @@ struct SlotRun {
     GroupState gs;
     bool has_group = false, waiting = false, need_mem = false;
     int generous = 0;               /* the staged job wants the full-rectangle slab (retry after PLANE_OVF) */
+    double t_done = 0;              /* when the slot ran out of work (diagnostics) */
     int r = 0;                      /* read being aligned (waiting / need_mem) or next read to submit */
     poa_job job; Pending pend;
 };
@@ -720,6 +721,9 @@ void worker_resident(Worker wk) {
     int64_t n_res = 0, n_retry = 0, n_parked = 0; double t_kernel_ns = 0, t_fuse = 0, t_stage = 0, t_idle = 0; uint64_t h2d = 0, d2h = 0;
     int64_t cells = 0, fwd_clk = 0, bt_clk = 0;
     int sm_hist[256]; memset(sm_hist, 0, sizeof sm_hist);
+    int64_t n_memwait = 0;
+    const auto t_loop0 = std::chrono::steady_clock::now();
+    double t_dev_idle_ns = 0, t_dev_fetch_ns = 0;
     PhaseClock pc;
 
     auto park = [&](SlotRun &sl, const char *why) {
@@ -735,7 +739,7 @@ void worker_resident(Worker wk) {
         for (;;) {
             if (!sl.has_group) {
                 const int g = wk.next_chunk->fetch_add(1);
-                if (g >= wk.n_groups) return;
+                if (g >= wk.n_groups) { if (sl.t_done == 0) sl.t_done = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop0).count(); return; }
                 group_begin(sl.gs, wk, g, sl.ab);
                 sl.has_group = true; sl.r = 0;
             }
@@ -773,7 +777,7 @@ void worker_resident(Worker wk) {
         bool any_busy = false, progressed = false;
         for (SlotRun &sl : slots) {
             if (sl.need_mem) {                              /* staged, waiting for arena room */
-                any_busy = true;
+                any_busy = true; ++n_memwait;
                 if (poa_resident_submit(rs, sl.slot, abpt, &sl.job.plan, sl.generous)) { sl.need_mem = false; sl.waiting = true; h2d += sl.job.plan.bytes; progressed = true; }
                 continue;
             }
@@ -812,6 +816,7 @@ void worker_resident(Worker wk) {
                     capture_cb(wk.eng, &cj);
                 }
                 if (prof && res.prof[5] >= 0 && res.prof[5] < 256) sm_hist[res.prof[5]] += 1;
+                t_dev_idle_ns += (double)res.prof[3]; t_dev_fetch_ns += (double)res.prof[4];
                 ++n_res; t_kernel_ns += (double)(res.t_end_ns - res.t_start_ns); cells += res.cells; fwd_clk += res.fwd_clk; bt_clk += res.bt_clk;
                 d2h += (uint64_t)res.n_ops * 8 + sizeof(PoaResultDev);
             }
@@ -844,6 +849,9 @@ void worker_resident(Worker wk) {
     if (prof) {
         fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f ms\n", poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3]);
         { int used = 0; for (int z = 0; z < 256; ++z) used += sm_hist[z] > 0; fprintf(stderr, "[worker-resident] this worker's %d slots ran on %d distinct SMs\n", ns, used); }
+        { double lo = 1e30, hi = 0; for (SlotRun &sl : slots) { if (sl.t_done < lo) lo = sl.t_done; if (sl.t_done > hi) hi = sl.t_done; }
+          fprintf(stderr, "[worker-resident] slots ran out of work between %.0f and %.0f ms after the start; sweeps spent waiting for arena memory: %lld\n", lo, hi, (long long)n_memwait); }
+        fprintf(stderr, "[worker-resident] per job on the device: waiting for the host %.2f ms, blob fetch %.2f ms\n", n_res ? t_dev_idle_ns * 1e-6 / n_res : 0.0, n_res ? t_dev_fetch_ns * 1e-6 / n_res : 0.0);
         fprintf(stderr, "[worker-resident %d slots] jobs %lld slab retries %lld parked groups %lld: stage %.0f result+fuse %.0f idle %.0f ms; device time/job %.1f ms\n",
                 ns, (long long)n_res, (long long)n_retry, (long long)n_parked, t_stage, t_fuse, t_idle, n_res ? t_kernel_ns * 1e-6 / n_res : 0.0);
     }

@@ -1284,6 +1284,7 @@ __global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *
     uint64_t t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     const uint64_t deadline = t0 + budget_ns;             /* backstop: a resident CTA never outlives its budget */
     uint32_t last = 0;
+    uint64_t t_free = t0;                                  /* when this slot last became idle */
     for (;;) {
         /* ---- wait for the next job of this slot ---- */
         uint32_t seq = 0, polls = 0; bool quit = false;
@@ -1300,6 +1301,7 @@ __global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *
             __nanosleep(polls < 64 ? 2000 : 20000); ++polls;
         }
         if (seq == last) return;                         /* quit (or deadline) with no job pending */
+        uint64_t t_seen; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_seen));
         __threadfence_system();
         /* ---- the job's description: lanes 0..7 each fetch 16 bytes of the 128-byte mailbox ---- */
         PoaJobDesc jd; uint32_t bytes;
@@ -1321,18 +1323,19 @@ __global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(sl.host_blob); uint4 *dst = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(jd.blob));
             const uint32_t n16 = (bytes + 15) >> 4;
-            for (uint32_t t = lane; t < n16; t += 32 * 4) {
-                uint4 v[4];
+            for (uint32_t t = lane; t < n16; t += 32 * 8) {       /* 8 x 512 B in flight per warp */
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const uint32_t k = t + 32 * u;
                     if (k < n16) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + k) : "memory");
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const uint32_t k = t + 32 * u; if (k < n16) dst[k] = v[u]; }
+                for (int u = 0; u < 8; ++u) { const uint32_t k = t + 32 * u; if (k < n16) dst[k] = v[u]; }
             }
             __threadfence_block(); __syncwarp();
         }
+        uint64_t t_fetched; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_fetched));
         p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
         __syncwarp();
         /* ---- graph-CIGAR back to the host, then publish ---- */
@@ -1342,9 +1345,13 @@ __global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *
             st = __shfl_sync(FULL, st, 0); n_ops = __shfl_sync(FULL, n_ops, 0);
             if (st == POA_ST_OK) for (int t = lane; t < n_ops; t += 32) sl.host_cigar[t] = jd.cigar[t];
         }
+        if (lane == 0) {                                 /* diagnostics: how long the slot sat idle, how long the blob took */
+            sl.result->prof[3] = (int64_t)(t_seen - t_free); sl.result->prof[4] = (int64_t)(t_fetched - t_seen);
+        }
         __threadfence_system();
         __syncwarp();
         if (lane == 0) signal_done(jd);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_free));
         last = seq;
         __syncwarp();
     }

@@ -47,6 +47,9 @@ struct poa_resident {
     PoaParamsDev *d_prm = NULL;
     /* per slot (host): sequence number and the arena slice of the job in flight */
     uint32_t *seq = NULL; uint8_t **job_mem = NULL; size_t *job_bytes = NULL;
+    /* every slot owns a fixed region sized for the usual graph growth (no allocator on the hot path);
+     * only outliers (full-rectangle retries, unusually bushy graphs) borrow from the arena per job */
+    uint8_t *slab = NULL; size_t slot_bytes = 0;
     int64_t launches = 0;
 };
 
@@ -82,6 +85,27 @@ static void *dev_view(void *host_ptr) {
     void *d = NULL;
     CKR(cudaHostGetDevicePointer(&d, host_ptr, 0));
     return d;
+}
+
+/* HBM workspace of one job: blob | rowinfo | rowoff | cigar | query profile | planes */
+struct JobLayout { size_t o_blob, o_info, o_off, o_cig, o_qp, o_planes, total; uint64_t units; size_t cigar_cap; };
+static JobLayout job_layout(const abpoa_para_t *abpt, int n_rows, int qlen, int w, size_t blob_bytes, int generous) {
+    JobLayout L;
+    const int P = abpt->gap_mode == ABPOA_LINEAR_GAP ? 1 : (abpt->gap_mode == ABPOA_AFFINE_GAP ? 3 : 5);
+    uint64_t per_row = (uint64_t)((qlen + 1 + 7) / 8 + 1);
+    if (!generous && w >= 0) { const uint64_t est = (uint64_t)((2 * w + 1 + 32 + 7) / 8 + 2); if (est < per_row) per_row = est; }
+    L.units = per_row * (uint64_t)P * (uint64_t)n_rows;
+    const size_t qstride = (((size_t)qlen + 1 + 7) & ~(size_t)7) + 8;
+    L.cigar_cap = (size_t)qlen + n_rows + 8;
+    size_t off = 0;
+    L.o_blob = off; off += al256(blob_bytes);
+    L.o_info = off; off += al256((size_t)n_rows * sizeof(PoaRowInfo));
+    L.o_off = off; off += al256((size_t)n_rows * 4);
+    L.o_cig = off; off += al256(L.cigar_cap * 8);
+    L.o_qp = off; off += al256((size_t)abpt->m * qstride * 2);
+    L.o_planes = off; off += al256((size_t)L.units * POA_GROUP * 2);
+    L.total = off;
+    return L;
 }
 
 /* Start the resident kernel for one batch call.  want_slots = number of groups that should be in
@@ -130,6 +154,19 @@ extern "C" int poa_resident_start(poa_resident *r, const abpoa_para_t *abpt, int
     }
     if ((size_t)n_slots > r->d_slots_cap) { if (r->d_slots) cudaFree(r->d_slots); CKR(cudaMalloc((void **)&r->d_slots, (size_t)n_slots * sizeof(PoaSlotDev))); r->d_slots_cap = (size_t)n_slots; }
 
+    /* fixed per-slot workspace: graphs of 5 % error reads end near 2.5 rows per read base */
+    {
+        int slot_rows = 3 * qmax + 512;
+        const size_t lim = poa_arena_capacity(r->arena) / 10 * 7;
+        for (;;) {
+            const size_t bb = al256(sizeof(PoaJobHeader) + 64 + ((size_t)slot_rows + 1) * 8 + 32 + (size_t)2 * slot_rows * 4 * (abpt->inc_path_score ? 2 : 1) + 64 + (size_t)qmax + 64);
+            r->slot_bytes = job_layout(abpt, slot_rows, qmax, w, bb, 0).total;
+            if ((size_t)n_slots * r->slot_bytes <= lim || slot_rows <= qmax + 512) break;
+            slot_rows = slot_rows / 10 * 9;
+        }
+        if ((size_t)n_slots * r->slot_bytes > lim) return 0;
+        r->slab = poa_arena_borrow(r->arena, (size_t)n_slots * r->slot_bytes);
+    }
     r->n_slots = n_slots; r->stage_rows = stage_rows; r->qlen_cap = qmax; r->m = abpt->m; r->gap_mode = abpt->gap_mode; r->align_mode = abpt->align_mode;
     r->blob_cap = blob_cap; r->cigar_words = cigar_words;
 
@@ -159,7 +196,7 @@ extern "C" int poa_resident_start(poa_resident *r, const abpoa_para_t *abpt, int
     static const uint64_t budget_ns = [] { const char *e = getenv("ABPOA_GPU_RESIDENT_BUDGET_S"); return (uint64_t)(e && *e ? atoll(e) : 900) * 1000000000ull; }();
     /* Ask for so much shared memory per CTA that exactly ceil(n_slots / SMs) CTAs fit one SM: whatever order
      * the block scheduler fills SMs in, the slots end up spread evenly over the whole chip. */
-    static const bool spread = [] { const char *e = getenv("ABPOA_GPU_RESIDENT_SPREAD"); return !(e && *e == '0'); }();
+    static const bool spread = [] { const char *e = getenv("ABPOA_GPU_RESIDENT_SPREAD"); return e && *e == '1'; }();
     int smem_ask = 0;
     if (spread) {
         const int per = (n_slots + n_sm - 1) / n_sm;
@@ -180,6 +217,7 @@ extern "C" void poa_resident_stop(poa_resident *r) {
     CKR(cudaStreamSynchronize(r->st));
     poa_hold_frees(0);
     for (int s = 0; s < r->n_slots; ++s) if (r->job_mem[s]) { poa_arena_return(r->arena, r->job_mem[s], r->job_bytes[s]); r->job_mem[s] = NULL; }
+    if (r->slab) { poa_arena_return(r->arena, r->slab, (size_t)r->n_slots * r->slot_bytes); r->slab = NULL; }
     r->running = false;
 }
 
@@ -197,28 +235,19 @@ extern "C" uint8_t *poa_resident_stage(poa_resident *r, int slot) { return r->h_
  * to the slot's warp.  generous: planes for the full rectangle (retry of a PLANE_OVF job).  Returns 0
  * when the arena has no room right now (nothing submitted; the caller retries on a later sweep). */
 extern "C" int poa_resident_submit(poa_resident *r, int slot, const abpoa_para_t *abpt, const poa_blob_plan *pl, int generous) {
-    const int P = abpt->gap_mode == ABPOA_LINEAR_GAP ? 1 : (abpt->gap_mode == ABPOA_AFFINE_GAP ? 3 : 5);
-    const uint64_t full = (uint64_t)((pl->qlen + 1 + 7) / 8 + 1);
-    uint64_t per_row = full;
-    if (!generous && pl->w >= 0) { const uint64_t est = (uint64_t)((2 * pl->w + 1 + 32 + 7) / 8 + 2); if (est < per_row) per_row = est; }
-    const uint64_t units = per_row * (uint64_t)P * (uint64_t)pl->n_rows;
-    const size_t qstride = (((size_t)pl->qlen + 1 + 7) & ~(size_t)7) + 8;
-    const size_t cigar_cap = (size_t)pl->qlen + pl->n_rows + 8;
-    size_t off = 0;
-    const size_t o_blob = off; off += al256(pl->bytes);
-    const size_t o_info = off; off += al256((size_t)pl->n_rows * sizeof(PoaRowInfo));
-    const size_t o_off = off; off += al256((size_t)pl->n_rows * 4);
-    const size_t o_cig = off; off += al256(cigar_cap * 8);
-    const size_t o_qp = off; off += al256((size_t)abpt->m * qstride * 2);
-    const size_t o_planes = off; off += al256((size_t)units * POA_GROUP * 2);
-    uint8_t *mem = poa_arena_try_borrow(r->arena, off);
-    if (!mem) return 0;
-    r->job_mem[slot] = mem; r->job_bytes[slot] = off;
+    const JobLayout L = job_layout(abpt, pl->n_rows, pl->qlen, pl->w, pl->bytes, generous);
+    uint8_t *mem;
+    if (L.total <= r->slot_bytes) mem = r->slab + (size_t)slot * r->slot_bytes;          /* the slot's own region */
+    else {
+        mem = poa_arena_try_borrow(r->arena, L.total);
+        if (!mem) return 0;
+        r->job_mem[slot] = mem; r->job_bytes[slot] = L.total;
+    }
     PoaMailbox *mb = r->h_mail + slot;
     *(volatile uint64_t *)&r->h_results[slot].t_end_ns = 0;
-    mb->blob_bytes = (uint32_t)pl->bytes; mb->cigar_cap = (uint32_t)cigar_cap; mb->pad0 = 0; mb->plane_cap_units = units;
-    mb->blob = mem + o_blob; mb->planes = mem + o_planes; mb->rowinfo = (PoaRowInfo *)(mem + o_info); mb->rowoff = (uint32_t *)(mem + o_off);
-    mb->cigar = (uint64_t *)(mem + o_cig); mb->qprof = (int16_t *)(mem + o_qp);
+    mb->blob_bytes = (uint32_t)pl->bytes; mb->cigar_cap = (uint32_t)L.cigar_cap; mb->pad0 = 0; mb->plane_cap_units = L.units;
+    mb->blob = mem + L.o_blob; mb->planes = mem + L.o_planes; mb->rowinfo = (PoaRowInfo *)(mem + L.o_info); mb->rowoff = (uint32_t *)(mem + L.o_off);
+    mb->cigar = (uint64_t *)(mem + L.o_cig); mb->qprof = (int16_t *)(mem + L.o_qp);
     __atomic_store_n(&mb->seq, ++r->seq[slot], __ATOMIC_RELEASE);
     return 1;
 }
