@@ -215,7 +215,8 @@ def load_library(path: os.PathLike | str) -> PoaLibrary:
 
 def product() -> PoaLibrary:
     """The B200 library.  Raises if it has not been built - there is no fallback."""
-    return load_library(PRODUCT_LIB)
+    override = os.environ.get("ABPOA_B200_LIB")          # experiments: another build of the same library
+    return load_library(Path(override) if override else PRODUCT_LIB)
 
 
 def reference() -> PoaLibrary:

@@ -85,7 +85,7 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     e->arena = poa_arena_new(device, want);
     {
         const char *pd = getenv("ABPOA_GPU_PIPE_DEPTH");
-        e->pipe_depth = pd && *pd ? atoi(pd) : 4;
+        e->pipe_depth = pd && *pd ? atoi(pd) : 2;
         if (e->pipe_depth < 1) e->pipe_depth = 1;
         if (e->pipe_depth > 8) e->pipe_depth = 8;
     }
@@ -95,7 +95,10 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
         e->ctx.push_back(c);
     }
     e->wall_ms = 0;
-    { const char *rs = getenv("ABPOA_GPU_RESIDENT"); e->resident = (rs && *rs == '0') ? NULL : poa_resident_new(device, e->arena); }
+    /* resident-kernel engine: opt-in (ABPOA_GPU_RESIDENT=1).  It removes every per-alignment launch and copy,
+     * but on this box its alignments run ~1.4x slower than under the launch-per-round path,
+     * so the pipelined launch path stays the default. */
+    { const char *rs = getenv("ABPOA_GPU_RESIDENT"); e->resident = (rs && *rs == '1') ? poa_resident_new(device, e->arena) : NULL; }
     e->res_jobs = e->res_fallback = 0; e->res_kernel_ms = 0; e->res_cells = e->res_fwd_clk = e->res_bt_clk = 0; e->res_h2d = e->res_d2h = 0; e->res_launches = 0; e->capture_on = false; e->parked_vec = NULL;
     return e;
 }

@@ -1247,8 +1247,15 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 }
 
 
+/* POA_P16_MINB (build-time, experiments): minimum resident CTAs per SM the compiler must allow for, i.e. a
+ * register cap of 65536 / (32 * POA_P16_MINB) per thread */
+#ifdef POA_P16_MINB
+#define POA_P16_BOUNDS __launch_bounds__(32, POA_P16_MINB)
+#else
+#define POA_P16_BOUNDS __launch_bounds__(32)
+#endif
 template <int GAP, int MODE>
-__global__ void __launch_bounds__(32) poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
+__global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
                                                            int n_jobs, int ring_rows, int ring_cells) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const int lane = threadIdx.x;

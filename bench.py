@@ -263,8 +263,16 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "poa_align_kernel", "bytes_per_cell": (bytes16 + bytes32) / max(rp["cells"], 1), "mean_in_degree": d,
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+    traffic, traffic_note = None, None
+    tf = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tf.exists():
+        t_ = json.loads(tf.read_text())
+        traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
+        traffic_note = (f"ncu capture of one replay launch ({t_['jobs']} jobs, {t_['duration_ms']:.1f} ms): "
+                        f"{t_['dram_bytes_write'] / 1e9:.1f} GB written + {t_['dram_bytes_read'] / 1e9:.1f} GB read; see {t_['source']}")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": "poa_align_kernel_p16", "bytes_per_cell": (bytes16 + bytes32) / max(rp["cells"], 1), "mean_in_degree": d,
                 "peak_source": peak_src, "launches_per_pass": rp["launches"], "replay_mismatches": rp["mismatches"],
                 "int16_cell_fraction": rp["cells16"] / max(rp["cells"], 1)}
 
@@ -278,10 +286,11 @@ def main():
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int16/int32 planes, int32 registers", "data": "synthetic", "config": cfgdesc,
+        "dtype": "int16 (packed int16x2 DPX arithmetic; int32 kernel only as overflow fallback)", "data": "synthetic", "config": cfgdesc,
         "clocks": clocks, "reads_per_s": tot_reads / elapsed,
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
-                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl or "auto"},
+                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl or "auto",
+                "engine": "resident kernel (ABPOA_GPU_RESIDENT=1)" if os.environ.get("ABPOA_GPU_RESIDENT") == "1" else "pipelined launches, one per half-chunk round"},
         "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"]},

@@ -58,3 +58,21 @@ def test_batch_amino_acid(reference_lib):
     cfg = synth.WORKLOADS["aa_blosum62_2k"].cfg
     groups = [synth.make_group(1100 + g, 6, 500, 0.10, m=27) for g in range(10)]
     check_batch(reference_lib, cfg, groups, n_workers=2, groups_per_launch=4)
+
+
+@pytest.mark.parametrize("which", ["affine", "convex_msa_ragged"])
+def test_batch_resident_engine(reference_lib, monkeypatch, which):
+    """The opt-in resident-kernel engine (ABPOA_GPU_RESIDENT=1: one slot per group, mailboxes in
+    mapped pinned memory, no launch per alignment) must give the same per-read results."""
+    monkeypatch.setenv("ABPOA_GPU_RESIDENT", "1")
+    monkeypatch.setenv("ABPOA_GPU_RESIDENT_BUDGET_S", "120")
+    if which == "affine":
+        cfg = PoaConfig(**AFFINE)
+        groups = [synth.make_group(500 + g, 8, 300 + 20 * (g % 5), 0.05) for g in range(70)]
+        check_batch(reference_lib, cfg, groups, n_workers=4)
+    else:
+        cfg = PoaConfig(out_msa=True)
+        groups = [synth.make_group(700 + g, 3 + (g % 6), 200 + 150 * (g % 4), 0.06) for g in range(23)]
+        groups.append([])
+        groups.append(synth.make_group(9, 1, 100, 0.0))
+        check_batch(reference_lib, cfg, groups, n_workers=3)
