@@ -58,6 +58,27 @@ def physical_cores() -> int:
 # ------------------------------------------------------------------------------------------------
 # reference arm (CPU): oracle/_ref/libabpoa_ref.so, one process per core, whole groups per process
 # ------------------------------------------------------------------------------------------------
+def rank_cpu_share(rank: int, world: int) -> list[int]:
+    """CPUs for one rank when several ranks share the host: the allowed physical cores, sorted by
+    (package, core), are cut into `world` contiguous slices and a rank takes ALL hardware threads
+    of its slice (ranks 0..world/2-1 land on socket 0, the rest on socket 1 on a two-socket box)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    by_core: dict[tuple[int, int], list[int]] = {}
+    for c in allowed:
+        try:
+            pkg = int(Path(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id").read_text())
+            core = int(Path(f"/sys/devices/system/cpu/cpu{c}/topology/core_id").read_text())
+        except Exception:
+            pkg, core = 0, c
+        by_core.setdefault((pkg, core), []).append(c)
+    cores = sorted(by_core)
+    n = len(cores)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    if hi <= lo:
+        return allowed
+    return sorted(c for k in cores[lo:hi] for c in by_core[k])
+
+
 def _ref_worker(args):
     wname, seeds, n_reads, length = args
     from abpoa_b200 import capi, synth
@@ -198,9 +219,15 @@ def main():
     packed = PackedGroups(groups)
     lib = capi.product()
     abpt = make_para(lib, w.cfg)
-    workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(32, (os.cpu_count() or 8) // 2 // max(world, 1)))
+    # host threads: one per physical core at N=1 (32 measured best: more streams than hardware queues hurts);
+    # with several ranks on one host every rank gets its own slice of cores and uses all their hardware threads
+    if world > 1:
+        share = rank_cpu_share(local_rank, world)
+        os.sched_setaffinity(0, share)                 # the engine pins its workers inside the process's CPU set
+        workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(32, len(share)))
+    else:
+        workers = int(os.environ.get("ABPOA_GPU_WORKERS", "0")) or max(4, min(32, (os.cpu_count() or 8) // 2))
     gpl = int(os.environ.get("ABPOA_GPU_GROUPS_PER_LAUNCH", "0"))      # 0: the engine spreads the groups over workers x pipe depth
-    os.environ.setdefault("ABPOA_GPU_CPU_BASE", str(local_rank * workers))      # disjoint cores per rank
     eng = BatchEngine(device=local_rank, n_workers=workers, groups_per_launch=gpl)
 
     for _ in range(args.warmup):
