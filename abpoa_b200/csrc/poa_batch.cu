@@ -67,7 +67,8 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
     unsigned hc = std::thread::hardware_concurrency();
     if (n_workers <= 0) {
         const char *env = getenv("ABPOA_GPU_WORKERS");
-        n_workers = env && *env ? atoi(env) : (int)(hc ? hc : 8);
+        n_workers = env && *env ? atoi(env) : (int)(hc ? (hc + 1) / 2 : 8);      /* ~ one per physical core */
+        if (n_workers > 32 && !(env && *env)) n_workers = 32;                    /* 2 streams each: stay within the 32 hardware work queues x 2 */
         if (n_workers > 64) n_workers = 64;
         if (n_workers < 2) n_workers = 2;
     }

@@ -90,6 +90,17 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
     int np = 0;
     for (int r = 0; r < n_rows; ++r) {
         const int id = id_of_index[r];
+        if (r + 16 < n_rows) {                       /* rows ahead: their degree, residue, band centre and in-edge row */
+            const int ia = id_of_index[r + 16];
+            __builtin_prefetch(cin + ia, 0); __builtin_prefetch(cbase + ia, 0);
+            if (with_remain) __builtin_prefetch(max_remain + ia, 0);
+            __builtin_prefetch(poa_graph_in_ids_inline(abg, ia), 0);
+        }
+        if (r + 8 < n_rows) {                        /* second level: the row numbers of the predecessors of a nearer row */
+            const int ib = id_of_index[r + 8];
+            const int nb = cin[ib] < 4 ? cin[ib] : 4; const int *ids = poa_graph_in_ids_inline(abg, ib);
+            for (int e = 0; e < nb; ++e) __builtin_prefetch(index_of_id + ids[e], 0);
+        }
         const int rem = with_remain ? max_remain[id] - end_remain - 1 : 0;
         rowmeta[2 * r] = np;
         rowmeta[2 * r + 1] = (int32_t)((uint32_t)rem << 8) | cbase[id];

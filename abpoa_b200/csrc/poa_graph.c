@@ -29,6 +29,7 @@ __thread double poa_prof_ms[8];
 static inline double prof_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 #define POA_INL 4                 /* inline edge slots per node and direction */
+#define POA_FUSE_AHEAD 12          /* graph-CIGAR ops of look-ahead for the fusion loop's prefetches */
 
 typedef struct {
     abpoa_graph_t pub;          /* must stay first: callers hold &pub */
@@ -573,6 +574,11 @@ void abpoa_BFS_set_node_remain(abpoa_graph_t *abg, int src_id, int sink_id) {
     remain[sink_id] = -1;
     for (int i = hi - 1; i >= lo; --i) {
         const int cur = order[i];
+        if (i - 16 >= lo) {                          /* the order is known: fetch the mirror rows of the nodes ahead */
+            const size_t v = (size_t)order[i - 16];
+            __builtin_prefetch(cout + v, 0); __builtin_prefetch(x->out_id4 + v * POA_INL, 0); __builtin_prefetch(x->out_w4 + v * POA_INL, 0);
+            __builtin_prefetch(remain + v, 1);
+        }
         const int ne = cout[cur]; const int *oid = out_ids_of(x, cur);
         if (ne == 1) remain[cur] = remain[oid[0]] + 1;
         else {
@@ -772,6 +778,16 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
         for (int c = 0; c < res.n_cigar; ++c) {
             const abpoa_cigar_t cg = res.graph_cigar[c];
             const int op = (int)(cg & 0xf);
+            if (c + POA_FUSE_AHEAD < res.n_cigar) {      /* the path's node ids are known in advance: pull their mirror rows in early */
+                const abpoa_cigar_t ca = res.graph_cigar[c + POA_FUSE_AHEAD];
+                if ((ca & 0xf) == ABPOA_CMATCH) {
+                    const size_t v = (size_t)((ca >> 34) & 0x3fffffff);
+                    __builtin_prefetch(x->in_id4 + v * POA_INL, 1); __builtin_prefetch(x->in_w4 + v * POA_INL, 1);
+                    __builtin_prefetch(x->out_id4 + v * POA_INL, 1); __builtin_prefetch(x->out_w4 + v * POA_INL, 1);
+                    __builtin_prefetch(x->cin + v, 0); __builtin_prefetch(x->cout + v, 0); __builtin_prefetch(x->cnread + v, 1);
+                    __builtin_prefetch(x->cbase + v, 0);
+                }
+            }
             if (op == ABPOA_CMATCH) {
                 const int node_id = (int)((cg >> 34) & 0x3fffffff);
                 ++qi;
@@ -883,6 +899,8 @@ int64_t poa_graph_edge_count(const abpoa_graph_t *abg) { return cgx(abg)->n_edge
 const uint8_t *poa_graph_bases(const abpoa_graph_t *abg) { return cgx(abg)->cbase; }
 const int *poa_graph_in_degrees(const abpoa_graph_t *abg) { return cgx(abg)->cin; }
 const int *poa_graph_in_ids(const abpoa_graph_t *abg, int id) { return in_ids_of(cgx(abg), id); }
+/* address of the node's inline in-edge slots (valid to PREFETCH even when the list has spilled to the heap) */
+const int *poa_graph_in_ids_inline(const abpoa_graph_t *abg, int id) { return cgx(abg)->in_id4 + (size_t)id * POA_INL; }
 
 /* debugging aid: copy out / clear this thread's phase timers */
 void poa_prof_snapshot(double *out8, int clear) {

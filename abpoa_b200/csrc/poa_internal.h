@@ -63,6 +63,7 @@ int64_t poa_graph_edge_count(const abpoa_graph_t *abg);
 const uint8_t *poa_graph_bases(const abpoa_graph_t *abg);
 const int *poa_graph_in_degrees(const abpoa_graph_t *abg);
 const int *poa_graph_in_ids(const abpoa_graph_t *abg, int id);
+const int *poa_graph_in_ids_inline(const abpoa_graph_t *abg, int id);
 
 /* log2 / popcount tables the reference exposes as globals (src/abpoa_output.c:13-14) */
 void poa_set_65536_table(void);
