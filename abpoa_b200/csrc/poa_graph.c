@@ -775,6 +775,8 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
         x->tracking = x->fast_order && abg->is_topological_sorted && abpt->align_mode == ABPOA_GLOBAL_MODE &&
                       beg_node_id == ABPOA_SRC_NODE_ID && end_node_id == ABPOA_SINK_NODE_ID;
         x->old_n = abg->node_n; x->n_new = 0; x->n_new_edges = 0;
+        const int fast_ok = !add_read_id && !add_read_weight;       /* no per-edge read sets / read weights to maintain */
+        x->public_stale = 1;
         for (int c = 0; c < res.n_cigar; ++c) {
             const abpoa_cigar_t cg = res.graph_cigar[c];
             const int op = (int)(cg & 0xf);
@@ -791,6 +793,18 @@ int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, i
             if (op == ABPOA_CMATCH) {
                 const int node_id = (int)((cg >> 34) & 0x3fffffff);
                 ++qi;
+                /* by far the most common step: the read follows the heaviest edge between two nodes it matches
+                 * (first slot of both inline lists).  Bumping a first slot cannot break the weight order. */
+                if (fast_ok && !last_is_new && x->cbase[node_id] == seq[qi] && (last_id != beg_node_id || inc_both_ends)) {
+                    const size_t v = (size_t)node_id * POA_INL, u = (size_t)last_id * POA_INL;
+                    if (x->cin[node_id] <= POA_INL && x->cout[last_id] <= POA_INL && x->in_id4[v] == last_id && x->out_id4[u] == node_id) {
+                        x->in_w4[v] += weight[qi]; x->out_w4[u] += weight[qi];
+                        x->cnread[last_id] += 1;
+                        last_id = node_id;
+                        if (qpos_to_node_id) qpos_to_node_id[qi] = last_id;
+                        continue;
+                    }
+                }
                 const uint8_t add = (last_id != beg_node_id || inc_both_ends) ? 1 : 0;
                 int target, target_is_new = 0;
                 if (gx(abg)->cbase[node_id] == seq[qi]) target = node_id;
