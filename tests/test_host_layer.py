@@ -133,3 +133,17 @@ def test_handle_reuse_after_reset_with_high_degree_nodes(product_lib):
         s.generate()
         assert all(np.array_equal(x, y) for x, y in zip(s.consensus(), fresh["cons"]))
         assert all(np.array_equal(x, y) for x, y in zip(s.msa_rows(), fresh["msa"]))
+
+
+def test_bench_rank_cpu_shares_are_disjoint_and_complete():
+    """bench.py gives every rank of a multi-GPU run its own slice of the host's cores."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    allowed = sorted(os.sched_getaffinity(0))
+    for world in (1, 2, 4):
+        shares = [mod.rank_cpu_share(r, world) for r in range(world)]
+        flat = [c for sh in shares for c in sh]
+        if len(allowed) >= world:
+            assert sorted(flat) == allowed and len(set(flat)) == len(flat), (world, shares)

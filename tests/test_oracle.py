@@ -49,3 +49,18 @@ def test_spliced_order_matches_golden(product_lib, name):
     spliced, fallback = r["order_stats"]
     assert spliced > 0 and fallback == 0, (spliced, fallback)
     assert_digest_equal(group_digest(r, cfg.m), GOLDEN["cases"][name], name)
+
+
+@pytest.mark.parametrize("name", GLOBAL_CASES)
+def test_consensus_only_mode_matches_golden(product_lib, name):
+    """Consensus-only runs (no RC-MSA, hence no per-edge read sets) take the host's fast paths: the
+    heaviest-edge shortcut of the fusion loop and the spliced topological order.  Alignments, consensus
+    and coverage must equal the golden vectors (which were generated with the MSA on)."""
+    case = CASES[name]
+    cfg = PoaConfig(**case["cfg"])
+    r = run_group(product_lib, cfg, case_reads(case), want_msa=False, use_oracle=True, fast_order=True)
+    got, want = group_digest(r, cfg.m), GOLDEN["cases"][name]
+    assert len(got["alns"]) == len(want["alns"])
+    for i, (x, y) in enumerate(zip(got["alns"], want["alns"])):
+        assert x == y, f"{name} read {i}: {x} != {y}"
+    assert got["cons"] == want["cons"] and got["cov_sha1"] == want["cov_sha1"], name
