@@ -55,6 +55,12 @@ def main():
     dll.poa_prof_snapshot.argtypes = [C.POINTER(C.c_double), C.c_int]
     dll.poa_add_alignment_nosync.restype = C.c_int
     prof = (C.c_double * 8)()
+
+    class BlobPlan(C.Structure):
+        _fields_ = [("n_rows", C.c_int), ("n_pred_max", C.c_int), ("qlen", C.c_int), ("beg_index", C.c_int), ("whole_graph", C.c_int),
+                    ("w", C.c_int), ("with_remain", C.c_int), ("with_score", C.c_int), ("bytes", C.c_size_t)]
+    plan = BlobPlan()
+    blob = np.zeros(1 << 20, dtype=np.uint8)
     n_reads = max(len(g) for g in groups)
     for rep in range(reps):
         abs_ = [lib.abpoa_init() for _ in range(G)]
@@ -62,7 +68,7 @@ def main():
             lib.abpoa_reset(abs_[g], abpt, max(len(r) for r in groups[g]))
             dll.poa_graph_set_fast_order(abs_[g].contents.abg, fast)
         dll.poa_prof_snapshot(prof, 1)
-        t_sort = t_fuse = 0.0
+        t_sort = t_fuse = t_flat = 0.0
         for r in range(n_reads):
             for g in range(G):
                 if r >= len(groups[g]):
@@ -80,12 +86,21 @@ def main():
                 seq = np.ascontiguousarray(groups[g][r], dtype=np.uint8)
                 dll.poa_add_alignment_nosync(ab, abpt, 0, 1, seq.ctypes.data_as(c_u8_p), None, len(seq), None, res, r, len(groups[g]), 1)
                 t2 = time.perf_counter()
+                # flattening of the fused graph for the NEXT read (what the batch worker does before a launch)
+                if r + 1 < len(groups[g]):
+                    nxt = np.ascontiguousarray(groups[g][r + 1], dtype=np.uint8)
+                    dll.poa_blob_plan_make(C.byref(plan), abg, abpt, 0, 1, len(nxt))
+                    if plan.bytes > len(blob):
+                        blob = np.zeros(int(plan.bytes) * 2, dtype=np.uint8)
+                    dll.poa_blob_fill(blob.ctypes.data_as(c_u8_p), C.byref(plan), abg, abpt, 0, 1, nxt.ctypes.data_as(c_u8_p))
+                t3 = time.perf_counter()
                 t_sort += t1 - t0
                 t_fuse += t2 - t1
+                t_flat += t3 - t2
         dll.poa_prof_snapshot(prof, 0)
         n_f = sum(len(g) for g in groups)
         print(f"{name} G={G}: per fusion: sort {t_sort / n_f * 1e3:.3f} ms (bfs {prof[0] / n_f:.3f} order {prof[1] / n_f:.3f} remain {prof[2] / n_f:.3f}) "
-              f"fuse {t_fuse / n_f * 1e3:.3f} ms (thread_cigar {prof[3] / n_f:.3f})", flush=True)
+              f"fuse {t_fuse / n_f * 1e3:.3f} ms (thread_cigar {prof[3] / n_f:.3f}) flatten {t_flat / n_f * 1e3:.3f} ms", flush=True)
         sig = 0
         for g in range(G):
             sig = (sig * 1000003 + abs_[g].contents.abg.contents.node_n) & 0xFFFFFFFF
