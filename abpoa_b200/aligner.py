@@ -186,14 +186,15 @@ class PoaSession:
         self.n_seq += 1
         self.ab.contents.abs.contents.n_seq = self.n_seq     # as pyabpoa.pyx:243 does
 
-    def run_reads(self, reads: Sequence[np.ndarray], count_cells: bool = True) -> list[ReadAlignment]:
-        """Progressive POA of one group, read by read, recording every alignment."""
+    def run_reads(self, reads: Sequence[np.ndarray], count_cells: bool = True, weights: Sequence[np.ndarray] | None = None) -> list[ReadAlignment]:
+        """Progressive POA of one group, read by read, recording every alignment.
+        weights: per-read base weights (the reference's -Q quality weights), used when cfg.use_qv."""
         self.reset(max((len(r) for r in reads), default=1024))
         out = []
-        for r in reads:
+        for i, r in enumerate(reads):
             a, res = self.align(r, count_cells)
             out.append(a)
-            self.add(r, res, len(reads))
+            self.add(r, res, len(reads), weights[i] if weights is not None else None)
         return out
 
     # ---- whole-group call ---------------------------------------------------------------

@@ -34,7 +34,18 @@ CASES = {
     "syn_gap_at_end": dict(cfg=dict(put_gap_at_end=True), synth=(114, 8, 600, 0.08, 5)),
     "syn_ragged": dict(cfg=dict(), synth_ragged=(115, [900, 40, 1200, 7, 600, 1, 1000])),
     "syn_high_error": dict(cfg=dict(), synth=(116, 8, 800, 0.25, 5)),
+    # -Q: per-base quality weights become edge weights (predecessor order, consensus); the DP itself is unchanged
+    "syn_qv_weights": dict(cfg=dict(use_qv=True), synth=(117, 8, 600, 0.08, 5), weights=117),
 }
+
+
+def case_weights(case, reads):
+    """Deterministic quality-like weights (1..40 per base) for cases that ask for them, else None."""
+    if "weights" not in case:
+        return None
+    import numpy as np
+    rng = np.random.default_rng(case["weights"])
+    return [rng.integers(1, 41, size=len(r)).astype(np.int32) for r in reads]
 
 
 def case_reads(case):

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 from abpoa_b200 import capi, synth  # noqa: E402
 from abpoa_b200.aligner import PoaConfig, decode  # noqa: E402
-from cases import CASES, case_reads  # noqa: E402
+from cases import CASES, case_reads, case_weights  # noqa: E402
 from helpers import run_group  # noqa: E402
 
 
@@ -34,7 +34,7 @@ def main():
     for name, case in CASES.items():
         cfg = PoaConfig(**case["cfg"])
         reads = case_reads(case)
-        r = run_group(ref, cfg, reads, want_msa=True)
+        r = run_group(ref, cfg, reads, want_msa=True, weights=case_weights(case, reads))
         out["cases"][name] = {
             "alns": [
                 {"aligned": a.aligned, "score": a.best_score, "cells": a.cells, "n_cigar": int(len(a.cigar)), "cigar_sha1": sha(a.cigar),

@@ -28,7 +28,7 @@ def read_fasta(path: Path, m: int = 5) -> list[np.ndarray]:
     return seqs
 
 
-def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: bool = False, fast_order: bool = False):
+def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: bool = False, fast_order: bool = False, weights=None):
     """Progressive POA of one group through `lib`; returns per-read records + consensus (+ MSA).
 
     use_oracle=True: the graph / consensus / MSA code of `lib` is driven, but every
@@ -43,10 +43,10 @@ def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: boo
             if fast_order:      # what the batch engine does per handle: spliced topological order between reads
                 s.lib.dll.poa_graph_set_fast_order(s.ab.contents.abg, 1)
             alns = []
-            for r in reads:
+            for i, r in enumerate(reads):
                 a, res = oracle_align(s, r)
                 alns.append(a)
-                s.add(r, res, len(reads))
+                s.add(r, res, len(reads), weights[i] if weights is not None else None)
             if fast_order:      # ... and the reference's Kahn order again before consensus / MSA
                 import ctypes as C
                 spl, fb = C.c_int64(0), C.c_int64(0)
@@ -58,7 +58,7 @@ def run_group(lib, cfg: PoaConfig, reads, want_msa: bool = True, use_oracle: boo
                     g.is_topological_sorted = 0
                     s.lib.abpoa_topological_sort(s.ab.contents.abg, s.abpt)
         else:
-            alns = s.run_reads(reads)
+            alns = s.run_reads(reads, weights=weights)
         s.generate()
         return {
             "order_stats": getattr(s, "order_stats", None),

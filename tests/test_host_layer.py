@@ -112,6 +112,19 @@ def test_product_has_no_cpu_fallback(tmp_path):
     assert "no CUDA device" in p.stderr or "CUDA" in p.stderr
 
 
+def test_batch_engine_has_no_cpu_fallback():
+    """The batched entry point must refuse to start without a CUDA device, too."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from abpoa_b200.batch import BatchEngine\n"
+        "e = BatchEngine(n_workers=2)\n"
+        "print('STARTED')\n" % str(ROOT))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert p.returncode != 0 and "STARTED" not in p.stdout
+    assert "no CUDA device" in p.stderr or "CUDA" in p.stderr
+
+
 def test_handle_reuse_after_reset_with_high_degree_nodes(product_lib):
     """A handle that held a bushy graph (nodes with more than 4 edges, spilled out of the inline
     slots) must give the same result as a fresh handle after abpoa_reset()."""

@@ -13,7 +13,7 @@ from pathlib import Path
 import pytest
 
 from abpoa_b200.aligner import PoaConfig
-from cases import CASES, case_reads
+from cases import CASES, case_reads, case_weights
 from helpers import assert_digest_equal, assert_group_equal, group_digest, run_group
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
@@ -23,7 +23,8 @@ GOLDEN = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text
 def test_oracle_matches_golden(product_lib, name):
     case = CASES[name]
     cfg = PoaConfig(**case["cfg"])
-    got = group_digest(run_group(product_lib, cfg, case_reads(case), use_oracle=True), cfg.m)
+    reads = case_reads(case)
+    got = group_digest(run_group(product_lib, cfg, reads, use_oracle=True, weights=case_weights(case, reads)), cfg.m)
     assert_digest_equal(got, GOLDEN["cases"][name], name)
 
 
@@ -45,7 +46,8 @@ def test_spliced_order_matches_golden(product_lib, name):
     (score, graph-CIGAR in node ids, end points, DP cells), consensus and RC-MSA must be unchanged."""
     case = CASES[name]
     cfg = PoaConfig(**case["cfg"])
-    r = run_group(product_lib, cfg, case_reads(case), use_oracle=True, fast_order=True)
+    reads = case_reads(case)
+    r = run_group(product_lib, cfg, reads, use_oracle=True, fast_order=True, weights=case_weights(case, reads))
     spliced, fallback = r["order_stats"]
     assert spliced > 0 and fallback == 0, (spliced, fallback)
     assert_digest_equal(group_digest(r, cfg.m), GOLDEN["cases"][name], name)
@@ -58,7 +60,8 @@ def test_consensus_only_mode_matches_golden(product_lib, name):
     and coverage must equal the golden vectors (which were generated with the MSA on)."""
     case = CASES[name]
     cfg = PoaConfig(**case["cfg"])
-    r = run_group(product_lib, cfg, case_reads(case), want_msa=False, use_oracle=True, fast_order=True)
+    reads = case_reads(case)
+    r = run_group(product_lib, cfg, reads, want_msa=False, use_oracle=True, fast_order=True, weights=case_weights(case, reads))
     got, want = group_digest(r, cfg.m), GOLDEN["cases"][name]
     assert len(got["alns"]) == len(want["alns"])
     for i, (x, y) in enumerate(zip(got["alns"], want["alns"])):
