@@ -11,6 +11,10 @@
  *
  * Results are identical to calling abpoa_msa() group by group (reference
  * src/abpoa_align.c:401-471) with the same abpoa_para_t.
+ *
+ * Two engines sit behind abpoa_gpu_msa_batch: pipelined launches (default; each
+ * worker keeps ABPOA_GPU_PIPE_DEPTH sub-chunks in flight) and, with ABPOA_GPU_RESIDENT=1, one
+ * resident kernel per call that is fed through per-group mailboxes in mapped pinned memory.
  */
 #ifndef ABPOA_GPU_H
 #define ABPOA_GPU_H
@@ -48,7 +52,7 @@ typedef struct {
 typedef struct {
     double kernel_ms;                   /* sum over streams of CUDA-event time of the alignment kernels */
     double wall_ms;                     /* wall time of the last abpoa_gpu_msa_batch call               */
-    int64_t cells, alignments, launches, retries;
+    int64_t cells, alignments, launches, retries;    /* launches: kernel launches (the resident engine: one per call) */
     uint64_t h2d_bytes, d2h_bytes;
     int n_workers, device;
     int64_t fwd_clk, bt_clk;            /* SM clock cycles inside the forward DP / the backtrace, summed over alignments */
