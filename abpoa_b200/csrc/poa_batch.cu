@@ -172,8 +172,10 @@ extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int wa
     return 0;
 }
 
+static void parked_delete(abpoa_gpu_batch *e);
 extern "C" void abpoa_gpu_batch_free(abpoa_gpu_batch_t *e) {
     if (e && e->resident) { poa_resident_free(e->resident); e->resident = NULL; }
+    if (e) parked_delete(e);
     if (!e) return;
     abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_free(c);
@@ -889,6 +891,10 @@ void finish_parked(abpoa_gpu_batch *e, abpoa_para_t *abpt, int flags, const abpo
 }
 
 }  // namespace
+
+static void parked_delete(abpoa_gpu_batch *e) {
+    if (e->parked_vec) { delete (std::vector<ParkedGroup> *)e->parked_vec; e->parked_vec = NULL; }
+}
 
 extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
                                    abpoa_gpu_group_result_t *results, int flags) {
