@@ -97,3 +97,19 @@ def test_linear_banded_decisions_match_reference(product_lib, reference_lib):
         assert all(np.array_equal(p, q) for p, q in zip(a["msa"], b["msa"])), f"seed {seed}: RC-MSA"
     assert n_aln >= 250
     print(f"banded linear: {n_aln} alignments, {n_band_diff} with a different band (cell count)")
+
+
+@pytest.mark.parametrize("shape", [(301, 14, 4000, 0.10), (302, 25, 1500, 0.20), (303, 40, 600, 0.30)])
+def test_spliced_order_on_bushy_graphs_vs_live_reference(product_lib, reference_lib, shape):
+    """Deeper groups with high error rates grow large aligned-node groups and long insertion chains --
+    the cases the splice rules (anchor behind the whole aligned group, inherited anchors) exist for.
+    Every alignment, the consensus and the RC-MSA must equal the live reference, with no fallback to
+    the full Kahn pass."""
+    from abpoa_b200 import synth
+    seed, n, length, err = shape
+    reads = synth.make_group(seed, n, length, err)
+    cfg = PoaConfig()
+    a = run_group(product_lib, cfg, reads, use_oracle=True, fast_order=True)
+    spliced, fallback = a["order_stats"]
+    assert spliced >= n - 2 and fallback == 0, (spliced, fallback)
+    assert_group_equal(a, run_group(reference_lib, cfg, reads), f"bushy {shape}")
