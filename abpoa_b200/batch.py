@@ -88,7 +88,8 @@ def fnv1a_words(words: np.ndarray) -> int:
 class PackedGroups:
     """Host-side argument block for abpoa_gpu_msa_batch (keeps the numpy buffers alive)."""
 
-    def __init__(self, groups: Sequence[Sequence[np.ndarray]]):
+    def __init__(self, groups: Sequence[Sequence[np.ndarray]], weights=None):
+        """weights: optional per group list of per-read int32 base weights (the reference's -Q), or None."""
         self.n = len(groups)
         self._keep = []
         self.arr = (abpoa_gpu_group_t * self.n)()
@@ -104,6 +105,11 @@ class PackedGroups:
             self.arr[g].seq_lens = C.cast(lens, c_int_p)
             self.arr[g].seqs = C.cast(ptrs, C.POINTER(c_u8_p))
             self.arr[g].qual_weights = None
+            if weights is not None and weights[g] is not None:
+                ws = [np.ascontiguousarray(w, dtype=np.int32) for w in weights[g]]
+                wp = (c_int_p * n)(*[w.ctypes.data_as(c_int_p) for w in ws])
+                self._keep += [ws, wp]
+                self.arr[g].qual_weights = C.cast(wp, C.POINTER(c_int_p))
             self.total_bases += sum(len(a) for a in arrs)
             self.total_reads += n
 
@@ -148,10 +154,10 @@ class BatchEngine:
             self.d.abpoa_gpu_group_result_free(C.byref(r))
         return out
 
-    def run(self, cfg: PoaConfig, groups, record_reads: bool = False):
+    def run(self, cfg: PoaConfig, groups, record_reads: bool = False, weights=None):
         abpt = make_para(self.lib, cfg)
         try:
-            return self.run_packed(abpt, PackedGroups(groups), record_reads)
+            return self.run_packed(abpt, PackedGroups(groups, weights), record_reads)
         finally:
             self.lib.abpoa_free_para(abpt)
 

@@ -39,11 +39,6 @@ struct abpoa_gpu_batch {
     std::mutex cap_mu; std::vector<CapturedJob> captured;
     int dev, n_workers, groups_per_launch;
     int pipe_depth;                 /* sub-chunks (stream contexts) each worker keeps in flight */
-    poa_resident *resident;         /* resident-kernel engine (NULL: ABPOA_GPU_RESIDENT=0) */
-    int64_t res_jobs, res_fallback; /* alignments served by slots / sent through the launch path instead */
-    double res_kernel_ms; int64_t res_cells, res_fwd_clk, res_bt_clk; uint64_t res_h2d, res_d2h; int64_t res_launches;
-    bool capture_on;
-    void *parked_vec;               /* std::vector<ParkedGroup>* (type lives below) */
     int fast_order;                 /* spliced topological order in global mode (ABPOA_GPU_EXACT_ORDER=1 turns it off) */
     poa_arena *arena;
     std::vector<poa_dev_ctx *> ctx;
@@ -96,11 +91,6 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
         e->ctx.push_back(c);
     }
     e->wall_ms = 0;
-    /* resident-kernel engine: opt-in (ABPOA_GPU_RESIDENT=1).  It removes every per-alignment launch and copy,
-     * but on this box its alignments run ~1.4x slower than under the launch-per-round path,
-     * so the pipelined launch path stays the default. */
-    { const char *rs = getenv("ABPOA_GPU_RESIDENT"); e->resident = (rs && *rs == '1') ? poa_resident_new(device, e->arena) : NULL; }
-    e->res_jobs = e->res_fallback = 0; e->res_kernel_ms = 0; e->res_cells = e->res_fwd_clk = e->res_bt_clk = 0; e->res_h2d = e->res_d2h = 0; e->res_launches = 0; e->capture_on = false; e->parked_vec = NULL;
     return e;
 }
 
@@ -172,10 +162,7 @@ extern "C" int abpoa_gpu_replay(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int wa
     return 0;
 }
 
-static void parked_delete(abpoa_gpu_batch *e);
 extern "C" void abpoa_gpu_batch_free(abpoa_gpu_batch_t *e) {
-    if (e && e->resident) { poa_resident_free(e->resident); e->resident = NULL; }
-    if (e) parked_delete(e);
     if (!e) return;
     abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_free(c);
@@ -191,15 +178,11 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
         out->launches += s->launches; out->retries += s->retries; out->h2d_bytes += s->h2d_bytes; out->d2h_bytes += s->d2h_bytes;
         out->fwd_clk += s->fwd_clk; out->bt_clk += s->bt_clk;
     }
-    /* alignments served by the resident kernel (no stream context involved) */
-    out->kernel_ms += e->res_kernel_ms; out->cells += e->res_cells; out->alignments += e->res_jobs; out->launches += e->res_launches;
-    out->retries += e->res_fallback; out->h2d_bytes += e->res_h2d; out->d2h_bytes += e->res_d2h; out->fwd_clk += e->res_fwd_clk; out->bt_clk += e->res_bt_clk;
     out->wall_ms = e->wall_ms; out->n_workers = e->n_workers; out->device = e->dev;
 }
 
 extern "C" void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *e) {
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_reset_stats(c);
-    e->res_jobs = e->res_fallback = 0; e->res_kernel_ms = 0; e->res_cells = e->res_fwd_clk = e->res_bt_clk = 0; e->res_h2d = e->res_d2h = 0; e->res_launches = 0;
     e->wall_ms = 0;
 }
 
@@ -559,8 +542,11 @@ void half_start_round(HalfChunk &h, const Worker &wk, int r, SinkCtx *sc) {
         h.jobs.push_back(j);
     }
     if (h.jobs.empty()) return;
-    if (poa_engine_submit(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size())) h.submitted = true;
-    else poa_engine_run(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size(), sink_to_res, sc);      /* mixed kinds / too big: blocking */
+    /* 1: launched asynchronously.  0: mixed kernel kinds / too big for one launch, -1: the arena is short right
+     * now -- both take the blocking path, which (through the context's pressure callback) first drains this
+     * worker's other sub-chunks so that the thread never waits for planes while holding some. */
+    if (poa_engine_submit(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size()) == 1) h.submitted = true;
+    else poa_engine_run(h.ctx, abpt, h.jobs.data(), (int)h.jobs.size(), sink_to_res, sc);
 }
 
 /* wait for the half's launch, then fuse read r into every group that has one */
@@ -601,6 +587,14 @@ void worker_pipelined(Worker wk) {
     }
     std::vector<HalfChunk> half((size_t)K);
     for (int k = 0; k < K; ++k) half[k].ctx = wk.ctxs[k];
+    /* pressure callback of every context of this worker: collect whatever the worker has in flight (results are
+     * parked in Pending records; half_finish_round fuses them later) so that their planes return to the arena */
+    struct Drain { std::vector<HalfChunk> *half; SinkCtx *sc; } drain = { &half, &sc };
+    auto drain_fn = [](void *user) {
+        Drain *d = (Drain *)user;
+        for (HalfChunk &o : *d->half) if (o.submitted) { o.submitted = false; poa_engine_collect(o.ctx, sink_to_res, d->sc); }
+    };
+    for (int k = 0; k < K; ++k) poa_dev_ctx_set_pressure_cb(half[k].ctx, drain_fn, &drain);
     PhaseClock pc; double t_start = 0, t_finish = 0;
     for (;;) {
         int got = 0, rounds = 0;
@@ -637,6 +631,7 @@ void worker_pipelined(Worker wk) {
         }
     }
 
+    for (int k = 0; k < K; ++k) poa_dev_ctx_set_pressure_cb(half[k].ctx, NULL, NULL);
     for (int k = 0; k < K; ++k) for (abpoa_t *ab : half[k].handles) abpoa_free(ab);
     if (prof) {
         double wait = 0, fill = 0, copy = 0, kern = 0;
@@ -648,253 +643,7 @@ void worker_pipelined(Worker wk) {
 }
 
 
-/* ------------------------------------------------------------------ resident worker
- * Owns slots [slot0, slot1) of the resident kernel.  Every slot carries one read group at a time
- * through its chain  flatten -> (device) align -> fuse -> flatten ...  fully asynchronously: the
- * thread sweeps its slots, consumes whichever results have arrived and immediately re-arms the slot
- * with the group's next read.  Groups are drawn one by one from the shared counter. */
-struct SlotRun {
-    int slot = -1;
-    abpoa_t *ab = NULL;
-    GroupState gs;
-    bool has_group = false, waiting = false, need_mem = false;
-    int generous = 0;               /* the staged job wants the full-rectangle slab (retry after PLANE_OVF) */
-    double t_done = 0;              /* when the slot ran out of work (diagnostics) */
-    int r = 0;                      /* read being aligned (waiting / need_mem) or next read to submit */
-    poa_job job; Pending pend;
-};
-/* a group the slots cannot finish (graph outgrew the staging buffers, scores left the int16 window):
- * completed through the launch path once the resident kernel has stopped */
-struct ParkedGroup { GroupState gs; abpoa_t *ab; int r; };
-std::vector<ParkedGroup> &parked_of(abpoa_gpu_batch *e) {
-    if (!e->parked_vec) e->parked_vec = new std::vector<ParkedGroup>();
-    return *(std::vector<ParkedGroup> *)e->parked_vec;
-}
-
-void group_begin(GroupState &s, const Worker &wk, int g, abpoa_t *ab) {
-    abpoa_para_t *abpt = wk.abpt;
-    s.in = &wk.groups[g]; s.out = &wk.results[g]; s.ab = ab; s.next_read = 0;
-    memset(s.out, 0, sizeof *s.out);
-    const int n = s.in->n_seq;
-    int max_len = 1024;
-    for (int i = 0; i < n; ++i) if (s.in->seq_lens[i] > max_len) max_len = s.in->seq_lens[i];
-    abpoa_reset(s.ab, abpt, max_len);
-    poa_graph_set_fast_order(s.ab->abg, wk.eng->fast_order);
-    abpoa_seq_t *abs = s.ab->abs;
-    abs->n_seq = n; poa_seq_reserve(abs);
-    for (int i = 0; i < n; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
-    s.weights = (int **)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int *));
-    for (int i = 0; i < n; ++i) {
-        const int l = s.in->seq_lens[i];
-        const int *qw = (abpt->use_qv && s.in->qual_weights && s.in->qual_weights[i]) ? s.in->qual_weights[i] : NULL;
-        if (qw) { s.weights[i] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1)); memcpy(s.weights[i], qw, sizeof(int) * (size_t)l); }
-    }
-    if (wk.flags & ABPOA_GPU_RECORD_READS) {
-        s.out->read_best_score = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
-        s.out->read_n_cigar = (int32_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
-        s.out->read_cigar_hash = (uint64_t *)poa_xcalloc((size_t)(n > 0 ? n : 1), sizeof(uint64_t));
-    }
-}
-void group_end(GroupState &s, abpoa_para_t *abpt) {
-    finish_group(s, abpt);
-    for (int i = 0; i < s.in->n_seq; ++i) free(s.weights[i]);
-    free(s.weights);
-}
-/* read r of the group is aligned (pend) or needs no alignment (empty graph): record + fuse */
-void fuse_read(GroupState &s, const Worker &wk, int r, Pending &pd) {
-    abpoa_para_t *abpt = wk.abpt;
-    if (wk.flags & ABPOA_GPU_RECORD_READS) {
-        s.out->read_best_score[r] = pd.have ? pd.res.best_score : 0;
-        s.out->read_n_cigar[r] = pd.res.n_cigar;
-        s.out->read_cigar_hash[r] = fnv1a(pd.res.graph_cigar, pd.res.n_cigar);
-    }
-    poa_add_alignment_nosync(s.ab, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, (uint8_t *)s.in->seqs[r], s.weights[r], s.in->seq_lens[r],
-                             NULL, pd.res, r, s.in->n_seq, 1);
-    if (pd.res.n_cigar) free(pd.res.graph_cigar);
-    memset(&pd.res, 0, sizeof pd.res); pd.have = false;
-}
-
-void worker_resident(Worker wk) {
-    const bool prof = getenv("ABPOA_GPU_PROFILE") != NULL;
-    pin_worker(wk.index);
-    if (cudaSetDevice(wk.eng->dev) != cudaSuccess) poa_die("libabpoa_b200", "worker cannot select device %d", wk.eng->dev);
-    abpoa_para_t *abpt = wk.abpt;
-    poa_resident *rs = wk.eng->resident;
-    SinkCtx sc = { abpt };
-    const int ns = wk.slot1 - wk.slot0;
-    std::vector<SlotRun> slots((size_t)ns);
-    for (int k = 0; k < ns; ++k) { slots[k].slot = wk.slot0 + k; slots[k].ab = abpoa_init(); }
-    int64_t n_res = 0, n_retry = 0, n_parked = 0; double t_kernel_ns = 0, t_fuse = 0, t_stage = 0, t_idle = 0; uint64_t h2d = 0, d2h = 0;
-    int64_t cells = 0, fwd_clk = 0, bt_clk = 0;
-    int sm_hist[256]; memset(sm_hist, 0, sizeof sm_hist);
-    int64_t n_memwait = 0;
-    const auto t_loop0 = std::chrono::steady_clock::now();
-    double t_dev_idle_ns = 0, t_dev_fetch_ns = 0;
-    PhaseClock pc;
-
-    auto park = [&](SlotRun &sl, const char *why) {
-        if (prof && n_parked < 3) fprintf(stderr, "[resident] slot %d read %d parked for the launch path (%s): rows %d qlen %d bytes %zu\n",
-                                          sl.slot, sl.r, why, sl.job.plan.n_rows, sl.job.plan.qlen, (size_t)sl.job.plan.bytes);
-        ParkedGroup pg = { sl.gs, sl.ab, sl.r };
-        { std::lock_guard<std::mutex> lk(wk.eng->cap_mu); parked_of(wk.eng).push_back(pg); }
-        sl.ab = abpoa_init(); sl.has_group = false; sl.waiting = sl.need_mem = false; ++n_parked;
-    };
-    /* Drive one slot forward until it has a job on the device (or waits for arena memory), or its
-     * group -- and the supply of groups -- is exhausted. */
-    auto advance = [&](SlotRun &sl) {
-        for (;;) {
-            if (!sl.has_group) {
-                const int g = wk.next_chunk->fetch_add(1);
-                if (g >= wk.n_groups) { if (sl.t_done == 0) sl.t_done = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop0).count(); return; }
-                group_begin(sl.gs, wk, g, sl.ab);
-                sl.has_group = true; sl.r = 0;
-            }
-            GroupState &s = sl.gs;
-            bool parked = false;
-            while (sl.r < s.in->n_seq) {
-                const int r = sl.r;
-                abpoa_graph_t *abg = s.ab->abg;
-                sl.pend.gs = &s; sl.pend.have = false; memset(&sl.pend.res, 0, sizeof(abpoa_res_t));
-                if (abg->node_n <= 2) { fuse_read(s, wk, r, sl.pend); ++sl.r; continue; }      /* empty graph: no DP (reference :195) */
-                if (!abg->is_topological_sorted) abpoa_topological_sort(abg, abpt);
-                poa_job &j = sl.job; memset(&j, 0, sizeof j);
-                j.abg = abg; j.beg_node_id = ABPOA_SRC_NODE_ID; j.end_node_id = ABPOA_SINK_NODE_ID;
-                j.query = s.in->seqs[r]; j.tag = &sl.pend;
-                poa_blob_plan_make(&j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, s.in->seq_lens[r]);
-                if (!poa_resident_fits(rs, abpt, &j.plan)) { park(sl, "does not fit a slot"); parked = true; break; }
-                pc.tic();
-                poa_blob_fill(poa_resident_stage(rs, sl.slot), &j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, j.query);
-                sl.generous = 0;
-                if (poa_resident_submit(rs, sl.slot, abpt, &j.plan, 0)) { sl.waiting = true; h2d += j.plan.bytes; }
-                else sl.need_mem = true;
-                t_stage += pc.toc();
-                return;
-            }
-            if (parked) continue;           /* the slot is free again: next group */
-            group_end(s, abpt);
-            sl.has_group = false;
-        }
-    };
-
-    for (SlotRun &sl : slots) advance(sl);
-    struct timespec nap = { 0, 50 * 1000 };
-    int idle_sweeps = 0;
-    for (;;) {
-        bool any_busy = false, progressed = false;
-        for (SlotRun &sl : slots) {
-            if (sl.need_mem) {                              /* staged, waiting for arena room */
-                any_busy = true; ++n_memwait;
-                if (poa_resident_submit(rs, sl.slot, abpt, &sl.job.plan, sl.generous)) { sl.need_mem = false; sl.waiting = true; h2d += sl.job.plan.bytes; progressed = true; }
-                continue;
-            }
-            if (!sl.waiting) continue;
-            any_busy = true;
-            const PoaResultDev *rr = poa_resident_poll(rs, sl.slot);
-            if (!rr) continue;
-            progressed = true; sl.waiting = false;
-            pc.tic();
-            const PoaResultDev res = *rr;
-            poa_job &j = sl.job;
-            j.status = res.status; j.bits = 15; j.ref_bits = poa_score_bits(abpt, j.plan.qlen, j.plan.n_rows);
-            if (res.status == POA_ST_PLANE_OVF && !sl.generous) {        /* band outgrew the estimated slab: same job, full rectangle */
-                poa_resident_release(rs, sl.slot);
-                sl.generous = 1; ++n_retry;
-                if (poa_resident_submit(rs, sl.slot, abpt, &j.plan, 1)) sl.waiting = true; else sl.need_mem = true;
-                t_fuse += pc.toc();
-                continue;
-            }
-            if (res.status == POA_ST_RANGE || res.status == POA_ST_PLANE_OVF || res.status == POA_ST_CIGAR_OVF) {
-                poa_resident_release(rs, sl.slot);
-                park(sl, res.status == POA_ST_RANGE ? "scores left the int16 window" : "workspace overflow");
-                t_fuse += pc.toc();
-                advance(sl);
-                continue;
-            }
-            if (res.status == POA_ST_OK) {
-                j.best_score = res.best_score; j.best_i = res.best_i; j.best_j = res.best_j; j.start_i = res.start_i; j.start_j = res.start_j;
-                j.n_aln_bases = res.n_aln_bases; j.n_matched_bases = res.n_matched_bases; j.cells = res.cells; j.max_band = res.max_band;
-                j.n_ops = res.n_ops; j.ops = poa_resident_cigar(rs, sl.slot);
-                if (wk.eng->capture_on) {
-                    poa_captured_job cj;
-                    cj.blob = poa_resident_stage(rs, sl.slot); cj.bytes = j.plan.bytes; cj.n_rows = j.plan.n_rows; cj.qlen = j.plan.qlen; cj.w = j.plan.w;
-                    cj.n_pred = ((const int32_t *)(cj.blob + ((const PoaJobHeader *)cj.blob)->off_rowmeta))[2 * j.plan.n_rows];
-                    cj.bits = 15; cj.best_score = res.best_score; cj.n_ops = res.n_ops; cj.cells = res.cells; cj.plane_units = res.plane_units_used;
-                    capture_cb(wk.eng, &cj);
-                }
-                if (prof && res.prof[5] >= 0 && res.prof[5] < 256) sm_hist[res.prof[5]] += 1;
-                t_dev_idle_ns += (double)res.prof[3]; t_dev_fetch_ns += (double)res.prof[4];
-                ++n_res; t_kernel_ns += (double)(res.t_end_ns - res.t_start_ns); cells += res.cells; fwd_clk += res.fwd_clk; bt_clk += res.bt_clk;
-                d2h += (uint64_t)res.n_ops * 8 + sizeof(PoaResultDev);
-            }
-            sink_to_res(&sc, &j);            /* OK: copies the CIGAR out; BT_ERROR: reports and aborts like the reference */
-            poa_resident_release(rs, sl.slot);
-            fuse_read(sl.gs, wk, sl.r, sl.pend);
-            ++sl.r;
-            t_fuse += pc.toc();
-            advance(sl);
-        }
-        if (!any_busy) break;
-        if (!progressed) {
-            pc.tic();
-            nanosleep(&nap, NULL);
-            if ((++idle_sweeps & 0xfff) == 0 && !poa_resident_alive(rs)) {
-                for (SlotRun &sl : slots) if (sl.waiting) fprintf(stderr, "[resident] worker %d slot %d still waiting: read %d rows %d qlen %d bytes %zu (done so far: %lld jobs)\n",
-                                                                  wk.index, sl.slot, sl.r, sl.job.plan.n_rows, sl.job.plan.qlen, (size_t)sl.job.plan.bytes, (long long)n_res);
-                poa_die("libabpoa_b200/resident", "the resident kernel ended while jobs were outstanding (time budget ABPOA_GPU_RESIDENT_BUDGET_S used up?)");
-            }
-            t_idle += pc.toc();
-        }
-    }
-    for (SlotRun &sl : slots) abpoa_free(sl.ab);
-    {
-        std::lock_guard<std::mutex> lk(wk.eng->cap_mu);
-        wk.eng->res_jobs += n_res; wk.eng->res_fallback += n_retry;
-        wk.eng->res_kernel_ms += t_kernel_ns * 1e-6; wk.eng->res_cells += cells; wk.eng->res_fwd_clk += fwd_clk; wk.eng->res_bt_clk += bt_clk;
-        wk.eng->res_h2d += h2d; wk.eng->res_d2h += d2h;
-    }
-    if (prof) {
-        fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f ms\n", poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3]);
-        { int used = 0; for (int z = 0; z < 256; ++z) used += sm_hist[z] > 0; fprintf(stderr, "[worker-resident] this worker's %d slots ran on %d distinct SMs\n", ns, used); }
-        { double lo = 1e30, hi = 0; for (SlotRun &sl : slots) { if (sl.t_done < lo) lo = sl.t_done; if (sl.t_done > hi) hi = sl.t_done; }
-          fprintf(stderr, "[worker-resident] slots ran out of work between %.0f and %.0f ms after the start; sweeps spent waiting for arena memory: %lld\n", lo, hi, (long long)n_memwait); }
-        fprintf(stderr, "[worker-resident] per job on the device: waiting for the host %.2f ms, blob fetch %.2f ms\n", n_res ? t_dev_idle_ns * 1e-6 / n_res : 0.0, n_res ? t_dev_fetch_ns * 1e-6 / n_res : 0.0);
-        fprintf(stderr, "[worker-resident %d slots] jobs %lld slab retries %lld parked groups %lld: stage %.0f result+fuse %.0f idle %.0f ms; device time/job %.1f ms\n",
-                ns, (long long)n_res, (long long)n_retry, (long long)n_parked, t_stage, t_fuse, t_idle, n_res ? t_kernel_ns * 1e-6 / n_res : 0.0);
-    }
-}
-
-/* groups the slots handed back: finish them read by read through the launch path */
-void finish_parked(abpoa_gpu_batch *e, abpoa_para_t *abpt, int flags, const abpoa_gpu_group_t *groups, abpoa_gpu_group_result_t *results, int n_groups) {
-    if (parked_of(e).empty()) return;
-    std::atomic<int> dummy(0);
-    Worker wk = { 0, e, e->ctx[0], &e->ctx[0], 1, abpt, flags, &dummy, 1, 0, 0, n_groups, groups, results };
-    SinkCtx sc = { abpt };
-    for (ParkedGroup &pg : parked_of(e)) {
-        GroupState &s = pg.gs;
-        for (int r = pg.r; r < s.in->n_seq; ++r) {
-            Pending pend; pend.gs = &s; pend.have = false; memset(&pend.res, 0, sizeof pend.res);
-            abpoa_graph_t *abg = s.ab->abg;
-            if (abg->node_n > 2) {
-                if (!abg->is_topological_sorted) abpoa_topological_sort(abg, abpt);
-                poa_job j; memset(&j, 0, sizeof j);
-                j.abg = abg; j.beg_node_id = ABPOA_SRC_NODE_ID; j.end_node_id = ABPOA_SINK_NODE_ID; j.query = s.in->seqs[r]; j.tag = &pend;
-                poa_blob_plan_make(&j.plan, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, s.in->seq_lens[r]);
-                poa_engine_run(e->ctx[0], abpt, &j, 1, sink_to_res, &sc);
-                e->res_fallback += 1;
-            }
-            fuse_read(s, wk, r, pend);
-        }
-        group_end(s, abpt);
-        abpoa_free(pg.ab);
-    }
-    parked_of(e).clear();
-}
-
 }  // namespace
-
-static void parked_delete(abpoa_gpu_batch *e) {
-    if (e->parked_vec) { delete (std::vector<ParkedGroup> *)e->parked_vec; e->parked_vec = NULL; }
-}
 
 extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
                                    abpoa_gpu_group_result_t *results, int flags) {
@@ -905,30 +654,6 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     if (flags & ABPOA_GPU_CAPTURE_JOBS) abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_set_capture(c, (flags & ABPOA_GPU_CAPTURE_JOBS) ? capture_cb : NULL, e);
     std::atomic<int> next_chunk(0);
-    /* ---- resident kernel: every group owns a slot, no launches / copies per alignment ---- */
-    if (e->resident && !abpt->amb_strand) {
-        int qmax = 1;
-        for (int g = 0; g < n_groups; ++g) for (int i = 0; i < groups[g].n_seq; ++i) if (groups[g].seq_lens[i] > qmax) qmax = groups[g].seq_lens[i];
-        /* the launch path serves the rare retries: size one context per worker now, while nothing is resident */
-        for (int w = 0; w < e->n_workers; ++w) poa_dev_ctx_reserve(e->ctx[(size_t)e->pipe_depth * w], 1, 3 * qmax + 1024, qmax);
-        const int n_slots = poa_resident_start(e->resident, abpt, n_groups, qmax);
-        if (n_slots > 0) {
-            e->capture_on = (flags & ABPOA_GPU_CAPTURE_JOBS) != 0;
-            const int nw = e->n_workers < n_slots ? e->n_workers : n_slots;
-            std::vector<std::thread> th;
-            for (int w = 0; w < nw; ++w) {
-                Worker wk = { w, e, e->ctx[(size_t)e->pipe_depth * w], &e->ctx[(size_t)e->pipe_depth * w], e->pipe_depth, abpt, flags, &next_chunk, 1,
-                              (int)((int64_t)n_slots * w / nw), (int)((int64_t)n_slots * (w + 1) / nw), n_groups, groups, results };
-                th.emplace_back(worker_resident, wk);
-            }
-            for (auto &t : th) t.join();
-            poa_resident_stop(e->resident);
-            e->res_launches += 1;
-            finish_parked(e, abpt, flags, groups, results, n_groups);
-            e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            return 0;
-        }
-    }
     /* groups per launch: as given, else spread the batch evenly over every sub-chunk slot (workers x pipe depth) */
     int G = e->groups_per_launch;
     if (G <= 0) { const int slots = e->n_workers * e->pipe_depth; G = (n_groups + slots - 1) / slots; if (G > 32) G = 32; if (G < 1) G = 1; }

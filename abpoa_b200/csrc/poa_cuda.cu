@@ -60,6 +60,7 @@ static uint8_t *arena_take(poa_arena *a, size_t bytes) {
     bytes = al256(bytes);
     if (bytes > a->cap) poa_die("libabpoa_b200/cuda", "one launch needs %zu bytes of DP planes, arena holds %zu", bytes, a->cap);
     std::unique_lock<std::mutex> lk(a->mu);
+    int waited_s = 0;
     for (;;) {
         for (size_t i = 0; i < a->free_list.size(); ++i)
             if (a->free_list[i].second >= bytes) {
@@ -68,7 +69,16 @@ static uint8_t *arena_take(poa_arena *a, size_t bytes) {
                 if (a->free_list[i].second == 0) a->free_list.erase(a->free_list.begin() + i);
                 return a->base + off;
             }
-        a->cv.wait(lk);
+        /* Backstop (the callers never wait here while holding planes, see poa_engine_submit): a wait
+         * that lasts minutes means the arena is held by launches that cannot finish. */
+        if (a->cv.wait_for(lk, std::chrono::seconds(60)) == std::cv_status::timeout) {
+            waited_s += 60;
+            size_t free_b = 0, largest = 0;
+            for (auto &f : a->free_list) { free_b += f.second; if (f.second > largest) largest = f.second; }
+            fprintf(stderr, "[libabpoa_b200/cuda] waiting %d s for %zu bytes of DP planes (arena %zu, free %zu, largest free range %zu)\n",
+                    waited_s, bytes, a->cap, free_b, largest);
+            if (waited_s >= 600) poa_die("libabpoa_b200/cuda", "no plane memory became available within 600 s (arena %zu bytes, request %zu)", a->cap, bytes);
+        }
     }
 }
 static void arena_give(poa_arena *a, uint8_t *p, size_t bytes) {
@@ -120,6 +130,7 @@ struct poa_dev_ctx {
     size_t planes_limit;              /* hard cap for the plane slab (bytes); 0 = ask the device */
     poa_engine_stats stats;
     poa_capture_fn capture; void *capture_user;
+    poa_pressure_fn pressure; void *pressure_user;   /* called before this context WAITS for plane memory */
     PoaJobDesc last_desc; int last_bits, last_gap, last_rows;   /* debug: job 0 of the most recent launch */
 };
 
@@ -136,7 +147,7 @@ poa_dev_ctx *poa_dev_ctx_new_on(int dev) {
     poa_dev_ctx *c = new poa_dev_ctx();
     c->arena = NULL; c->st = NULL; c->h_in = c->h_out = c->d_in = c->d_work = c->d_planes = c->h_res = NULL;
     c->h_in_cap = c->h_out_cap = c->d_in_cap = c->d_work_cap = c->d_planes_cap = c->h_res_cap = c->planes_limit = 0;
-    memset(&c->stats, 0, sizeof c->stats); c->capture = NULL; c->capture_user = NULL; memset(&c->last_desc, 0, sizeof c->last_desc);
+    memset(&c->stats, 0, sizeof c->stats); c->capture = NULL; c->capture_user = NULL; c->pressure = NULL; c->pressure_user = NULL; memset(&c->last_desc, 0, sizeof c->last_desc);
     c->last_bits = c->last_gap = c->last_rows = 0;
     if (dev >= 0) { c->dev = dev; CK(cudaSetDevice(c->dev)); }
     else CK(cudaGetDevice(&c->dev));
@@ -152,6 +163,7 @@ poa_dev_ctx *poa_dev_ctx_new(void) {
 }
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a) { c->arena = a; }
 void poa_dev_ctx_set_capture(poa_dev_ctx *c, poa_capture_fn fn, void *user) { c->capture = fn; c->capture_user = user; }
+void poa_dev_ctx_set_pressure_cb(poa_dev_ctx *c, poa_pressure_fn fn, void *user) { c->pressure = fn; c->pressure_user = user; }
 
 void poa_dev_ctx_free(poa_dev_ctx *c) {
     if (!c) return;
@@ -179,28 +191,8 @@ static void stream_wait(poa_dev_ctx *c) {
     CK(cudaEventSynchronize(c->ev_done));
 }
 
-/* cudaFree / cudaFreeHost wait for every kernel on the device -- including the resident kernel,
- * which only ends when its batch call does.  While one is running, buffers that are outgrown are
- * parked here and released when it has stopped. */
-static std::atomic<int> g_hold_frees(0);
-static std::mutex g_parked_mu;
-static std::vector<void *> g_parked_dev, g_parked_host;
-static void release_dev(void *p) {
-    if (g_hold_frees.load()) { std::lock_guard<std::mutex> lk(g_parked_mu); g_parked_dev.push_back(p); }
-    else CK(cudaFree(p));
-}
-static void release_host(void *p) {
-    if (g_hold_frees.load()) { std::lock_guard<std::mutex> lk(g_parked_mu); g_parked_host.push_back(p); }
-    else CK(cudaFreeHost(p));
-}
-void poa_hold_frees(int on) {
-    g_hold_frees.store(on);
-    if (on) return;
-    std::lock_guard<std::mutex> lk(g_parked_mu);
-    for (void *p : g_parked_dev) cudaFree(p);
-    for (void *p : g_parked_host) cudaFreeHost(p);
-    g_parked_dev.clear(); g_parked_host.clear();
-}
+static void release_dev(void *p) { CK(cudaFree(p)); }
+static void release_host(void *p) { CK(cudaFreeHost(p)); }
 
 static void grow_host(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return;
@@ -247,6 +239,18 @@ void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
     memcpy(p->mat, abpt->mat, (size_t)abpt->m * abpt->m * sizeof(int));
 }
 
+/* Environment switches, read on every call (a launch costs far more than a getenv) so that tests can
+ * flip them per case:
+ *   ABPOA_GPU_NO_P16=1      never use the packed int16x2 kernel
+ *   ABPOA_GPU_FORCE_P16=1   admit every int16/int32 job to it (the run-time range guard must then catch overflow)
+ *   ABPOA_GPU_SLAB_PCT=n    give each job only n % of the estimated plane slab (forces the PLANE_OVF redo) */
+static inline int env_flag(const char *name) { const char *e = getenv(name); return e && *e == '1'; }
+static inline int use_p16_for(const abpoa_para_t *abpt, int qlen, int n_rows) {
+    if (env_flag("ABPOA_GPU_NO_P16")) return 0;
+    if (env_flag("ABPOA_GPU_FORCE_P16")) return abpt->max_mat <= 1000 && abpt->min_mis <= 1000;
+    return poa_p16_ok(abpt, qlen, n_rows);
+}
+
 static inline int planes_of(int gap_mode) { return gap_mode == ABPOA_LINEAR_GAP ? 1 : (gap_mode == ABPOA_AFFINE_GAP ? 3 : 5); }
 
 /* plane slab (in 8-cell units) a job is given: `generous` = the full rectangle */
@@ -257,6 +261,8 @@ static uint64_t plane_units_for(const poa_job *j, int gap_mode, int generous) {
     if (!generous && j->plan.w >= 0) {
         const uint64_t est = (uint64_t)((2 * j->plan.w + 1 + 32 + 7) / 8 + 2);
         if (est < per_row) per_row = est;
+        const char *pct = getenv("ABPOA_GPU_SLAB_PCT");
+        if (pct && *pct) { per_row = per_row * (uint64_t)atoi(pct) / 100; if (per_row < 2) per_row = 2; }
     }
     return per_row * (uint64_t)P * (uint64_t)j->plan.n_rows;
 }
@@ -270,10 +276,12 @@ static inline double now_ms(void) {
 /* One launch = begin (stage + H2D + kernel, returns at once) and finish (sleep until the jobs
  * report, copy CIGARs back, publish results).  A context has at most one launch outstanding;
  * a worker that owns two contexts overlaps the fusion of one half-chunk with the kernel of the other. */
-static void run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx_in, int n, int bits, int generous) {
+/* try_only: take the planes without blocking; returns false (nothing staged, nothing held) when the arena
+ * has no room right now. */
+static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx_in, int n, int bits, int generous, bool try_only = false) {
     CK(cudaSetDevice(c->dev));
     LaunchState &L = c->ls;
-    L.abpt = abpt; L.jobs = jobs; L.idx.assign(idx_in, idx_in + n); L.n = n; L.bits = bits; L.active = true;
+    L.abpt = abpt; L.jobs = jobs; L.idx.assign(idx_in, idx_in + n); L.n = n; L.bits = bits;
     const int *idx = L.idx.data();
     const double t_begin = now_ms();
     const int S = bits == 32 ? 4 : 2;          /* bits: 15 = packed int16x2 kernel, 16 / 32 = generic kernel */
@@ -307,9 +315,11 @@ static void run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     grow_dev(&c->d_in, &c->d_in_cap, in_bytes, 1);
     grow_dev(&c->d_work, &c->d_work_cap, work_bytes, 1);
     uint8_t *planes_base;
-    if (c->arena) planes_base = arena_take(c->arena, plane_bytes);
-    else { grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1); planes_base = c->d_planes; }
-    L.planes_base = planes_base; L.in_bytes = in_bytes;
+    if (c->arena) {
+        planes_base = try_only ? poa_arena_try_borrow(c->arena, plane_bytes) : arena_take(c->arena, plane_bytes);
+        if (!planes_base) return false;
+    } else { grow_dev(&c->d_planes, &c->d_planes_cap, plane_bytes, generous ? 0 : 1); planes_base = c->d_planes; }
+    L.planes_base = planes_base; L.in_bytes = in_bytes; L.active = true;
 
     poa_fill_params((PoaParamsDev *)c->h_in, abpt, bits);
     PoaJobDesc *desc = (PoaJobDesc *)(c->h_in + off_desc);
@@ -348,6 +358,7 @@ static void run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
                              (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     L.t_begin = t_begin; L.t_filled = t_filled;
+    return true;
 }
 
 static void run_finish(poa_dev_ctx *c) {
@@ -430,8 +441,14 @@ static void run_finish(poa_dev_ctx *c) {
     }
 }
 
+/* Blocking launch.  A thread must not WAIT for plane memory while it holds planes of other launches
+ * (every worker doing so can exhaust the arena with nobody able to finish): when the arena is short the
+ * owner's pressure callback first drains whatever else the thread has in flight. */
 static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, const int *idx, int n, int bits, int generous) {
-    run_begin(c, abpt, jobs, idx, n, bits, generous);
+    if (!run_begin(c, abpt, jobs, idx, n, bits, generous, true)) {
+        if (c->pressure) c->pressure(c->pressure_user);
+        run_begin(c, abpt, jobs, idx, n, bits, generous, false);
+    }
     run_finish(c);
 }
 
@@ -441,20 +458,22 @@ static void run_same_width(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jo
  * redoes the rare overflow / range jobs synchronously and delivers every job to the sink. */
 int poa_engine_submit(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n) {
     if (n <= 0 || c->ls.active) return 0;
-    static const int use_p16 = [] { const char *e = getenv("ABPOA_GPU_NO_P16"); return !(e && *e == '1'); }();
     int kind = -1; size_t bytes = 0;
     const size_t limit = c->arena ? poa_arena_capacity(c->arena) / 4 : c->planes_limit;
     for (int t = 0; t < n; ++t) {
         const int rb = poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows);
         jobs[t].ref_bits = rb;
-        const int k = (use_p16 && poa_p16_ok(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows)) ? 15 : rb;
+        const int k = use_p16_for(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows) ? 15 : rb;
         if (kind < 0) kind = k; else if (k != kind) return 0;
         bytes += (size_t)plane_units_for(&jobs[t], abpt->gap_mode, 0) * POA_GROUP * (k == 32 ? 4 : 2);
     }
     if (limit && bytes > limit) return 0;
     std::vector<int> idx(n);
     for (int t = 0; t < n; ++t) idx[t] = t;
-    run_begin(c, abpt, jobs, idx.data(), n, kind, 0);
+    /* Never WAIT for planes here: the caller may hold the planes of its other sub-chunks, and if every
+     * worker did that the arena could be exhausted with nobody able to finish.  -1 tells the caller
+     * to drain what it has in flight first and then take the blocking path (poa_engine_run). */
+    if (!run_begin(c, abpt, jobs, idx.data(), n, kind, 0, true)) return -1;
     return 1;
 }
 
@@ -487,12 +506,11 @@ void poa_engine_collect(poa_dev_ctx *c, poa_job_sink sink, void *user) {
  * `sink` callback right after the launch that produced them. */
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user) {
     if (n <= 0) return;
-    static const int use_p16 = [] { const char *e = getenv("ABPOA_GPU_NO_P16"); return !(e && *e == '1'); }();
     std::vector<int> kinds[3];                      /* 0: packed int16x2, 1: generic int16, 2: generic int32 */
     for (int t = 0; t < n; ++t) {
         const int rb = poa_score_bits(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows);
         jobs[t].ref_bits = rb;
-        if (use_p16 && poa_p16_ok(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows)) kinds[0].push_back(t);
+        if (use_p16_for(abpt, jobs[t].plan.qlen, jobs[t].plan.n_rows)) kinds[0].push_back(t);
         else kinds[rb == 16 ? 1 : 2].push_back(t);
     }
     /* a launch may borrow at most this much of the plane memory (leave room for other streams) */
@@ -620,6 +638,12 @@ extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, 
             out[(size_t)p * cap + (j - ri.beg)] = S == 2 ? (int32_t)((int16_t *)buf.data())[k] : ((int32_t *)buf.data())[k];
         }
     return P;
+}
+
+/* debugging aid: redo launches (PLANE_OVF / RANGE) of the handle's single-alignment context so far */
+extern "C" int64_t poa_debug_retries(abpoa_t *ab) {
+    poa_dev_ctx *c = (poa_dev_ctx *)ab->abm->s_mem;
+    return c ? c->stats.retries : -1;
 }
 
 /* ------------------------------------------------------------------ replay of HBM-resident jobs

@@ -68,27 +68,6 @@ typedef struct PoaJobDesc {
     int16_t *qprof;                     /* packed kernel: query profile scratch [m][qstride] in HBM         */
 } PoaJobDesc;
 
-/* ---- resident kernel (poa_resident_kernel_p16): one slot per read group ----
- * Mailbox + control block live in MAPPED PINNED HOST memory (the device polls them, the host
- * writes them); PoaSlotDev is a device-memory table of per-slot pointers. */
-typedef struct PoaMailbox {              /* 128 B, written by the host; seq last (release) */
-    uint32_t seq;                       /* bumped by the host when a new job's blob is in the staging buffer */
-    uint32_t blob_bytes;
-    uint32_t cigar_cap;
-    uint32_t pad0;
-    uint64_t plane_cap_units;
-    /* the job's workspace in HBM (a slice of the plane arena, sized for THIS job by the host) */
-    uint8_t *blob; void *planes; PoaRowInfo *rowinfo; uint32_t *rowoff; uint64_t *cigar; int16_t *qprof;
-    uint64_t pad1[7];
-} PoaMailbox;
-typedef struct PoaResidentCtl { uint32_t quit; uint32_t pad[15]; } PoaResidentCtl;
-typedef struct PoaSlotDev {             /* device-memory table, fixed for the lifetime of the resident kernel */
-    const uint8_t *host_blob;           /* staging buffer of the slot (device view of pinned host memory)   */
-    PoaResultDev *result;               /* mapped pinned host memory                                         */
-    uint64_t *host_cigar;               /* mapped pinned host memory                                         */
-    const PoaMailbox *mail;             /* mapped pinned host memory                                         */
-} PoaSlotDev;
-
 /* alignment parameters, identical for all jobs of a launch */
 typedef struct PoaParamsDev {
     int32_t m;

@@ -53,36 +53,23 @@ size_t poa_arena_capacity(const poa_arena *a);
 poa_dev_ctx *poa_dev_ctx_new_on(int dev);
 void poa_dev_ctx_use_arena(poa_dev_ctx *c, poa_arena *a);
 void poa_dev_ctx_set_capture(poa_dev_ctx *c, poa_capture_fn fn, void *user);
+/* called (on the launching thread) before a context waits for plane memory: the owner drains its other launches */
+typedef void (*poa_pressure_fn)(void *user);
+void poa_dev_ctx_set_pressure_cb(poa_dev_ctx *c, poa_pressure_fn fn, void *user);
 /* replay support: run pre-uploaded blobs (device pointers) as one launch on the context's stream */
 typedef struct { const uint8_t *d_blob; int n_rows, qlen, w; uint64_t plane_units; } poa_replay_job;
 double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const poa_replay_job *jobs, int n, int bits,
                                  int32_t *out_score, int32_t *out_nops, int64_t *out_cells);
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint);
 
-/* ---- resident kernel (poa_resident.cu): one slot per read group, mailboxes in mapped pinned memory ---- */
-typedef struct poa_resident poa_resident;
 struct PoaResultDev; struct PoaParamsDev;
-poa_resident *poa_resident_new(int dev, poa_arena *arena);
-void poa_resident_free(poa_resident *r);
-int poa_resident_start(poa_resident *r, const abpoa_para_t *abpt, int want_slots, int qmax);   /* returns slots, 0 = not applicable */
-void poa_resident_stop(poa_resident *r);
-int poa_resident_slots(const poa_resident *r);
-int64_t poa_resident_launches(const poa_resident *r);
-int poa_resident_fits(const poa_resident *r, const abpoa_para_t *abpt, const poa_blob_plan *pl);
-uint8_t *poa_resident_stage(poa_resident *r, int slot);
-int poa_resident_submit(poa_resident *r, int slot, const abpoa_para_t *abpt, const poa_blob_plan *pl, int generous);   /* 0: no arena memory right now, retry */
-void poa_resident_release(poa_resident *r, int slot);            /* give the finished job's workspace back */
-const struct PoaResultDev *poa_resident_poll(const poa_resident *r, int slot);
-const uint64_t *poa_resident_cigar(const poa_resident *r, int slot);
-int poa_resident_alive(poa_resident *r);
 uint8_t *poa_arena_borrow(poa_arena *a, size_t bytes);
 uint8_t *poa_arena_try_borrow(poa_arena *a, size_t bytes);
 void poa_arena_return(poa_arena *a, uint8_t *p, size_t bytes);
 void poa_fill_params(struct PoaParamsDev *p, const abpoa_para_t *abpt, int bits);
-void poa_hold_frees(int on);       /* park cudaFree / cudaFreeHost while a resident kernel runs (they would wait for it) */
 
 void poa_engine_run(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n, poa_job_sink sink, void *user);
-int poa_engine_submit(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n);
+int poa_engine_submit(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, int n);   /* 1 launched, 0 not one launch, -1 arena short */
 void poa_engine_collect(poa_dev_ctx *c, poa_job_sink sink, void *user);
 void poa_job_to_res(const poa_job *j, const abpoa_para_t *abpt, abpoa_res_t *res);
 void poa_dev_ctx_set_planes_limit(poa_dev_ctx *c, size_t bytes);

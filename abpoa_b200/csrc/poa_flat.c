@@ -110,7 +110,10 @@ void poa_blob_fill(uint8_t *dst, const poa_blob_plan *pl, const abpoa_graph_t *a
                 const int pr = index_of_id[iid[e]] - beg_index;
                 if (pr < 0 || pr >= n_rows) continue;
                 if (live && !live[pr]) continue;
-                if (pscore) pscore[np] = poa_edge_path_score(abg, id, e);
+                /* -G on a sub-graph: the reference indexes abpoa_get_incre_path_score with the position in the
+                 * FILTERED predecessor list (pre_index k, src/abpoa_align_simd.c:134, :215), not with the in-edge
+                 * index; for whole-graph alignments the two coincide.  Followed literally for bit-exactness. */
+                if (pscore) pscore[np] = poa_edge_path_score(abg, id, np - rowmeta[2 * r]);
                 pred[np++] = pr;
             }
         }

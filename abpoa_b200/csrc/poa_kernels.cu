@@ -95,10 +95,8 @@ template <int GAP> struct Planes {
     static constexpr int H = 0, E1 = 1, E2 = 2, F1 = (GAP == AG ? 2 : 3), F2 = 4;
 };
 
-/* Blob loads.  NOT ld.global.nc (__ldg): the resident kernel rewrites a slot's blob buffer between
- * jobs, and the read-only path is not kept coherent with stores of the same kernel -- a line left
- * over from the previous job's backtrace (its last steps read the first rows' metadata) would be
- * served to the next job.  Plain loads go through L1 coherently for same-SM writers. */
+/* Blob loads: plain coherent loads (blobs may be produced on the device by an earlier kernel of the
+ * same stream; nothing here relies on the read-only path). */
 template <typename T> __device__ __forceinline__ T ldb(const T *p) { return *p; }
 
 /* ------------------------------------------------------------------ job view */
@@ -1232,7 +1230,12 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     }
     res.best_score = best_score; res.best_i = best_i; res.best_j = best_j;
     res.cells = cells; res.max_band = max_band; res.plane_units_used = cursor;
-    if (guard_lo || guard_hi || best_score <= NEGP + 2000) res.status = POA_ST_RANGE;    /* scores left the safe int16 window: redo in 32 bits */
+    /* Scores left the safe int16 window: redo in 32 bits.  Besides the row maxima, the widest band is
+     * watched: beg/end follow min(ml, r) - w / max(mr, r) + w, so when the arg-max drifts away from the
+     * remain-centre a row can be far wider than 2w and a cell far from the row's maximum could reach the
+     * NEGP clamp without the maxima ever leaving [-14000, 29000]. */
+    if (guard_lo || guard_hi || best_score <= NEGP + 2000) res.status = POA_ST_RANGE;
+    if (banded && MODE != LOCAL && (int64_t)max_band * max(e1, e2) + max(oe1, oe2) > 15000) res.status = POA_ST_RANGE;
     const long long clk1 = clock64();
     res.fwd_clk = clk1 - clk0;
 #ifndef POA_KPROF
@@ -1266,102 +1269,6 @@ __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict
     p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
     __syncwarp();
     if (lane == 0) signal_done(jd);
-}
-
-/* ------------------------------------------------------------------ resident kernel
- * One launch for a whole batch call: CTA s serves slot s for as long as the call lasts.  A slot is
- * one read group's private workspace in HBM plus a mailbox in mapped pinned host memory.  The host
- * thread that owns the group writes the flattened graph + read into the slot's staging buffer
- * (pinned host memory) and bumps mail->seq; the warp sees it, pulls the blob over PCIe/C2C into
- * HBM itself, aligns, pushes the graph-CIGAR back into pinned host memory and stamps the result.
- * No stream, launch, memcpy or event per alignment: the ~1000 sequential chains of a batch advance
- * independently, each limited only by its own (kernel + fusion) latency. */
-__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t *p) {
-    uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-template <int GAP, int MODE>
-__global__ void __launch_bounds__(32) poa_resident_kernel_p16(const PoaSlotDev *__restrict__ slots, const PoaParamsDev *__restrict__ prm,
-                                                              int n_slots, int ring_rows, int ring_cells,
-                                                              const volatile PoaResidentCtl *ctl, uint64_t budget_ns) {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    const int lane = threadIdx.x;
-    if ((int)blockIdx.x >= n_slots) return;
-    const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
-    const PoaSlotDev sl = slots[blockIdx.x];
-    uint64_t t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    const uint64_t deadline = t0 + budget_ns;             /* backstop: a resident CTA never outlives its budget */
-    uint32_t last = 0;
-    uint64_t t_free = t0;                                  /* when this slot last became idle */
-    for (;;) {
-        /* ---- wait for the next job of this slot ---- */
-        uint32_t seq = 0, polls = 0; bool quit = false;
-        for (;;) {
-            if (lane == 0) {
-                seq = ld_sys_u32(&sl.mail->seq);
-                if (seq == last) {
-                    uint64_t now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (ld_sys_u32(&ctl->quit) != 0 || now > deadline) quit = true;
-                }
-            }
-            seq = __shfl_sync(FULL, seq, 0); quit = __shfl_sync(FULL, (int)quit, 0) != 0;
-            if (seq != last || quit) break;
-            __nanosleep(polls < 64 ? 2000 : 20000); ++polls;
-        }
-        if (seq == last) return;                         /* quit (or deadline) with no job pending */
-        uint64_t t_seen; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_seen));
-        __threadfence_system();
-        /* ---- the job's description: lanes 0..7 each fetch 16 bytes of the 128-byte mailbox ---- */
-        PoaJobDesc jd; uint32_t bytes;
-        {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (lane < 8) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                                       : "l"(reinterpret_cast<const uint4 *>(sl.mail) + lane) : "memory");
-            auto word = [&](int w) { return __shfl_sync(FULL, w & 3 ? (w & 2 ? ((w & 1) ? v.w : v.z) : v.y) : v.x, w >> 2); };
-            auto ptr64 = [&](int w) { return (uint64_t)word(w) | ((uint64_t)word(w + 1) << 32); };
-            bytes = word(1);
-            jd.cigar_cap = (int32_t)word(2); jd.pad = 0;
-            jd.plane_cap_units = ptr64(4);
-            jd.blob = reinterpret_cast<const uint8_t *>(ptr64(6)); jd.planes = reinterpret_cast<void *>(ptr64(8));
-            jd.rowinfo = reinterpret_cast<PoaRowInfo *>(ptr64(10)); jd.rowoff = reinterpret_cast<uint32_t *>(ptr64(12));
-            jd.cigar = reinterpret_cast<uint64_t *>(ptr64(14)); jd.qprof = reinterpret_cast<int16_t *>(ptr64(16));
-            jd.result = sl.result; jd.done = nullptr;
-        }
-        /* ---- pull the blob into HBM (uncached system-memory reads: the staging buffer is rewritten per job) ---- */
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(sl.host_blob); uint4 *dst = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(jd.blob));
-            const uint32_t n16 = (bytes + 15) >> 4;
-            for (uint32_t t = lane; t < n16; t += 32 * 8) {       /* 8 x 512 B in flight per warp */
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t k = t + 32 * u;
-                    if (k < n16) asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + k) : "memory");
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const uint32_t k = t + 32 * u; if (k < n16) dst[k] = v[u]; }
-            }
-            __threadfence_block(); __syncwarp();
-        }
-        uint64_t t_fetched; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_fetched));
-        p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
-        __syncwarp();
-        /* ---- graph-CIGAR back to the host, then publish ---- */
-        {
-            int st = 0, n_ops = 0;
-            if (lane == 0) { st = sl.result->status; n_ops = sl.result->n_ops; }
-            st = __shfl_sync(FULL, st, 0); n_ops = __shfl_sync(FULL, n_ops, 0);
-            if (st == POA_ST_OK) for (int t = lane; t < n_ops; t += 32) sl.host_cigar[t] = jd.cigar[t];
-        }
-        if (lane == 0) {                                 /* diagnostics: how long the slot sat idle, how long the blob took */
-            sl.result->prof[3] = (int64_t)(t_seen - t_free); sl.result->prof[4] = (int64_t)(t_fetched - t_seen);
-        }
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) signal_done(jd);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_free));
-        last = seq;
-        __syncwarp();
-    }
 }
 
 /* ------------------------------------------------------------------ launcher */
@@ -1450,36 +1357,3 @@ extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, 
     return launch_mode<CG, int32_t>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
 }
 
-/* ------------------------------------------------------------------ resident kernel launcher */
-/* query_only carries, when launching, the dynamic shared memory to ASK for if that is more than the ring
- * needs: it caps how many CTAs fit an SM, so the hardware spreads the slots over all SMs evenly. */
-template <int GAP, int MODE>
-static cudaError_t resident_one(int query_only, int *max_ctas_per_sm, const PoaSlotDev *slots, const PoaParamsDev *prm, int n_slots,
-                                int ring_rows, int ring_cells, const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
-    size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
-    if (!query_only && max_ctas_per_sm && (size_t)*max_ctas_per_sm > smem) smem = (size_t)*max_ctas_per_sm;
-    cudaError_t e = cudaFuncSetAttribute(poa_resident_kernel_p16<GAP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) return e;
-    if (query_only) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, poa_resident_kernel_p16<GAP, MODE>, 32, smem);
-    poa_resident_kernel_p16<GAP, MODE><<<n_slots, 32, smem, st>>>(slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns);
-    return cudaGetLastError();
-}
-template <int GAP>
-static cudaError_t resident_mode(int mode, int q, int *o, const PoaSlotDev *slots, const PoaParamsDev *prm, int n, int rr, int rc,
-                                 const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
-    switch (mode) {
-    case GLOBAL: return resident_one<GAP, GLOBAL>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
-    case LOCAL:  return resident_one<GAP, LOCAL>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
-    default:     return resident_one<GAP, EXTEND>(q, o, slots, prm, n, rr, rc, ctl, budget_ns, st);
-    }
-}
-/* query_only: report how many resident CTAs fit one SM (nothing is launched) */
-extern "C" cudaError_t poa_launch_resident_p16(int gap_mode, int align_mode, int query_only, int *max_ctas_per_sm, const PoaSlotDev *slots,
-                                               const PoaParamsDev *prm, int n_slots, int ring_rows, int ring_cells,
-                                               const PoaResidentCtl *ctl, uint64_t budget_ns, cudaStream_t st) {
-    switch (gap_mode) {
-    case LG: return resident_mode<LG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
-    case AG: return resident_mode<AG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
-    default: return resident_mode<CG>(align_mode, query_only, max_ctas_per_sm, slots, prm, n_slots, ring_rows, ring_cells, ctl, budget_ns, st);
-    }
-}

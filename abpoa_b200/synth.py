@@ -77,6 +77,10 @@ WORKLOADS = {
     # configs[2]: 1000 groups x 50 reads x 10 kbp, global, convex (-O 4,24 -E 2,1): the headline
     "convex_10k": Workload("convex_10k", 1000, 50, 10000, 0.05,
                            PoaConfig(align_mode=ABPOA_GLOBAL_MODE, gap_open1=4, gap_ext1=2, gap_open2=24, gap_ext2=1)),
+    # not a BASELINE config: the headline shape with AFFINE gaps -- the shape north_star's "60 % HBM roofline on the
+    # affine inner kernel" is measured on (widest practical rows, many groups)
+    "affine_10k": Workload("affine_10k", 1000, 50, 10000, 0.05,
+                           PoaConfig(align_mode=ABPOA_GLOBAL_MODE, gap_open1=4, gap_ext1=2, gap_open2=0, gap_ext2=0)),
     # configs[3]: 500 groups x 100 reads x 5 kbp, local, linear (-m1 -O 0 -E 2)
     "local_linear_5k": Workload("local_linear_5k", 500, 100, 5000, 0.05,
                                 PoaConfig(align_mode=ABPOA_LOCAL_MODE, gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0)),

@@ -79,8 +79,30 @@ def rank_cpu_share(rank: int, world: int) -> list[int]:
     return sorted(c for k in cores[lo:hi] for c in by_core[k])
 
 
+ALL_CPUS = sorted(os.sched_getaffinity(0))        # before any rank pinning: the reference arm may use every core of the box
+
+
+def socket_cpus() -> dict[int, list[int]]:
+    """One hardware thread per physical core, grouped by socket."""
+    out: dict[int, dict[int, int]] = {}
+    for c in ALL_CPUS:
+        try:
+            pkg = int(Path(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id").read_text())
+            core = int(Path(f"/sys/devices/system/cpu/cpu{c}/topology/core_id").read_text())
+        except Exception:
+            pkg, core = 0, c
+        out.setdefault(pkg, {}).setdefault(core, c)
+    return {p: sorted(v.values()) for p, v in out.items()}
+
+
 def _ref_worker(args):
-    wname, seeds, n_reads, length = args
+    wname, seeds, n_reads, length, cpu = args
+    import resource
+    if cpu is not None:
+        try:
+            os.sched_setaffinity(0, {cpu})
+        except OSError:
+            pass
     from abpoa_b200 import capi, synth
     from abpoa_b200.aligner import PoaSession
     w = synth.WORKLOADS[wname]
@@ -88,28 +110,57 @@ def _ref_worker(args):
     cells = 0
     reads_done = 0
     groups = [synth.make_group(seed, n_reads, length, w.err, w.cfg.m) for seed in seeds]     # outside the timed window
+    cons = []
     with PoaSession(w.cfg, lib) as s:
+        ru0 = resource.getrusage(resource.RUSAGE_SELF)
         t0 = time.perf_counter()
         for reads in groups:
             for a in s.run_reads(reads):
                 cells += a.cells
             reads_done += len(reads)
+            s.generate()
+            cons.append(bytes(s.consensus()[0]) if s.consensus() else b"")
         dt = time.perf_counter() - t0
-    return cells, reads_done, dt
+        ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    return cells, reads_done, dt, ru1.ru_utime - ru0.ru_utime, ru1.ru_stime - ru0.ru_stime, list(zip(seeds, cons))
 
 
-def reference_pass(wname: str, n_groups: int, cores: int, n_reads: int, length: int, base_seed: int):
-    """Time the reference on `n_groups` groups spread over `cores` processes. Returns (cells, reads, wall_s)."""
+def reference_pass(wname: str, n_groups: int, cpus: list[int], n_reads: int, length: int, base_seed: int):
+    """Time the reference on `n_groups` groups spread over one process per CPU of `cpus` (each pinned).
+    Returns a dict: cells, reads, wall_s, user_s, sys_s, cons {seed: consensus bytes}."""
+    cores = len(cpus)
     seeds = [base_seed + g for g in range(n_groups)]
-    shards = [seeds[i::cores] for i in range(cores)]
-    shards = [s for s in shards if s]
+    shards = [(seeds[i::cores], cpus[i]) for i in range(cores)]
+    shards = [s for s in shards if s[0]]
     ctx = mp.get_context("fork")
     with ctx.Pool(len(shards)) as pool:
-        res = pool.map(_ref_worker, [(wname, s, n_reads, length) for s in shards])
+        res = pool.map(_ref_worker, [(wname, s, n_reads, length, c) for s, c in shards])
     # all workers start together; the job ends when the slowest one does (process start-up,
     # read generation and imports are outside each worker's clock)
-    wall = max(r[2] for r in res)
-    return sum(r[0] for r in res), sum(r[1] for r in res), wall
+    cons = {}
+    for r in res:
+        cons.update(dict(r[5]))
+    return {"cells": sum(r[0] for r in res), "reads": sum(r[1] for r in res), "wall_s": max(r[2] for r in res),
+            "user_s": sum(r[3] for r in res), "sys_s": sum(r[4] for r in res), "procs": len(shards), "cons": cons}
+
+
+def cpu_baseline_block(wname: str, w, ref_groups: int, base_seed: int) -> tuple[dict, dict]:
+    """The unmodified reference on every physical core of the box (both sockets) and on the cores of ONE
+    socket (what north_star calls the single-socket baseline); user+sys next to wall (the
+    reference's quadratic, sparsely touched slab makes it page-fault bound at 10 kbp)."""
+    socks = socket_cpus()
+    all_cores = sorted(c for v in socks.values() for c in v)
+    one = socks[sorted(socks)[0]]
+    a = reference_pass(wname, ref_groups or len(all_cores), all_cores, w.n_reads, w.length, base_seed)
+    blk = {"value": a["cells"] / a["wall_s"] / 1e9, "unit": "GCUPS", "cores": a["procs"], "kind": "reference", "reads_per_s": a["reads"] / a["wall_s"],
+           "wall_s": a["wall_s"], "user_s": a["user_s"], "sys_s": a["sys_s"],
+           "sample": f"{len(a['cons'])} groups of the same workload ({a['reads']} reads, {a['cells'] / 1e9:.1f} G cells), one pinned process per physical core "
+                     f"({a['procs']} cores, {len(socks)} sockets), {a['wall_s']:.1f} s wall; CPU time {a['user_s']:.0f} s user + {a['sys_s']:.0f} s sys"}
+    if len(socks) > 1:
+        b = reference_pass(wname, len(one), one, w.n_reads, w.length, base_seed)
+        blk["single_socket"] = {"value": b["cells"] / b["wall_s"] / 1e9, "cores": b["procs"], "reads_per_s": b["reads"] / b["wall_s"],
+                                "wall_s": b["wall_s"], "user_s": b["user_s"], "sys_s": b["sys_s"]}
+    return blk, a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,25 +227,35 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        socks = socket_cpus()
+        all_cores = sorted(c for v in socks.values() for c in v)
+        cores = len(all_cores)
         ref_groups = args.ref_groups or cores
         # bounded sample: one group per core per step keeps the whole run within minutes
         per_step = []
         for s in range(args.warmup + args.steps):
             if s < args.warmup and s > 0:
                 continue                      # the CPU needs no repeated warm-up; one untimed pass suffices
-            cells, reads, wall = reference_pass(args.workload, ref_groups, cores, w.n_reads, w.length, 1000 + 7919 * s)
+            r = reference_pass(args.workload, ref_groups, all_cores, w.n_reads, w.length, 1000 + 7919 * s)
             if s >= args.warmup:
-                per_step.append((cells, reads, wall))
-        cells = sum(p[0] for p in per_step)
-        reads = sum(p[1] for p in per_step)
-        wall = sum(p[2] for p in per_step)
+                per_step.append(r)
+        cells = sum(p["cells"] for p in per_step)
+        reads = sum(p["reads"] for p in per_step)
+        wall = sum(p["wall_s"] for p in per_step)
+        user_s, sys_s = sum(p["user_s"] for p in per_step), sum(p["sys_s"] for p in per_step)
         val = cells / wall / 1e9
-        sample = f"{ref_groups} groups ({ref_groups * w.n_reads} reads) per step on {cores} processes (one per physical core); cells counted from ab->abm->dp_beg/dp_end"
+        sample = (f"{ref_groups} groups ({ref_groups * w.n_reads} reads) per step, one pinned process per physical core ({cores} cores, {len(socks)} sockets); "
+                  f"cells counted from ab->abm->dp_beg/dp_end; CPU time {user_s:.0f} s user + {sys_s:.0f} s sys over {wall:.1f} s wall")
+        single = None
+        if len(socks) > 1:            # north_star's "single-socket" figure: the same sample shape on the cores of socket 0 only
+            one = socks[sorted(socks)[0]]
+            b = reference_pass(args.workload, len(one), one, w.n_reads, w.length, 1000)
+            single = {"value": b["cells"] / b["wall_s"] / 1e9, "cores": b["procs"], "reads_per_s": b["reads"] / b["wall_s"], "wall_s": b["wall_s"], "user_s": b["user_s"], "sys_s": b["sys_s"]}
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall / max(len(per_step), 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/int32 (AVX2)", "data": "synthetic", "config": cfgdesc, "reads_per_s": reads / wall,
-            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference", "sample": sample, "user_s": user_s, "sys_s": sys_s, "wall_s": wall, "single_socket": single},
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -306,11 +367,8 @@ def main():
                 "int16_cell_fraction": rp["cells16"] / max(rp["cells"], 1)}
 
     cpu = None
-    if not args.no_cpu_baseline:
-        ref_groups = args.ref_groups or cores
-        rc, rr, rw = reference_pass(args.workload, ref_groups, cores, w.n_reads, w.length, 1000)
-        cpu = {"value": rc / rw / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference", "reads_per_s": rr / rw,
-               "sample": f"{ref_groups} groups of the same workload ({rr} reads, {rc / 1e9:.1f} G cells) on {cores} processes, one per physical core, {rw:.1f} s wall"}
+    if not args.no_cpu_baseline and world == 1:        # N=1 only (the contract); workers are pinned over ALL cores of the box
+        cpu, _ = cpu_baseline_block(args.workload, w, args.ref_groups, 1000)
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -113,3 +113,27 @@ def assert_digest_equal(got, want, tag=""):
         assert x == y, f"{tag} read {i}: {x} != {y}"
     for k in ("cons", "cov_sha1", "msa_len", "msa_sha1"):
         assert got[k] == want[k], f"{tag}: {k} differs"
+
+
+def _ref_records_worker(args):
+    """(spawned process) one group through the unmodified reference: per-read score / CIGAR length /
+    FNV-1a hash of the CIGAR words / DP cells, consensus, coverage."""
+    cfg_kw, reads, want_msa = args
+    from abpoa_b200 import capi
+    from abpoa_b200.batch import fnv1a_words
+    r = run_group(capi.load_library(capi.REFERENCE_LIB), PoaConfig(**cfg_kw), reads, want_msa=want_msa)
+    return {
+        "score": [a.best_score if a.aligned else 0 for a in r["alns"]],
+        "n_cigar": [len(a.cigar) for a in r["alns"]],
+        "hash": [fnv1a_words(a.cigar) if a.aligned else None for a in r["alns"]],
+        "cells": sum(a.cells for a in r["alns"]),
+        "cons": r["cons"], "cov": r["cov"], "msa": r["msa"],
+    }
+
+
+def reference_records(cfg: PoaConfig, groups, want_msa=False, procs=4):
+    """Run the groups through oracle/_ref in parallel worker processes (the reference is single-threaded and,
+    at 10 kbp, page-fault bound: ~15 s per 50-read group)."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(min(procs, len(groups))) as pool:
+        return pool.map(_ref_records_worker, [(dict(cfg.__dict__), g, want_msa) for g in groups])
