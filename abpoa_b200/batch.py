@@ -18,6 +18,7 @@ from .capi import c_int_p, c_u8_p, c_u64_p
 
 ABPOA_GPU_RECORD_READS = 0x1
 ABPOA_GPU_CAPTURE_JOBS = 0x2
+ABPOA_GPU_NO_CHAIN = 0x4
 
 
 class abpoa_gpu_group_t(C.Structure):
@@ -37,7 +38,8 @@ class abpoa_gpu_stats_t(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("wall_ms", C.c_double),
                 ("cells", C.c_int64), ("alignments", C.c_int64), ("launches", C.c_int64), ("retries", C.c_int64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int),
-                ("fwd_clk", C.c_int64), ("bt_clk", C.c_int64)]
+                ("fwd_clk", C.c_int64), ("bt_clk", C.c_int64),
+                ("chain_device_ms", C.c_double), ("chain_cells", C.c_int64), ("chain_groups", C.c_int), ("chain_fallback_groups", C.c_int)]
 
 
 class abpoa_gpu_replay_t(C.Structure):
@@ -131,9 +133,9 @@ class BatchEngine:
     def __exit__(self, *exc):
         self.close()
 
-    def run_packed(self, abpt, packed: PackedGroups, record_reads: bool = False, keep_results: bool = True, capture: bool = False):
+    def run_packed(self, abpt, packed: PackedGroups, record_reads: bool = False, keep_results: bool = True, capture: bool = False, no_chain: bool = False):
         res = (abpoa_gpu_group_result_t * packed.n)()
-        flags = (ABPOA_GPU_RECORD_READS if record_reads else 0) | (ABPOA_GPU_CAPTURE_JOBS if capture else 0)
+        flags = (ABPOA_GPU_RECORD_READS if record_reads else 0) | (ABPOA_GPU_CAPTURE_JOBS if capture else 0) | (ABPOA_GPU_NO_CHAIN if no_chain else 0)
         self.d.abpoa_gpu_msa_batch(self.h, abpt, packed.n, packed.arr, res, flags)
         out = []
         for g in range(packed.n):
@@ -154,10 +156,10 @@ class BatchEngine:
             self.d.abpoa_gpu_group_result_free(C.byref(r))
         return out
 
-    def run(self, cfg: PoaConfig, groups, record_reads: bool = False, weights=None):
+    def run(self, cfg: PoaConfig, groups, record_reads: bool = False, weights=None, no_chain: bool = False):
         abpt = make_para(self.lib, cfg)
         try:
-            return self.run_packed(abpt, PackedGroups(groups, weights), record_reads)
+            return self.run_packed(abpt, PackedGroups(groups, weights), record_reads, no_chain=no_chain)
         finally:
             self.lib.abpoa_free_para(abpt)
 

@@ -32,6 +32,7 @@
 #include "poa_internal.h"
 #include "poa_engine.h"
 #include "poa_device.cuh"
+#include "poa_chain_host.h"
 
 struct CapturedJob { uint8_t *blob; size_t bytes; int n_rows, qlen, w, n_pred, bits, best_score, n_ops; int64_t cells; uint64_t plane_units; };
 
@@ -43,6 +44,7 @@ struct abpoa_gpu_batch {
     poa_arena *arena;
     std::vector<poa_dev_ctx *> ctx;
     double wall_ms;
+    PoaChainStats chain;            /* device-resident chain engine (poa_chain.cu) */
 };
 
 extern "C" int abpoa_gpu_device_count(void) {
@@ -90,7 +92,7 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
         poa_dev_ctx_use_arena(c, e->arena);
         e->ctx.push_back(c);
     }
-    e->wall_ms = 0;
+    e->wall_ms = 0; memset(&e->chain, 0, sizeof e->chain);
     return e;
 }
 
@@ -179,10 +181,15 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
         out->fwd_clk += s->fwd_clk; out->bt_clk += s->bt_clk;
     }
     out->wall_ms = e->wall_ms; out->n_workers = e->n_workers; out->device = e->dev;
+    /* groups that ran on the device chain */
+    out->cells += e->chain.cells; out->alignments += e->chain.alignments; out->launches += e->chain.launches;
+    out->h2d_bytes += e->chain.h2d_bytes; out->d2h_bytes += e->chain.d2h_bytes; out->kernel_ms += e->chain.device_ms;
+    out->chain_device_ms = e->chain.device_ms; out->chain_cells = e->chain.cells; out->chain_groups = e->chain.groups_done; out->chain_fallback_groups = e->chain.groups_failed;
 }
 
 extern "C" void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *e) {
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_reset_stats(c);
+    memset(&e->chain, 0, sizeof e->chain);
     e->wall_ms = 0;
 }
 
@@ -197,6 +204,38 @@ extern "C" void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r) {
 }
 
 extern "C" { extern __thread double poa_prof_ms[8]; }
+
+/* Consensus / MSA of a finished group (reference abpoa_output, src/abpoa_align.c:354-370, with out_fp = NULL)
+ * copied into the caller's result record.  Consensus, MSA and the public index arrays use the reference's
+ * Kahn order, whatever order the alignments ran in. */
+void poa_finish_group_result(abpoa_t *ab, abpoa_para_t *abpt, abpoa_gpu_group_result_t *o) {
+    poa_graph_set_fast_order(ab->abg, 0);
+    if (ab->abg->node_n > 2) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
+    abpoa_output(ab, abpt, NULL);
+    const abpoa_cons_t *abc = ab->abc;
+    if (abpt->out_cons && abc->n_cons > 0) {
+        o->n_cons = abc->n_cons;
+        o->cons_len = (int *)poa_xmalloc(sizeof(int) * abc->n_cons);
+        o->cons_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * abc->n_cons);
+        o->cons_cov = (int **)poa_xmalloc(sizeof(int *) * abc->n_cons);
+        for (int c = 0; c < abc->n_cons; ++c) {
+            const int l = abc->cons_len[c];
+            o->cons_len[c] = l;
+            o->cons_base[c] = (uint8_t *)poa_xmalloc((size_t)(l > 0 ? l : 1));
+            o->cons_cov[c] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1));
+            memcpy(o->cons_base[c], abc->cons_base[c], (size_t)l);
+            memcpy(o->cons_cov[c], abc->cons_cov[c], sizeof(int) * (size_t)l);
+        }
+    }
+    if (abpt->out_msa && abc->msa_len > 0) {
+        o->msa_len = abc->msa_len; o->n_msa_rows = abc->n_seq + abc->n_cons;
+        o->msa_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * (size_t)o->n_msa_rows);
+        for (int r = 0; r < o->n_msa_rows; ++r) {
+            o->msa_base[r] = (uint8_t *)poa_xmalloc((size_t)abc->msa_len);
+            memcpy(o->msa_base[r], abc->msa_base[r], (size_t)abc->msa_len);
+        }
+    }
+}
 
 namespace {
 
@@ -286,37 +325,7 @@ void sink_to_res(void *user, poa_job *j) {
     pd->have = true;
 }
 
-void finish_group(GroupState &gs, abpoa_para_t *abpt) {
-    abpoa_t *ab = gs.ab;
-    /* consensus / MSA and the public index arrays use the reference's Kahn order */
-    poa_graph_set_fast_order(ab->abg, 0);
-    if (ab->abg->node_n > 2) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
-    abpoa_gpu_group_result_t *o = gs.out;
-    abpoa_output(ab, abpt, NULL);
-    const abpoa_cons_t *abc = ab->abc;
-    if (abpt->out_cons && abc->n_cons > 0) {
-        o->n_cons = abc->n_cons;
-        o->cons_len = (int *)poa_xmalloc(sizeof(int) * abc->n_cons);
-        o->cons_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * abc->n_cons);
-        o->cons_cov = (int **)poa_xmalloc(sizeof(int *) * abc->n_cons);
-        for (int c = 0; c < abc->n_cons; ++c) {
-            const int l = abc->cons_len[c];
-            o->cons_len[c] = l;
-            o->cons_base[c] = (uint8_t *)poa_xmalloc((size_t)(l > 0 ? l : 1));
-            o->cons_cov[c] = (int *)poa_xmalloc(sizeof(int) * (size_t)(l > 0 ? l : 1));
-            memcpy(o->cons_base[c], abc->cons_base[c], (size_t)l);
-            memcpy(o->cons_cov[c], abc->cons_cov[c], sizeof(int) * (size_t)l);
-        }
-    }
-    if (abpt->out_msa && abc->msa_len > 0) {
-        o->msa_len = abc->msa_len; o->n_msa_rows = abc->n_seq + abc->n_cons;
-        o->msa_base = (uint8_t **)poa_xmalloc(sizeof(uint8_t *) * (size_t)o->n_msa_rows);
-        for (int r = 0; r < o->n_msa_rows; ++r) {
-            o->msa_base[r] = (uint8_t *)poa_xmalloc((size_t)abc->msa_len);
-            memcpy(o->msa_base[r], abc->msa_base[r], (size_t)abc->msa_len);
-        }
-    }
-}
+void finish_group(GroupState &gs, abpoa_para_t *abpt) { poa_finish_group_result(gs.ab, abpt, gs.out); }
 
 struct PhaseClock {
     double plan = 0, run = 0, fuse = 0, finish = 0, setup = 0;
@@ -651,6 +660,22 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     if (!((abpt->disable_seeding && abpt->progressive_poa == 0) || abpt->align_mode != ABPOA_GLOBAL_MODE))
         poa_die(__func__, "minimizer seeding / guide-tree partitioning (-S / -p) is outside the scope of the B200 hot-path library.");
     const auto t0 = std::chrono::steady_clock::now();
+    /* ---- device-resident chain (poa_chain.cu): the whole progressive loop of a group runs on the GPU; whatever it
+     *      cannot take (parameters outside its scope, groups that outgrow their slot) goes through the launch engine ---- */
+    if (!(flags & (ABPOA_GPU_CAPTURE_JOBS | ABPOA_GPU_NO_CHAIN)) && poa_chain_eligible(abpt)) {
+        std::vector<int> todo((size_t)n_groups), rest;
+        for (int g = 0; g < n_groups; ++g) todo[g] = g;
+        poa_chain_run(e->dev, e->arena, abpt, e->n_workers, groups, results, todo, flags, rest, &e->chain);
+        if (!rest.empty()) {
+            std::sort(rest.begin(), rest.end());
+            std::vector<abpoa_gpu_group_t> sub(rest.size()); std::vector<abpoa_gpu_group_result_t> subres(rest.size());
+            for (size_t k = 0; k < rest.size(); ++k) sub[k] = groups[rest[k]];
+            abpoa_gpu_msa_batch(e, abpt, (int)rest.size(), sub.data(), subres.data(), flags | ABPOA_GPU_NO_CHAIN);
+            for (size_t k = 0; k < rest.size(); ++k) results[rest[k]] = subres[k];
+        }
+        e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    }
     if (flags & ABPOA_GPU_CAPTURE_JOBS) abpoa_gpu_capture_clear(e);
     for (poa_dev_ctx *c : e->ctx) poa_dev_ctx_set_capture(c, (flags & ABPOA_GPU_CAPTURE_JOBS) ? capture_cb : NULL, e);
     std::atomic<int> next_chunk(0);

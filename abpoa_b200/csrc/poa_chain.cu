@@ -1,0 +1,429 @@
+/* poa_chain.cu -- the device-resident progressive POA ("chain engine") behind abpoa_gpu_msa_batch.
+ *
+ * Reads of a group are strictly sequential (read i+1 is aligned to the graph that already contains
+ * read i; reference src/abpoa_align.c:312-352).  The launch-per-round engine of poa_batch.cu pays a
+ * host round trip per read (flatten -> H2D -> kernel -> D2H -> host fusion).  Here the graph lives in
+ * HBM: per round and cohort of groups the stream carries exactly two kernels,
+ *
+ *     poa_chain_align_kernel_p16   one warp per group: DP + backtrace of read r (poa_kernels.cu)
+ *     poa_chain_fuse_kernel        one CTA per group: fuse the graph-CIGAR, splice the order, edge order,
+ *                                  max_remain, flatten graph + read r+1 into the next job (poa_chain.cuh)
+ *
+ * and the host does nothing until the group is finished: reads go up once, the final graph comes
+ * back once (compact export, rebuilt by poa_graph_import) and the host runs consensus on it.
+ * Groups the device cannot finish (capacity, int16 window, band wider than estimated) are reported
+ * back and completed by the launch-per-round engine -- same results either way.
+ *
+ * Scope of the chain: global alignment, banded (wb >= 0), packed-int16 admissible scores, consensus
+ * output (no per-edge read sets), unit base weights.  Everything else takes the other engine.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "abpoa_gpu.h"
+#include "poa_internal.h"
+#include "poa_engine.h"
+#include "poa_device.cuh"
+#include "poa_chain.cuh"
+#include "poa_chain_host.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    poa_die("libabpoa_b200/chain", "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
+                                                  const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st);
+extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
+
+/* ------------------------------------------------------------------ kernels */
+__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_seed_kernel(PoaChainSlot *slots, const PoaChainParams *cp, int n) {
+    if ((int)blockIdx.x >= n) return;
+    chain_seed(&slots[blockIdx.x], cp);
+}
+
+__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_kernel(PoaChainSlot *slots, const int32_t *idx, const PoaChainParams *cp, int n) {
+    if ((int)blockIdx.x >= n) return;
+    chain_fuse(&slots[idx[blockIdx.x]], cp);
+}
+
+/* Compact export of the final graphs (layout: poa_graph_import in poa_graph.c).  ex_off[g] = first int32 word of
+ * group g's record in `ex`; a record is written only if it fits ex_cap[g] words (else word 0 = -1). */
+__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_export_kernel(PoaChainSlot *slots, const PoaChainParams *cp, int n,
+                                                                       int32_t *ex, const int64_t *ex_off, const int32_t *ex_cap) {
+    if ((int)blockIdx.x >= n) return;
+    PoaChainSlot *s = &slots[blockIdx.x];
+    int32_t *o = ex + ex_off[blockIdx.x];
+    const int K = cp->K, A = cp->A, nn = s->n_nodes;
+    if (s->failed) { if (threadIdx.x == 0) o[0] = -1; return; }
+    int32_t *ci = s->scr[0], *ca = s->scr[1];
+    POA_PAR_FOR(v, nn) { ci[v] = s->in_cnt[v]; ca[v] = s->aln_cnt[v]; }
+    __syncthreads();
+    const int n_in = cta_excl_scan(ci, nn);
+    __syncthreads();
+    const int n_aln = cta_excl_scan(ca, nn);
+    __syncthreads();
+    int32_t *co = s->scr[2];
+    POA_PAR_FOR(v, nn) co[v] = s->out_cnt[v];
+    __syncthreads();
+    const int n_out = cta_excl_scan(co, nn);
+    __syncthreads();
+    const int64_t words = 4 + 5ll * nn + 4ll * n_in + n_aln;
+    if (words > ex_cap[blockIdx.x] || n_out != n_in) { if (threadIdx.x == 0) o[0] = -1; return; }
+    int32_t *base = o + 4, *n_read = base + nn, *in_cnt = n_read + nn, *out_cnt = in_cnt + nn, *aln_cnt = out_cnt + nn;
+    int32_t *in_id = aln_cnt + nn, *in_w = in_id + n_in, *out_id = in_w + n_in, *out_w = out_id + n_in, *aln = out_w + n_in;
+    if (threadIdx.x == 0) { o[0] = nn; o[1] = n_in; o[2] = n_aln; o[3] = s->fused; }
+    POA_PAR_FOR(v, nn) {
+        base[v] = s->base[v]; n_read[v] = s->n_read[v]; in_cnt[v] = s->in_cnt[v]; out_cnt[v] = s->out_cnt[v]; aln_cnt[v] = s->aln_cnt[v];
+        for (int e = 0; e < s->in_cnt[v]; ++e) { in_id[ci[v] + e] = s->in_id[(size_t)v * K + e]; in_w[ci[v] + e] = s->in_w[(size_t)v * K + e]; }
+        for (int e = 0; e < s->out_cnt[v]; ++e) { out_id[co[v] + e] = s->out_id[(size_t)v * K + e]; out_w[co[v] + e] = s->out_w[(size_t)v * K + e]; }
+        for (int a = 0; a < s->aln_cnt[v]; ++a) aln[ca[v] + a] = s->aln_id[(size_t)v * A + a];
+    }
+}
+
+/* ------------------------------------------------------------------ host side */
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int poa_chain_eligible(const abpoa_para_t *abpt) {
+    const char *off = getenv("ABPOA_GPU_NO_CHAIN");
+    if (off && *off == '1') return 0;
+    if (abpt->align_mode != ABPOA_GLOBAL_MODE || abpt->wb < 0) return 0;
+    if (abpt->use_read_ids || abpt->out_msa || abpt->out_gfa || abpt->max_n_cons > 1 || abpt->cons_algrm != ABPOA_HB) return 0;
+    if (abpt->use_qv || abpt->amb_strand || abpt->inc_path_score || abpt->zdrop > 0 || abpt->rev_cigar || !abpt->ret_cigar) return 0;
+    if (abpt->put_gap_on_right || abpt->put_gap_at_end) return 0;         /* handled by the kernels, but keep the chain on the common configuration */
+    if (abpt->m > POA_MAX_M) return 0;
+    if (!(abpt->disable_seeding && abpt->progressive_poa == 0)) return 0;
+    return 1;
+}
+
+namespace {
+
+struct GroupPlan {
+    int g;                  /* index into the caller's groups */
+    int n_reads, qmax; int64_t bases;
+    int n_cap; size_t static_bytes; double pool_units_est;
+};
+
+struct Cohort {
+    std::vector<int> members;               /* indices into the wave's plan list */
+    cudaStream_t st = NULL;
+    cudaEvent_t ev_begin = NULL, ev_end = NULL;
+};
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+/* Run the groups listed in `todo` (eligible ones) through the device chain.  Groups that could not be
+ * finished are appended to `fallback`.  Returns 0. */
+int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, const abpoa_gpu_group_t *groups,
+                  abpoa_gpu_group_result_t *results, const std::vector<int> &todo, int flags, std::vector<int> &fallback, PoaChainStats *stats) {
+    CK(cudaSetDevice(dev));
+    const bool record = (flags & ABPOA_GPU_RECORD_READS) != 0;
+    const bool verbose = getenv("ABPOA_GPU_PROFILE") != NULL;
+    const int m = abpt->m;
+    const int K = [&] { const char *e = getenv("ABPOA_GPU_CHAIN_K"); return e && *e ? atoi(e) : (m > 5 ? 24 : 12); }();
+    const int A = m - 1 > 1 ? m - 1 : 1;
+    const int P = abpt->gap_mode == ABPOA_LINEAR_GAP ? 1 : (abpt->gap_mode == ABPOA_AFFINE_GAP ? 3 : 5);
+    int n_cohorts = [&] { const char *e = getenv("ABPOA_GPU_CHAIN_COHORTS"); return e && *e ? atoi(e) : 4; }();
+    if (n_cohorts < 1) n_cohorts = 1;
+
+    /* ---- per-group sizes ---- */
+    std::vector<GroupPlan> plans;
+    for (int g : todo) {
+        const abpoa_gpu_group_t &in = groups[g];
+        GroupPlan p; p.g = g; p.n_reads = in.n_seq; p.qmax = 0; p.bases = 0;
+        bool ok = in.n_seq >= 2;
+        for (int i = 0; i < in.n_seq; ++i) {
+            const int l = in.seq_lens[i];
+            if (l < 1) ok = false;
+            if (l > p.qmax) p.qmax = l;
+            p.bases += l;
+            if (ok && !poa_p16_ok(abpt, l, 3 * l)) ok = false;
+        }
+        if (!ok || p.qmax > (1 << 24)) { fallback.push_back(g); continue; }
+        const int64_t grow = (int64_t)((double)p.qmax * (1.0 + 0.10 * (p.n_reads - 1))) + 256;
+        p.n_cap = (int)std::min<int64_t>(2 + p.bases, grow);
+        const size_t nc = (size_t)p.n_cap, scr_n = std::max<size_t>((size_t)p.qmax + 2, nc);
+        size_t b = 0;
+        b += al256(nc);                                            /* base            */
+        b += 4 * al256(nc * 4);                                    /* counts, n_read  */
+        b += 4 * al256(nc * K * 4);                                /* edge lists      */
+        b += al256(nc * A * 4);                                    /* aligned sets    */
+        b += 4 * al256(nc * 4);                                    /* order x2, node_row, rem_row */
+        b += 6 * al256(scr_n * 4);                                 /* scratch         */
+        b += al256((size_t)p.bases) + al256(((size_t)p.n_reads + 1) * 4) + al256((size_t)p.n_reads * 4);   /* reads, offsets, w */
+        const size_t pred_cap = nc * 3;
+        b += al256(256 + (nc + 1) * 8 + pred_cap * 4 + 4 + (size_t)p.qmax + 64);    /* job blob        */
+        b += al256(nc * sizeof(PoaRowInfo)) + al256(nc * 4);       /* rowinfo, rowoff */
+        b += al256(((size_t)p.qmax + nc + 8) * 8);                 /* graph-CIGAR     */
+        b += al256((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);  /* query profile   */
+        b += al256(sizeof(PoaResultDev));
+        if (record) b += 2 * al256((size_t)p.n_reads * 4) + al256((size_t)p.n_reads * 8);
+        p.static_bytes = b;
+        const int wmax = poa_band_halfwidth(abpt, p.qmax);
+        const double rows_final = std::min<double>(2.0 + (double)p.bases, (double)p.qmax * (1.0 + 0.045 * (p.n_reads - 1)) + 64);
+        p.pool_units_est = rows_final * (double)((2 * wmax + 1 + 32 + 7) / 8 + 2) * P;
+        plans.push_back(p);
+    }
+    if (plans.empty()) return 0;
+
+    /* ---- waves: as many groups as the arena holds (static regions + plane pool) ---- */
+    const size_t arena_cap = poa_arena_capacity(arena);
+    size_t pos = 0;
+    std::vector<abpoa_t *> handles;
+    while (pos < plans.size()) {
+        size_t end = pos, need_static = 0; double need_pool = 0;
+        while (end < plans.size()) {
+            const size_t s2 = need_static + plans[end].static_bytes + sizeof(PoaChainSlot) + 4096;
+            const double p2 = need_pool + plans[end].pool_units_est * 16.0 * 1.15;
+            if (end > pos && (double)s2 + p2 + (64 << 20) > (double)arena_cap) break;
+            need_static = s2; need_pool = p2; ++end;
+        }
+        if ((double)need_static + need_pool * 0.5 + (64 << 20) > (double)arena_cap) {       /* a single group that does not fit */
+            fallback.push_back(plans[pos].g); ++pos; continue;
+        }
+        const int nw = (int)(end - pos);
+        const double t_wave0 = now_ms();
+        /* ---- carve the arena: everything of the wave in one borrow ---- */
+        const size_t total = arena_cap;
+        uint8_t *d_base = poa_arena_borrow(arena, total);
+        size_t doff = 0;
+        auto dtake = [&](size_t b) { uint8_t *q = d_base + doff; doff += al256(b); return q; };
+        PoaChainSlot *d_slots = (PoaChainSlot *)dtake((size_t)nw * sizeof(PoaChainSlot));
+        PoaChainParams *d_cp = (PoaChainParams *)dtake(sizeof(PoaChainParams));
+        PoaParamsDev *d_prm = (PoaParamsDev *)dtake(sizeof(PoaParamsDev));
+        unsigned long long *d_cursors = (unsigned long long *)dtake((size_t)n_cohorts * 2 * sizeof(unsigned long long));
+
+        /* pinned staging: slots | params | reads + offsets + w of every group | round index lists */
+        std::vector<PoaChainSlot> hs((size_t)nw);
+        size_t reads_bytes = 0;
+        for (int t = 0; t < nw; ++t) reads_bytes += al256((size_t)plans[pos + t].bases) + al256(((size_t)plans[pos + t].n_reads + 1) * 4) + al256((size_t)plans[pos + t].n_reads * 4);
+        uint8_t *h_reads = NULL; CK(cudaHostAlloc((void **)&h_reads, reads_bytes + 256, cudaHostAllocDefault));
+        uint8_t *d_reads = dtake(reads_bytes);
+        size_t roff = 0;
+        int max_reads = 0, band_cells = 64;
+        for (int t = 0; t < nw; ++t) {
+            const GroupPlan &p = plans[pos + t];
+            const abpoa_gpu_group_t &in = groups[p.g];
+            PoaChainSlot &s = hs[t]; memset(&s, 0, sizeof s);
+            const size_t nc = (size_t)p.n_cap, scr_n = std::max<size_t>((size_t)p.qmax + 2, nc);
+            s.n_cap = p.n_cap; s.pred_cap = (int32_t)(nc * 3); s.n_reads = p.n_reads;
+            s.base = dtake(nc);
+            s.in_cnt = (int32_t *)dtake(nc * 4); s.out_cnt = (int32_t *)dtake(nc * 4); s.aln_cnt = (int32_t *)dtake(nc * 4); s.n_read = (int32_t *)dtake(nc * 4);
+            s.in_id = (int32_t *)dtake(nc * K * 4); s.in_w = (int32_t *)dtake(nc * K * 4); s.out_id = (int32_t *)dtake(nc * K * 4); s.out_w = (int32_t *)dtake(nc * K * 4);
+            s.aln_id = (int32_t *)dtake(nc * A * 4);
+            s.order[0] = (int32_t *)dtake(nc * 4); s.order[1] = (int32_t *)dtake(nc * 4); s.node_row = (int32_t *)dtake(nc * 4); s.rem_row = (int32_t *)dtake(nc * 4);
+            for (int k = 0; k < 6; ++k) s.scr[k] = (int32_t *)dtake(scr_n * 4);
+            /* reads */
+            uint8_t *hr = h_reads + roff; const size_t rb = al256((size_t)p.bases), ob = al256(((size_t)p.n_reads + 1) * 4);
+            int32_t *hoff = (int32_t *)(hr + rb), *hw = (int32_t *)(hr + rb + ob);
+            int acc = 0;
+            for (int i = 0; i < p.n_reads; ++i) {
+                memcpy(hr + acc, in.seqs[i], (size_t)in.seq_lens[i]);
+                hoff[i] = acc; acc += in.seq_lens[i];
+                hw[i] = poa_band_halfwidth(abpt, in.seq_lens[i]);
+                const int bc = (2 * hw[i] + 1 + 40 + 7) / 8 * 8;
+                if (bc > band_cells) band_cells = bc;
+            }
+            hoff[p.n_reads] = acc;
+            s.reads = d_reads + roff; s.read_off = (const int32_t *)(d_reads + roff + rb); s.read_w = (const int32_t *)(d_reads + roff + rb + ob);
+            roff += rb + ob + al256((size_t)p.n_reads * 4);
+            /* job */
+            s.blob_cap = (int32_t)(256 + (nc + 1) * 8 + (size_t)s.pred_cap * 4 + 4 + (size_t)p.qmax + 64);
+            s.jd.blob = dtake((size_t)s.blob_cap);
+            s.jd.rowinfo = (PoaRowInfo *)dtake(nc * sizeof(PoaRowInfo)); s.jd.rowoff = (uint32_t *)dtake(nc * 4);
+            s.jd.cigar_cap = (int32_t)(p.qmax + p.n_cap + 8);
+            s.jd.cigar = (uint64_t *)dtake((size_t)s.jd.cigar_cap * 8);
+            s.jd.qprof = (int16_t *)dtake((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);
+            s.jd.result = (PoaResultDev *)dtake(sizeof(PoaResultDev));
+            if (record) { s.rec_score = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_nops = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_hash = (uint64_t *)dtake((size_t)p.n_reads * 8); }
+            if (p.n_reads > max_reads) max_reads = p.n_reads;
+        }
+        /* round index lists per cohort: wave-local slot indices of the groups that still have a read r */
+        std::vector<Cohort> coh((size_t)std::min(n_cohorts, nw));
+        for (int t = 0; t < nw; ++t) coh[(size_t)t % coh.size()].members.push_back(t);
+        std::vector<int32_t> h_idx; std::vector<std::vector<std::pair<size_t, int>>> round_of(coh.size());   /* (offset into h_idx, count) per round */
+        for (size_t c = 0; c < coh.size(); ++c)
+            for (int r = 1; r < max_reads; ++r) {
+                const size_t o = h_idx.size(); int cnt = 0;
+                for (int t : coh[c].members) if (plans[pos + t].n_reads > r) { h_idx.push_back(t); ++cnt; }
+                round_of[c].push_back({o, cnt});
+            }
+        int32_t *d_idx = (int32_t *)dtake(std::max<size_t>(h_idx.size(), 1) * 4);
+        /* export buffers */
+        std::vector<int64_t> h_exoff((size_t)nw); std::vector<int32_t> h_excap((size_t)nw); int64_t ex_words = 0;
+        for (int t = 0; t < nw; ++t) {
+            const GroupPlan &p = plans[pos + t];
+            const int64_t cap = 4 + 5ll * p.n_cap + 4ll * 3 * p.n_cap + (int64_t)p.n_cap * 2;
+            h_exoff[t] = ex_words; h_excap[t] = (int32_t)std::min<int64_t>(cap, INT32_MAX); ex_words += (cap + 63) & ~63ll;
+        }
+        int64_t *d_exoff = (int64_t *)dtake((size_t)nw * 8); int32_t *d_excap = (int32_t *)dtake((size_t)nw * 4);
+        /* the export buffer and the plane pool share what is left: planes are dead when the export runs */
+        doff = al256(doff);
+        if (doff > total) poa_die("libabpoa_b200/chain", "wave layout (%zu bytes) exceeds the arena (%zu bytes)", doff, total);
+        if (doff + (size_t)ex_words * 4 + (32 << 20) > total) {       /* cannot happen with the wave sizing above; be safe */
+            poa_arena_return(arena, d_base, total); CK(cudaFreeHost(h_reads));
+            for (int t = 0; t < nw; ++t) fallback.push_back(plans[pos + t].g);
+            pos = end; continue;
+        }
+        uint8_t *d_pool = d_base + doff; const size_t pool_bytes = total - doff;
+        int32_t *d_ex = (int32_t *)d_pool;
+        /* pool shares per cohort, proportional to the estimates */
+        std::vector<double> est(coh.size(), 0.0); double est_tot = 0;
+        for (size_t c = 0; c < coh.size(); ++c) { for (int t : coh[c].members) est[c] += plans[pos + t].pool_units_est; est_tot += est[c]; }
+        {
+            size_t o = 0;
+            for (size_t c = 0; c < coh.size(); ++c) {
+                const size_t share = c + 1 == coh.size() ? pool_bytes - o : (size_t)((double)pool_bytes * est[c] / est_tot) & ~(size_t)255;
+                for (int t : coh[c].members) { hs[t].pool_base = d_pool + o; hs[t].pool_units = share / 16; hs[t].pool_cursor = d_cursors + 2 * c; }
+                o += share;
+            }
+        }
+        PoaChainParams hcp; memset(&hcp, 0, sizeof hcp);
+        hcp.K = K; hcp.A = A; hcp.m = m; hcp.max_mat = abpt->max_mat; hcp.min_mis = abpt->min_mis; hcp.o1 = abpt->gap_open1; hcp.e1 = abpt->gap_ext1;
+        hcp.oe1 = abpt->gap_open1 + abpt->gap_ext1; hcp.oe2 = abpt->gap_open2 + abpt->gap_ext2; hcp.record = record ? 1 : 0; hcp.P = P;
+        PoaParamsDev hprm; poa_fill_params(&hprm, abpt, 15);
+
+        /* ---- upload (stream 0 of the wave), then fork the cohort streams ---- */
+        for (Cohort &c : coh) { CK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking)); CK(cudaEventCreate(&c.ev_begin)); CK(cudaEventCreate(&c.ev_end)); }
+        cudaStream_t s0 = coh[0].st;
+        cudaEvent_t ev_up, ev_t0, ev_t1; CK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming)); CK(cudaEventCreate(&ev_t0)); CK(cudaEventCreate(&ev_t1));
+        CK(cudaMemcpyAsync(d_reads, h_reads, reads_bytes, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_slots, hs.data(), (size_t)nw * sizeof(PoaChainSlot), cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_cp, &hcp, sizeof hcp, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_prm, &hprm, sizeof hprm, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_idx, h_idx.data(), h_idx.size() * 4, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_exoff, h_exoff.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(d_excap, h_excap.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemsetAsync(d_cursors, 0, (size_t)n_cohorts * 2 * sizeof(unsigned long long), s0));
+        const uint64_t h2d = reads_bytes + (uint64_t)nw * sizeof(PoaChainSlot) + sizeof hcp + sizeof hprm + h_idx.size() * 4 + (uint64_t)nw * 12;
+        /* timed region of the device work: inputs are resident when ev_t0 fires */
+        CK(cudaEventRecord(ev_t0, s0));
+        poa_chain_seed_kernel<<<nw, POA_CHAIN_T, 0, s0>>>(d_slots, d_cp, nw);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev_up, s0));
+        static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
+        int ring_rows = 2, ring_cells = 64;
+        poa_pick_ring(abpt->gap_mode, 16, band_cells, smem_budget, &ring_rows, &ring_cells);
+        int64_t launches = 1;
+        for (size_t c = 0; c < coh.size(); ++c) {
+            cudaStream_t st = coh[c].st;
+            if (c > 0) CK(cudaStreamWaitEvent(st, ev_up, 0));
+            for (int r = 1; r < max_reads; ++r) {
+                const std::pair<size_t, int> &ro = round_of[c][(size_t)r - 1];
+                if (ro.second == 0) break;
+                CK(poa_launch_chain_align_p16(abpt->gap_mode, d_slots, d_idx + ro.first, ro.second, r, d_prm, ring_rows, ring_cells, st));
+                poa_chain_fuse_kernel<<<ro.second, POA_CHAIN_T, 0, st>>>(d_slots, d_idx + ro.first, d_cp, ro.second);
+                CK(cudaGetLastError());
+                launches += 2;
+            }
+            CK(cudaEventRecord(coh[c].ev_end, st));
+        }
+        for (size_t c = 1; c < coh.size(); ++c) CK(cudaStreamWaitEvent(s0, coh[c].ev_end, 0));
+        CK(cudaEventRecord(ev_t1, s0));
+        /* ---- export: slot headers first (sizes), then the compact graphs ---- */
+        poa_chain_export_kernel<<<nw, POA_CHAIN_T, 0, s0>>>(d_slots, d_cp, nw, d_ex, d_exoff, d_excap);
+        CK(cudaGetLastError());
+        ++launches;
+        std::vector<PoaChainSlot> fin((size_t)nw);
+        PoaChainSlot *h_fin = NULL; CK(cudaHostAlloc((void **)&h_fin, (size_t)nw * sizeof(PoaChainSlot), cudaHostAllocDefault));
+        CK(cudaMemcpyAsync(h_fin, d_slots, (size_t)nw * sizeof(PoaChainSlot), cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        float dev_ms = 0.f; CK(cudaEventElapsedTime(&dev_ms, ev_t0, ev_t1));
+        memcpy(fin.data(), h_fin, (size_t)nw * sizeof(PoaChainSlot));
+        CK(cudaFreeHost(h_fin));
+        const double t_dev_done = now_ms();
+        /* word counts: header words 0..3 of every record */
+        std::vector<int32_t> hdr4((size_t)nw * 4);
+        {
+            int32_t *h_hdr = NULL; CK(cudaHostAlloc((void **)&h_hdr, (size_t)nw * 16, cudaHostAllocDefault));
+            for (int t = 0; t < nw; ++t) CK(cudaMemcpyAsync(h_hdr + 4 * t, d_ex + h_exoff[t], 16, cudaMemcpyDeviceToHost, s0));
+            CK(cudaStreamSynchronize(s0));
+            memcpy(hdr4.data(), h_hdr, (size_t)nw * 16);
+            CK(cudaFreeHost(h_hdr));
+        }
+        std::vector<int64_t> words((size_t)nw, 0), hoff2((size_t)nw, 0); int64_t tot_words = 0;
+        for (int t = 0; t < nw; ++t) {
+            if (fin[t].failed || hdr4[4 * t] < 2) continue;
+            words[t] = 4 + 5ll * hdr4[4 * t] + 4ll * hdr4[4 * t + 1] + hdr4[4 * t + 2];
+            hoff2[t] = tot_words; tot_words += words[t];
+        }
+        int32_t *h_ex = NULL; CK(cudaHostAlloc((void **)&h_ex, (size_t)std::max<int64_t>(tot_words, 1) * 4, cudaHostAllocDefault));
+        for (int t = 0; t < nw; ++t) if (words[t]) CK(cudaMemcpyAsync(h_ex + hoff2[t], d_ex + h_exoff[t], (size_t)words[t] * 4, cudaMemcpyDeviceToHost, s0));
+        /* per-read records */
+        std::vector<std::vector<int32_t>> rs((size_t)nw), rn((size_t)nw); std::vector<std::vector<uint64_t>> rh((size_t)nw);
+        if (record) for (int t = 0; t < nw; ++t) {
+            const int nr = plans[pos + t].n_reads;
+            rs[t].resize(nr); rn[t].resize(nr); rh[t].resize(nr);
+            CK(cudaMemcpyAsync(rs[t].data(), fin[t].rec_score, (size_t)nr * 4, cudaMemcpyDeviceToHost, s0));
+            CK(cudaMemcpyAsync(rn[t].data(), fin[t].rec_nops, (size_t)nr * 4, cudaMemcpyDeviceToHost, s0));
+            CK(cudaMemcpyAsync(rh[t].data(), fin[t].rec_hash, (size_t)nr * 8, cudaMemcpyDeviceToHost, s0));
+        }
+        CK(cudaStreamSynchronize(s0));
+        const uint64_t d2h = (uint64_t)tot_words * 4 + (uint64_t)nw * (sizeof(PoaChainSlot) + 16);
+        poa_arena_return(arena, d_base, total);
+        const double t_copied = now_ms();
+
+        /* ---- host: rebuild each graph, consensus ---- */
+        std::atomic<int> next(0); std::atomic<int> n_failed(0);
+        std::vector<int> failed_groups; std::mutex fmu;
+        int64_t cells = 0, alns = 0;
+        for (int t = 0; t < nw; ++t) if (!fin[t].failed && words[t]) { cells += fin[t].cells; alns += plans[pos + t].n_reads - 1; }
+        const int nth = std::max(1, std::min(n_workers, nw));
+        std::vector<std::thread> th;
+        for (int w = 0; w < nth; ++w)
+            th.emplace_back([&, w]() {
+                (void)w;
+                abpoa_t *ab = abpoa_init();
+                for (;;) {
+                    const int t = next.fetch_add(1);
+                    if (t >= nw) break;
+                    const GroupPlan &p = plans[pos + t];
+                    if (fin[t].failed || !words[t]) {
+                        if (verbose) fprintf(stderr, "[chain] group %d left the device chain after %d reads (flags 0x%x)\n", p.g, fin[t].fused, fin[t].failed);
+                        std::lock_guard<std::mutex> lk(fmu); failed_groups.push_back(p.g); n_failed += 1; continue;
+                    }
+                    abpoa_gpu_group_result_t *o = &results[p.g];
+                    memset(o, 0, sizeof *o);
+                    abpoa_reset(ab, abpt, p.qmax);
+                    abpoa_seq_t *abs = ab->abs;
+                    abs->n_seq = p.n_reads; poa_seq_reserve(abs);
+                    for (int i = 0; i < p.n_reads; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
+                    poa_graph_import(ab, abpt, h_ex + hoff2[t]);
+                    poa_finish_group_result(ab, abpt, o);
+                    o->dp_cells = fin[t].cells; o->n_aligned = p.n_reads - 1;
+                    if (record) {
+                        const int nr = p.n_reads;
+                        o->read_best_score = (int32_t *)poa_xcalloc((size_t)nr, sizeof(int32_t));
+                        o->read_n_cigar = (int32_t *)poa_xcalloc((size_t)nr, sizeof(int32_t));
+                        o->read_cigar_hash = (uint64_t *)poa_xcalloc((size_t)nr, sizeof(uint64_t));
+                        o->read_cigar_hash[0] = 1469598103934665603ull;               /* FNV-1a of an empty CIGAR, as the other engine records it */
+                        for (int i = 1; i < nr; ++i) { o->read_best_score[i] = rs[t][i]; o->read_n_cigar[i] = rn[t][i]; o->read_cigar_hash[i] = rh[t][i]; }
+                    }
+                }
+                abpoa_free(ab);
+            });
+        for (auto &x : th) x.join();
+        for (int g : failed_groups) fallback.push_back(g);
+        CK(cudaFreeHost(h_ex)); CK(cudaFreeHost(h_reads));
+        for (Cohort &c : coh) { cudaEventDestroy(c.ev_begin); cudaEventDestroy(c.ev_end); cudaStreamDestroy(c.st); }
+        cudaEventDestroy(ev_up); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+        if (stats) {
+            stats->device_ms += dev_ms; stats->cells += cells; stats->alignments += alns; stats->launches += launches;
+            stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; stats->groups_done += nw - n_failed.load(); stats->groups_failed += n_failed.load();
+        }
+        if (verbose)
+            fprintf(stderr, "[chain] wave of %d groups (%zu cohorts, K=%d): stage+launch+device %.0f ms (device %.1f ms), export copy %.0f ms, import+consensus %.0f ms; "
+                            "static %.2f GB, pool %.2f GB, export %.1f MB; %d groups handed to the launch engine\n",
+                    nw, coh.size(), K, t_dev_done - t_wave0, dev_ms, t_copied - t_dev_done, now_ms() - t_copied,
+                    (double)doff / 1e9, (double)pool_bytes / 1e9, (double)tot_words * 4 / 1e6, n_failed.load());
+        pos = end;
+    }
+    return 0;
+}

@@ -142,3 +142,16 @@ int poa_p16_ok(const abpoa_para_t *abpt, int qlen, int n_rows) {
     }
     return 1;
 }
+
+/* debugging aid (tests): the job blob poa_blob_fill builds for aligning `query` to the whole graph of `ab`,
+ * copied into `out` (capacity `cap`); returns its size or -1 */
+int poa_debug_blob(abpoa_t *ab, abpoa_para_t *abpt, const uint8_t *query, int qlen, uint8_t *out, int cap) {
+    abpoa_graph_t *abg = ab->abg;
+    if (abg->node_n <= 2) return -1;
+    if (!abg->is_topological_sorted) abpoa_topological_sort(abg, abpt);
+    poa_blob_plan pl;
+    poa_blob_plan_make(&pl, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, qlen);
+    if ((size_t)cap < pl.bytes) return -1;
+    poa_blob_fill(out, &pl, abg, abpt, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID, query);
+    return (int)pl.bytes;
+}

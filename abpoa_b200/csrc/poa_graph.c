@@ -858,6 +858,49 @@ int abpoa_add_graph_alignment(abpoa_t *ab, abpoa_para_t *abpt, uint8_t *seq, int
                                         res, read_id, tot_read_n, inc_both_ends);
 }
 
+/* ------------------------------------------------------------------ import of a device-built graph
+ * The device chain (poa_chain.cuh) builds the same graph, node id for node id, on the GPU; at the end of
+ * a read group it is exported as int32 words
+ *   [0] n  [1] total in-edges E  [2] total aligned-set entries  [3] reads fused
+ *   base[n] n_read[n] in_cnt[n] out_cnt[n] aln_cnt[n]  in_id[E] in_w[E] out_id[E] out_w[E]  aln[..]
+ * (edge lists node by node, in list order) and rebuilt here so that consensus / output run on the
+ * ordinary host structures.  The handle must be freshly abpoa_reset(). */
+void poa_graph_import(abpoa_t *ab, abpoa_para_t *abpt, const int32_t *ex) {
+    abpoa_graph_t *abg = ab->abg;
+    poa_graph_x *x = gx(abg);
+    const int n = ex[0], n_in = ex[1], n_fused = ex[3];
+    if (abg->node_n != 2 || n < 2) poa_die(__func__, "import needs an empty graph (node_n %d) and n >= 2 (%d)", abg->node_n, n);
+    const int32_t *base = ex + 4, *n_read = base + n, *in_cnt = n_read + n, *out_cnt = in_cnt + n, *aln_cnt = out_cnt + n;
+    const int32_t *in_id = aln_cnt + n, *in_w = in_id + n_in, *out_id = in_w + n_in, *out_w = out_id + n_in, *aln = out_w + n_in;
+    nodes_reserve(abg, n);
+    index_arrays_reserve(abg, abpt, abg->node_m);
+    for (int v = 2; v < n; ++v) { abg->node[v].base = (uint8_t)base[v]; x->cbase[v] = (uint8_t)base[v]; }
+    abg->node_n = n;
+    int pi = 0, po = 0, pa = 0;
+    for (int v = 0; v < n; ++v) {
+        abpoa_node_t *nd = &abg->node[v];
+        if (in_cnt[v] > 0) {
+            in_edges_reserve(x, v, in_cnt[v]);
+            memcpy(nd->in_id, in_id + pi, (size_t)in_cnt[v] * sizeof(int)); memcpy(nd->in_edge_weight, in_w + pi, (size_t)in_cnt[v] * sizeof(int));
+        }
+        nd->in_edge_n = in_cnt[v]; x->cin[v] = in_cnt[v]; pi += in_cnt[v];
+        if (in_cnt[v] >= 2) mark_fwd_counted(x, v);
+        if (out_cnt[v] > 0) {
+            out_edges_reserve(x, v, out_cnt[v], 0);
+            memcpy(nd->out_id, out_id + po, (size_t)out_cnt[v] * sizeof(int)); memcpy(nd->out_edge_weight, out_w + po, (size_t)out_cnt[v] * sizeof(int));
+        }
+        nd->out_edge_n = out_cnt[v]; x->cout[v] = out_cnt[v]; po += out_cnt[v];
+        for (int a = 0; a < aln_cnt[v]; ++a) aligned_push(abg, v, aln[pa + a]);
+        x->caln[v] = nd->aligned_node_n; pa += aln_cnt[v];
+        if (aln_cnt[v] > 0) mark_fwd_counted(x, v);
+        x->cnread[v] = n_read[v]; x->cspan[v] = n_fused;
+    }
+    if (pi != n_in || po != n_in) poa_die(__func__, "inconsistent export: %d in-edges, %d out-edges, header says %d", pi, po, n_in);
+    x->n_edges = n_in; x->public_stale = 1; x->span_pending = 0;
+    abg->is_topological_sorted = abg->is_called_cons = abg->is_set_msa_rank = 0;
+    poa_graph_sync_public(abg);
+}
+
 /* ------------------------------------------------------------------ sub-graph windows
  * abpoa_subgraph_nodes (reference src/abpoa_graph.c:595-687): widen the index window
  * [inc_beg, inc_end] until no edge enters it from outside, and return the node ids just

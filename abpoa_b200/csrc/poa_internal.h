@@ -59,6 +59,7 @@ void poa_graph_set_fast_order(abpoa_graph_t *abg, int on);
 void poa_graph_order_stats(const abpoa_graph_t *abg, int64_t *spliced, int64_t *fallback);
 int poa_add_alignment_nosync(abpoa_t *ab, abpoa_para_t *abpt, int beg_node_id, int end_node_id, uint8_t *seq, int *weight,
                              int seq_l, int *qpos_to_node_id, abpoa_res_t res, int read_id, int tot_read_n, int inc_both_ends);
+void poa_graph_import(abpoa_t *ab, abpoa_para_t *abpt, const int32_t *ex);     /* rebuild a device-built graph (poa_chain) */
 int64_t poa_graph_edge_count(const abpoa_graph_t *abg);
 const uint8_t *poa_graph_bases(const abpoa_graph_t *abg);
 const int *poa_graph_in_degrees(const abpoa_graph_t *abg);

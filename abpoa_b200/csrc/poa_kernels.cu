@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "poa_device.cuh"
+#include "poa_chain.cuh"
 
 #define FULL 0xffffffffu
 #define NEG POA_NEG32
@@ -1269,6 +1270,44 @@ __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict
     p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
     __syncwarp();
     if (lane == 0) signal_done(jd);
+}
+
+static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells);
+
+/* ------------------------------------------------------------------ chain engine entry
+ * The same job function, fed from device-resident slots (poa_chain.cuh): the job blob of a slot is written
+ * by the fuse kernel of the previous round, nothing comes from the host.  Block 0 also zeroes the plane-pool
+ * cursor the coming fuse kernel will fill (see PoaChainSlot). */
+template <int GAP>
+__global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__restrict__ slots, const int32_t *__restrict__ idx,
+                                                           const PoaParamsDev *__restrict__ prm, int n_jobs, int round, int ring_rows, int ring_cells) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const int lane = threadIdx.x;
+    const int job = blockIdx.x;
+    if (job >= n_jobs) return;
+    const PoaChainSlot *sl = &slots[idx[job]];
+    if (job == 0 && lane == 0 && sl->pool_cursor) sl->pool_cursor[(round + 1) & 1] = 0ull;
+    const PoaJobDesc jd = sl->jd;
+    const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
+    if (sl->failed || sl->fused != round || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
+    const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
+    p16_run_job<GAP, GLOBAL>(jd, prm, sm, ring_rows, ring_cells, lane);
+}
+
+template <int GAP>
+static cudaError_t launch_chain_one(const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round, const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
+    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
+    cudaError_t e = cudaFuncSetAttribute(poa_chain_align_kernel_p16<GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    poa_chain_align_kernel_p16<GAP><<<n_jobs, 32, smem, st>>>(slots, idx, prm, n_jobs, round, ring_rows, ring_cells);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
+                                                  const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
+    if (n_jobs <= 0) return cudaSuccess;
+    if (gap_mode == LG) return launch_chain_one<LG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
+    if (gap_mode == AG) return launch_chain_one<AG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
+    return launch_chain_one<CG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
 }
 
 /* ------------------------------------------------------------------ launcher */

@@ -12,9 +12,12 @@
  * Results are identical to calling abpoa_msa() group by group (reference
  * src/abpoa_align.c:401-471) with the same abpoa_para_t.
  *
- * Two engines sit behind abpoa_gpu_msa_batch: pipelined launches (default; each
- * worker keeps ABPOA_GPU_PIPE_DEPTH sub-chunks in flight) and, with ABPOA_GPU_RESIDENT=1, one
- * resident kernel per call that is fed through per-group mailboxes in mapped pinned memory.
+ * Two engines sit behind abpoa_gpu_msa_batch.  The device-resident CHAIN engine keeps
+ * the graph of every group in HBM and runs align -> fuse -> re-order -> flatten entirely on the GPU (global,
+ * banded, consensus output); reads go up once, final graphs come back once.  Everything else -- local /
+ * extend mode, RC-MSA, -s, -G, quality weights, groups that outgrow their device slot -- runs on the
+ * LAUNCH engine: worker threads flatten and fuse on the host and launch one kernel grid per round, each
+ * worker keeping ABPOA_GPU_PIPE_DEPTH sub-chunks in flight.  Same results either way.
  */
 #ifndef ABPOA_GPU_H
 #define ABPOA_GPU_H
@@ -56,10 +59,14 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     int n_workers, device;
     int64_t fwd_clk, bt_clk;            /* SM clock cycles inside the forward DP / the backtrace, summed over alignments */
+    /* device-resident chain engine: CUDA-event time from "reads resident in HBM" to "last group fused" (summed over
+     * waves), the DP cells computed inside it, groups it finished / handed back to the launch engine */
+    double chain_device_ms; int64_t chain_cells; int chain_groups, chain_fallback_groups;
 } abpoa_gpu_stats_t;
 
 #define ABPOA_GPU_RECORD_READS 0x1
 #define ABPOA_GPU_CAPTURE_JOBS 0x2      /* keep a copy of every flattened alignment job for abpoa_gpu_replay() */
+#define ABPOA_GPU_NO_CHAIN     0x4      /* do not use the device-resident chain engine (launch-per-round engine only) */
 
 int abpoa_gpu_device_count(void);
 

@@ -29,14 +29,21 @@ def compare(got, ref, tag):
         assert all(np.array_equal(x, y) for x, y in zip(r.cov, w["cov"])), f"{tag} group {gi}: coverage"
 
 
+@pytest.mark.parametrize("engine", ["chain", "launch"])
 @pytest.mark.parametrize("name,n_groups", [("convex_10k", 4), ("affine_1k", 6), ("local_linear_5k", 1), ("aa_blosum62_2k", 2)])
-def test_full_shape(reference_lib, name, n_groups):
+def test_full_shape(reference_lib, name, n_groups, engine):
+    """engine: the device-resident chain (default for global/banded/consensus runs) or the launch-per-round engine."""
     w = synth.WORKLOADS[name]
+    if engine == "chain" and w.cfg.align_mode != 0:
+        pytest.skip("local mode always takes the launch engine")
     groups = w.groups(n_groups, base_seed=4200)
     ref = reference_records(w.cfg, groups)
     with BatchEngine() as eng:
-        got = eng.run(w.cfg, groups, record_reads=True)
-    compare(got, ref, name)
+        got = eng.run(w.cfg, groups, record_reads=True, no_chain=(engine == "launch"))
+        st = eng.stats()
+    if engine == "chain":
+        assert st["chain_groups"] == n_groups and st["chain_fallback_groups"] == 0, st
+    compare(got, ref, f"{name}/{engine}")
 
 
 def test_full_shape_convex_generic_kernels(reference_lib, monkeypatch):
