@@ -15,8 +15,10 @@ C_SRCS  := $(wildcard $(CSRC)/*.c)
 CU_SRCS := $(wildcard $(CSRC)/*.cu)
 OBJS    := $(patsubst $(CSRC)/%.c,$(OBJ)/%.o,$(C_SRCS)) $(patsubst $(CSRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS))
 
+BIN     := abpoa_b200/bin/abpoa
+
 .PHONY: all oracle clean
-all: $(LIB)
+all: $(LIB) $(BIN)
 
 $(OBJ)/%.o: $(CSRC)/%.c $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -28,10 +30,15 @@ $(OBJ)/%.cu.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) $(
 
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker -Bsymbolic -lm -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker -Bsymbolic -lm -lpthread -lz
+
+# the `abpoa` command line (reference src/abpoa.c) over the library
+$(BIN): abpoa_b200/cli/abpoa_cli.c $(LIB) $(wildcard include/*.h)
+	@mkdir -p abpoa_b200/bin
+	$(CC) -O2 -g -Wall -Iinclude -o $@ $< -L$(LIBDIR) -labpoa_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
 
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(BIN)

@@ -285,7 +285,9 @@ class msa_result:
 
 
 class msa_aligner:
-    """pyabpoa.msa_aligner (python/pyabpoa.pyx:93-371) over the B200 library."""
+    """pyabpoa.msa_aligner (python/pyabpoa.pyx:93-371) over the B200 library: same constructor arguments, same
+    methods (msa, msa_align, msa_add, msa_output), same result fields.  One handle lives as long as the object,
+    so msa_align / msa_add / msa_output build a graph incrementally exactly as the Cython class does."""
 
     def __init__(self, aln_mode="g", is_aa=False, match=2, mismatch=4, score_matrix="", gap_open1=4, gap_open2=24,
                  gap_ext1=2, gap_ext2=1, extra_b=10, extra_f=0.01, cons_algrm="HB", lib: PoaLibrary | None = None):
@@ -294,7 +296,7 @@ class msa_aligner:
             raise Exception(f"Unknown align mode: {aln_mode}")
         algs = {"HB": ABPOA_HB, "MF": ABPOA_MF}
         if cons_algrm.upper() not in algs:
-            raise Exception(f"Unknown consensus calling mode: {cons_algrm}")
+            raise Exception(f"Unknown conseneus calling mode: {cons_algrm}")
         if isinstance(score_matrix, bytes):
             score_matrix = score_matrix.decode()
         self.m = 27 if is_aa else 5
@@ -302,28 +304,95 @@ class msa_aligner:
                               score_matrix=score_matrix or None, gap_open1=gap_open1, gap_open2=gap_open2,
                               gap_ext1=gap_ext1, gap_ext2=gap_ext2, wb=extra_b, wf=extra_f,
                               cons_algrm=algs[cons_algrm.upper()])
-        self._lib = lib
+        self._s = PoaSession(self._cfg, lib)          # abpoa_init + parameters, freed with the object
 
-    def msa(self, seqs, out_cons, out_msa, max_n_cons=1, min_freq=0.25, out_pog=b"", incr_fn=b""):
-        if out_pog or incr_fn:
-            raise NotImplementedError("graph plotting / incremental restore are outside the hot-path scope")
-        cfg = PoaConfig(**{**self._cfg.__dict__, "out_cons": bool(out_cons), "out_msa": bool(out_msa),
-                           "max_n_cons": max_n_cons, "min_freq": min_freq})
-        reads = [encode(s, self.m) for s in seqs]
-        with PoaSession(cfg, self._lib) as s:
-            s.reset(max(len(r) for r in reads))
-            for r in reads:
-                _, res = s.align(r, count_cells=False)
-                s.add(r, res, len(reads))
-            s.generate()
-            abc = s.ab.contents.abc.contents
-            n_cons = abc.n_cons if out_cons else 0
-            cons = s.consensus() if out_cons else []
-            covs = s.consensus_cov() if out_cons else []
-            rows = s.msa_rows() if out_msa else []
-            clu_n = [abc.clu_n_seq[i] for i in range(n_cons)]
-            clu_ids = [[abc.clu_read_ids[i][j] for j in range(clu_n[i])] for i in range(n_cons)]
-            qv = [[abc.cons_phred_score[i][j] for j in range(abc.cons_len[i])] for i in range(n_cons)]
-            return msa_result(len(reads), n_cons, clu_n, clu_ids, [len(c) for c in cons],
-                              [decode(c, self.m) for c in cons], [list(map(int, c)) for c in covs], qv,
-                              int(abc.msa_len) if out_msa else 0, [decode(r, self.m) for r in rows])
+    def __del__(self):
+        s = getattr(self, "_s", None)
+        if s is not None:
+            s.close()
+
+    def __bool__(self):
+        return self._s.ab is not None
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _set_outputs(self, out_cons, out_msa, max_n_cons, min_freq, use_qv):
+        if max_n_cons < 1 or max_n_cons > 2:
+            raise Exception("Error: max number of consensus sequences should be 1 or 2.")
+        a = self._s.abpt.contents
+        a.out_cons, a.out_msa = int(bool(out_cons)), int(bool(out_msa))
+        a.max_n_cons, a.min_freq = max_n_cons, min_freq
+        a.use_qv = int(use_qv)
+        self._s.lib.abpoa_post_set_para(self._s.abpt)
+
+    def _add_sequences(self, seqs, qscores, exist_n, tot_n):
+        """pyabpoa.pyx:176-209: align + fuse, read by read."""
+        if qscores is not None and len(qscores) != len(seqs):
+            raise ValueError("qscores must contain one entry per input sequence.")
+        s = self._s
+        for i, seq in enumerate(seqs):
+            codes = encode(seq, self.m)
+            weights = None
+            if qscores is not None:
+                if len(qscores[i]) != len(codes):
+                    raise ValueError("Each qscore array must have the same length as its sequence.")
+                weights = np.asarray([int(q) for q in qscores[i]], dtype=np.int32)
+                if (weights < 0).any():
+                    raise ValueError("Qscores must be non-negative integers.")
+            _, res = s.align(codes, count_cells=False)
+            wp = weights.ctypes.data_as(c_int_p) if weights is not None else None
+            s.lib.abpoa_add_graph_alignment(s.ab, s.abpt, codes.ctypes.data_as(c_u8_p), wp, len(codes), None, res, exist_n + i, tot_n, 1)
+            if res.n_cigar > 0:
+                capi.libc_free(res.graph_cigar)
+
+    def _result(self, tot_n):
+        s = self._s
+        a = s.abpt.contents
+        if a.out_msa:
+            s.lib.abpoa_generate_rc_msa(s.ab, s.abpt)
+        elif a.out_cons:
+            s.lib.abpoa_generate_consensus(s.ab, s.abpt)
+        abc = s.ab.contents.abc.contents
+        n_cons = abc.n_cons
+        cons = s.consensus()
+        covs = s.consensus_cov()
+        clu_n = [abc.clu_n_seq[i] for i in range(n_cons)]
+        clu_ids = [[abc.clu_read_ids[i][j] for j in range(clu_n[i])] for i in range(n_cons)]
+        qv = ["".join(chr(abc.cons_phred_score[i][j]) for j in range(abc.cons_len[i])) if abc.cons_phred_score else "" for i in range(n_cons)]
+        rows = s.msa_rows()
+        return msa_result(tot_n, n_cons, clu_n, clu_ids, [len(c) for c in cons], [decode(c, self.m) for c in cons],
+                          [list(map(int, c)) for c in covs], qv, int(abc.msa_len), [decode(r, self.m) for r in rows])
+
+    # ---- pyabpoa methods -------------------------------------------------------------------------
+    def msa_align(self, seqs, out_cons, out_msa, max_n_cons=1, min_freq=0.25, incr_fn=b"", qscores=None):
+        if incr_fn:
+            raise NotImplementedError("restoring a graph from a GFA / MSA file is outside the hot-path scope")
+        self._set_outputs(out_cons, out_msa, max_n_cons, min_freq, qscores is not None)
+        s = self._s
+        s.lib.abpoa_reset(s.ab, s.abpt, len(seqs[0]))
+        abs_ = s.ab.contents.abs.contents
+        abs_.n_seq += len(seqs)
+        self._add_sequences(seqs, qscores, 0, len(seqs))
+        return self
+
+    def msa_add(self, new_seqs, qscores=None):
+        if isinstance(new_seqs, str):
+            raise TypeError('Expected a list of strings. If you want to add a single sequence, pass it as a list: ["ACGT..."]')
+        s = self._s
+        abs_ = s.ab.contents.abs.contents
+        exist_n = abs_.n_seq
+        if exist_n == 0:
+            raise Exception("Error: no existing sequences in the graph. Please run msa() or msa_align() first.")
+        abs_.n_seq += len(new_seqs)
+        if qscores is not None:
+            s.abpt.contents.use_qv = 1
+        self._add_sequences(new_seqs, qscores, exist_n, exist_n + len(new_seqs))
+        return self
+
+    def msa_output(self):
+        return self._result(self._s.ab.contents.abs.contents.n_seq)
+
+    def msa(self, seqs, out_cons, out_msa, max_n_cons=1, min_freq=0.25, out_pog=b"", incr_fn=b"", qscores=None):
+        if out_pog:
+            raise NotImplementedError("graph plotting is outside the hot-path scope")
+        self.msa_align(seqs, out_cons, out_msa, max_n_cons, min_freq, incr_fn, qscores)
+        return self._result(len(seqs))

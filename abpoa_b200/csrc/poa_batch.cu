@@ -45,6 +45,14 @@ struct abpoa_gpu_batch {
     std::vector<poa_dev_ctx *> ctx;
     double wall_ms;
     PoaChainStats chain;            /* device-resident chain engine (poa_chain.cu) */
+    struct PoaEmit *emit;           /* abpoa_gpu_msa_batch_write in progress: per-group output text */
+};
+
+/* per-group text of abpoa_output(), collected while a batch runs and written in group order afterwards */
+struct PoaEmit {
+    const char *const *const *names;          /* [n_groups][n_seq] or NULL */
+    std::vector<char *> buf; std::vector<size_t> len;
+    const int *map;                           /* engine-local group index -> caller's group index (fallback sub-batches) */
 };
 
 extern "C" int abpoa_gpu_device_count(void) {
@@ -92,7 +100,7 @@ extern "C" abpoa_gpu_batch_t *abpoa_gpu_batch_init(int device, int n_workers, in
         poa_dev_ctx_use_arena(c, e->arena);
         e->ctx.push_back(c);
     }
-    e->wall_ms = 0; memset(&e->chain, 0, sizeof e->chain);
+    e->wall_ms = 0; memset(&e->chain, 0, sizeof e->chain); e->emit = NULL;
     return e;
 }
 
@@ -185,6 +193,7 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
     out->cells += e->chain.cells; out->alignments += e->chain.alignments; out->launches += e->chain.launches;
     out->h2d_bytes += e->chain.h2d_bytes; out->d2h_bytes += e->chain.d2h_bytes; out->kernel_ms += e->chain.device_ms;
     out->chain_device_ms = e->chain.device_ms; out->chain_cells = e->chain.cells; out->chain_groups = e->chain.groups_done; out->chain_fallback_groups = e->chain.groups_failed;
+    out->chain_dp_ms = e->chain.dp_ms; out->chain_fuse_ms = e->chain.fuse_ms; out->chain_dp_launches = e->chain.dp_launches;
 }
 
 extern "C" void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *e) {
@@ -208,10 +217,22 @@ extern "C" { extern __thread double poa_prof_ms[8]; }
 /* Consensus / MSA of a finished group (reference abpoa_output, src/abpoa_align.c:354-370, with out_fp = NULL)
  * copied into the caller's result record.  Consensus, MSA and the public index arrays use the reference's
  * Kahn order, whatever order the alignments ran in. */
-void poa_finish_group_result(abpoa_t *ab, abpoa_para_t *abpt, abpoa_gpu_group_result_t *o) {
+void poa_finish_group_result(abpoa_t *ab, abpoa_para_t *abpt, abpoa_gpu_group_result_t *o, struct PoaEmit *emit, int gidx) {
     poa_graph_set_fast_order(ab->abg, 0);
     if (ab->abg->node_n > 2) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
-    abpoa_output(ab, abpt, NULL);
+    if (emit) {
+        const int g = emit->map ? emit->map[gidx] : gidx;
+        abpoa_seq_t *abs = ab->abs;
+        if (emit->names && emit->names[g]) for (int i = 0; i < abs->n_seq; ++i) { const char *nm = emit->names[g][i]; poa_str_assign(&abs->name[i], nm ? nm : "", nm ? (int)strlen(nm) : 0); }
+        abpoa_para_t local = *abpt;               /* the header of a list-mode consensus carries the group number (reference src/abpoa.c:154-159) */
+        local.batch_index = g + 1;
+        char *text = NULL; size_t tl = 0;
+        FILE *mf = open_memstream(&text, &tl);
+        if (!mf) poa_die(__func__, "open_memstream failed");
+        abpoa_output(ab, &local, mf);
+        fclose(mf);
+        emit->buf[g] = text; emit->len[g] = tl;
+    } else abpoa_output(ab, abpt, NULL);
     const abpoa_cons_t *abc = ab->abc;
     if (abpt->out_cons && abc->n_cons > 0) {
         o->n_cons = abc->n_cons;
@@ -325,7 +346,7 @@ void sink_to_res(void *user, poa_job *j) {
     pd->have = true;
 }
 
-void finish_group(GroupState &gs, abpoa_para_t *abpt) { poa_finish_group_result(gs.ab, abpt, gs.out); }
+void finish_group(GroupState &gs, abpoa_para_t *abpt, abpoa_gpu_batch *eng, int gidx) { poa_finish_group_result(gs.ab, abpt, gs.out, eng->emit, gidx); }
 
 struct PhaseClock {
     double plan = 0, run = 0, fuse = 0, finish = 0, setup = 0;
@@ -462,7 +483,7 @@ void worker_main(Worker wk) {
         }
         pc.tic();
         for (int t = 0; t < ng; ++t) {
-            finish_group(gs[t], abpt);
+            finish_group(gs[t], abpt, wk.eng, g0 + t);
             for (int i = 0; i < gs[t].in->n_seq; ++i) free(gs[t].weights[i]);
             free(gs[t].weights);
         }
@@ -632,7 +653,7 @@ void worker_pipelined(Worker wk) {
             pc.tic();
             if (h.fused_rounds < h.max_reads) half_finish_round(h, wk, h.max_reads - 1, &sc);
             for (int t = 0; t < h.ng; ++t) {
-                finish_group(h.gs[t], abpt);
+                finish_group(h.gs[t], abpt, wk.eng, h.g0 + t);
                 for (int i = 0; i < h.gs[t].in->n_seq; ++i) free(h.gs[t].weights[i]);
                 free(h.gs[t].weights);
             }
@@ -665,12 +686,17 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     if (!(flags & (ABPOA_GPU_CAPTURE_JOBS | ABPOA_GPU_NO_CHAIN)) && poa_chain_eligible(abpt)) {
         std::vector<int> todo((size_t)n_groups), rest;
         for (int g = 0; g < n_groups; ++g) todo[g] = g;
-        poa_chain_run(e->dev, e->arena, abpt, e->n_workers, groups, results, todo, flags, rest, &e->chain);
+        poa_chain_run(e->dev, e->arena, abpt, e->n_workers, groups, results, todo, flags, rest, &e->chain, e->emit);
         if (!rest.empty()) {
             std::sort(rest.begin(), rest.end());
             std::vector<abpoa_gpu_group_t> sub(rest.size()); std::vector<abpoa_gpu_group_result_t> subres(rest.size());
             for (size_t k = 0; k < rest.size(); ++k) sub[k] = groups[rest[k]];
+            const int *outer_map = e->emit ? e->emit->map : NULL;
+            std::vector<int> map2(rest.size());
+            for (size_t k = 0; k < rest.size(); ++k) map2[k] = outer_map ? outer_map[rest[k]] : rest[k];
+            if (e->emit) e->emit->map = map2.data();
             abpoa_gpu_msa_batch(e, abpt, (int)rest.size(), sub.data(), subres.data(), flags | ABPOA_GPU_NO_CHAIN);
+            if (e->emit) e->emit->map = outer_map;
             for (size_t k = 0; k < rest.size(); ++k) results[rest[k]] = subres[k];
         }
         e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -693,5 +719,23 @@ extern "C" int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int
     }
     for (auto &t : th) t.join();
     e->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+/* abpoa_gpu_msa_batch + the text the reference CLI prints per group in list mode (src/abpoa.c:148-168: one
+ * abpoa_msa1 per file with abpt->batch_index = file number), written to out_fp in group order. */
+extern "C" int abpoa_gpu_msa_batch_write(abpoa_gpu_batch_t *e, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
+                                         const char *const *const *names, FILE *out_fp, abpoa_gpu_group_result_t *results, int flags) {
+    if (n_groups <= 0) return 0;
+    PoaEmit em; em.names = names; em.buf.assign((size_t)n_groups, (char *)NULL); em.len.assign((size_t)n_groups, 0); em.map = NULL;
+    std::vector<abpoa_gpu_group_result_t> tmp;
+    if (!results) { tmp.resize((size_t)n_groups); results = tmp.data(); }
+    e->emit = &em;
+    abpoa_gpu_msa_batch(e, abpt, n_groups, groups, results, flags);
+    e->emit = NULL;
+    for (int g = 0; g < n_groups; ++g) {
+        if (em.buf[g]) { if (out_fp) fwrite(em.buf[g], 1, em.len[g], out_fp); free(em.buf[g]); }
+        if (!tmp.empty()) abpoa_gpu_group_result_free(&results[g]);
+    }
     return 0;
 }

@@ -113,6 +113,7 @@ struct Cohort {
     std::vector<int> members;               /* indices into the wave's plan list */
     cudaStream_t st = NULL;
     cudaEvent_t ev_begin = NULL, ev_end = NULL;
+    std::vector<cudaEvent_t> marks;         /* per round: before DP, between DP and fuse, after fuse */
 };
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -122,7 +123,8 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 /* Run the groups listed in `todo` (eligible ones) through the device chain.  Groups that could not be
  * finished are appended to `fallback`.  Returns 0. */
 int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, const abpoa_gpu_group_t *groups,
-                  abpoa_gpu_group_result_t *results, const std::vector<int> &todo, int flags, std::vector<int> &fallback, PoaChainStats *stats) {
+                  abpoa_gpu_group_result_t *results, const std::vector<int> &todo, int flags, std::vector<int> &fallback, PoaChainStats *stats,
+                  struct PoaEmit *emit) {
     CK(cudaSetDevice(dev));
     const bool record = (flags & ABPOA_GPU_RECORD_READS) != 0;
     const bool verbose = getenv("ABPOA_GPU_PROFILE") != NULL;
@@ -318,9 +320,14 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             for (int r = 1; r < max_reads; ++r) {
                 const std::pair<size_t, int> &ro = round_of[c][(size_t)r - 1];
                 if (ro.second == 0) break;
+                cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+                coh[c].marks.push_back(e0); coh[c].marks.push_back(e1); coh[c].marks.push_back(e2);
+                CK(cudaEventRecord(e0, st));
                 CK(poa_launch_chain_align_p16(abpt->gap_mode, d_slots, d_idx + ro.first, ro.second, r, d_prm, ring_rows, ring_cells, st));
+                CK(cudaEventRecord(e1, st));
                 poa_chain_fuse_kernel<<<ro.second, POA_CHAIN_T, 0, st>>>(d_slots, d_idx + ro.first, d_cp, ro.second);
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(e2, st));
                 launches += 2;
             }
             CK(cudaEventRecord(coh[c].ev_end, st));
@@ -336,6 +343,16 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         CK(cudaMemcpyAsync(h_fin, d_slots, (size_t)nw * sizeof(PoaChainSlot), cudaMemcpyDeviceToHost, s0));
         CK(cudaStreamSynchronize(s0));
         float dev_ms = 0.f; CK(cudaEventElapsedTime(&dev_ms, ev_t0, ev_t1));
+        double dp_ms = 0, fuse_ms = 0; int64_t n_marks = 0;
+        for (Cohort &c : coh) {
+            for (size_t k = 0; k + 2 < c.marks.size(); k += 3) {
+                float a = 0.f, b = 0.f;
+                CK(cudaEventElapsedTime(&a, c.marks[k], c.marks[k + 1])); CK(cudaEventElapsedTime(&b, c.marks[k + 1], c.marks[k + 2]));
+                dp_ms += a; fuse_ms += b; ++n_marks;
+            }
+            for (cudaEvent_t ev : c.marks) cudaEventDestroy(ev);
+            c.marks.clear();
+        }
         memcpy(fin.data(), h_fin, (size_t)nw * sizeof(PoaChainSlot));
         CK(cudaFreeHost(h_fin));
         const double t_dev_done = now_ms();
@@ -396,7 +413,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                     abs->n_seq = p.n_reads; poa_seq_reserve(abs);
                     for (int i = 0; i < p.n_reads; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
                     poa_graph_import(ab, abpt, h_ex + hoff2[t]);
-                    poa_finish_group_result(ab, abpt, o);
+                    poa_finish_group_result(ab, abpt, o, emit, p.g);
                     o->dp_cells = fin[t].cells; o->n_aligned = p.n_reads - 1;
                     if (record) {
                         const int nr = p.n_reads;
@@ -417,8 +434,10 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         if (stats) {
             stats->device_ms += dev_ms; stats->cells += cells; stats->alignments += alns; stats->launches += launches;
             stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; stats->groups_done += nw - n_failed.load(); stats->groups_failed += n_failed.load();
+            stats->dp_ms += dp_ms; stats->fuse_ms += fuse_ms; stats->dp_launches += n_marks; stats->fuse_launches += n_marks;
         }
         if (verbose)
+            fprintf(stderr, "[chain] DP kernels %.1f ms + fuse kernels %.1f ms summed over %zu concurrent cohort streams (%lld rounds)\n", dp_ms, fuse_ms, coh.size(), (long long)n_marks),
             fprintf(stderr, "[chain] wave of %d groups (%zu cohorts, K=%d): stage+launch+device %.0f ms (device %.1f ms), export copy %.0f ms, import+consensus %.0f ms; "
                             "static %.2f GB, pool %.2f GB, export %.1f MB; %d groups handed to the launch engine\n",
                     nw, coh.size(), K, t_dev_done - t_wave0, dev_ms, t_copied - t_dev_done, now_ms() - t_copied,

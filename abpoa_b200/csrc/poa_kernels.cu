@@ -824,7 +824,11 @@ __device__ __forceinline__ P16Smem p16_smem_init(uint8_t *dyn_smem, const PoaPar
 
 /* One alignment job on one warp: forward DP + backtrace.  Writes *jd.result (every status) but does
  * NOT publish completion -- the caller does (signal_done), after whatever it still has to move. */
-template <int GAP, int MODE>
+/* LEAN (whole-graph jobs without -G path scores): rows with one or two predecessors that are still in the
+ * shared-memory ring -- practically every row -- take a straight-line path: every lane reads the predecessors'
+ * ring records itself (uniform-address shared loads) instead of lane k owning predecessor k and publishing it
+ * through reductions and shuffles, and the predecessor planes are folded in without a loop. */
+template <int GAP, int MODE, bool LEAN = false>
 __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParamsDev *__restrict__ prm, const P16Smem &sm,
                                             int ring_rows, int ring_cells, int lane) {
     typedef int16_t ST;
@@ -926,13 +930,15 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     const int pn_shift = pnv == 16 ? 4 : 3;
     const uint32_t cap32 = jd.plane_cap_units > 0xffffffffull ? 0xffffffffu : (uint32_t)jd.plane_cap_units;
     uint32_t cur32 = (uint32_t)cursor;
-    const bool has_ps = jv.predscore != nullptr;
+    const bool has_ps = LEAN ? false : (jv.predscore != nullptr);
 
     int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
     if (n_rows > 2) {
         { const int2 m1 = ldb(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
         if (lane < pe - pb) { mypred = ldb(jv.pred + pb + lane); if (has_ps) myps = ldb(jv.predscore + pb + lane); }
     }
+    int p0 = -1, p1 = -1;                                 /* LEAN: the row's first two predecessors, known to every lane */
+    if (LEAN) { p0 = __shfl_sync(FULL, mypred, 0); p1 = __shfl_sync(FULL, mypred, 1); }
     int nx_y = n_rows > 3 ? ldb(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     KP_DECL
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
@@ -943,13 +949,27 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y;
             if (lane < n_pe - pe) { n_mypred = ldb(jv.pred + pe + lane); if (has_ps) n_myps = ldb(jv.predscore + pe + lane); }
         }
+        int n_p0 = -1, n_p1 = -1;
+        if (LEAN) { n_p0 = __shfl_sync(FULL, n_mypred, 0); n_p1 = __shfl_sync(FULL, n_mypred, 1); }   /* consumed one row later: off the chain */
         const int np = pe - pb;
-        if (!(jv.live && !ldb(jv.live + i))) {
+        if (LEAN || !(jv.live && !ldb(jv.live + i))) {
 
+        /* ---- LEAN fast row: <= 2 predecessors, all in the ring, their whole bands cached there ---- */
+        bool lean_row = false;
+        uint4 lm0 = make_uint4(0u, 0u, 0u, 0u), lm1 = lm0;
+        if (LEAN) {
+            lean_row = np >= 1 && np <= 2 && (i - p0) <= rmask && (np < 2 || (i - p1) <= rmask);
+            if (lean_row) {
+                lm0 = ring_meta[p0 & rmask];
+                lm1 = np == 2 ? ring_meta[p1 & rmask] : lm0;
+                const int png0 = (int)(lm0.y >> 3) - (int)(lm0.x >> 3) + 1, png1 = (int)(lm1.y >> 3) - (int)(lm1.x >> 3) + 1;
+                if (png0 > ring_groups || png1 > ring_groups) lean_row = false;      /* a row wider than its ring slot: only a prefix is cached */
+            }
+        }
         /* ---- predecessor k on lane k: band hints + the two broadcast words ---- */
         unsigned wA = 0, wB = 0;                      /* A: pg0 | png<<12 | near<<25 | slot<<26 ; B: plane offset (8-cell units) */
         int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
-        if (lane < np) {
+        if (!lean_row && lane < np) {
             const int prow = mypred;
             const bool near = (i - prow) <= rmask;
             uint4 mi;
@@ -961,7 +981,11 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             wB = mi.w;
         }
         int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
-        if (banded) {
+        if (lean_row) {
+            ml = min(ml, (int)min(lm0.z & 0xffffu, lm1.z & 0xffffu));
+            mr = max(mr, (int)max(lm0.z >> 16, lm1.z >> 16));
+            min_pre_beg = (int)min(lm0.x, lm1.x);
+        } else if (banded) {
             ml = min(ml, __reduce_min_sync(FULL, l1));
             mr = max(mr, __reduce_max_sync(FULL, r1));
             min_pre_beg = __reduce_min_sync(FULL, b1);
@@ -1010,6 +1034,48 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
              * cell is inside the band, i.e. on later passes or when the band starts on a group boundary */
             const bool fix_left = (gp > g0) || ((beg & 7) == 0);
 
+            if (lean_row) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k == 1 && np < 2) break;
+                    const uint4 mi = k == 0 ? lm0 : lm1;
+                    const int pg0 = (int)(mi.x >> 3), png = (int)(mi.y >> 3) - pg0 + 1;
+                    const int rel = g - pg0;
+                    const bool inr = active && (unsigned)rel < (unsigned)png;
+                    const uint32_t prs = ring_s + (uint32_t)((k == 0 ? p0 : p1) & rmask) * ring_row_bytes;
+                    uint4 hp = make_uint4(NEGP2, NEGP2, NEGP2, NEGP2), ep1 = hp, ep2 = hp;
+                    if (inr) {
+                        const uint32_t a = prs + (uint32_t)rel * 16u;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hp.x), "=r"(hp.y), "=r"(hp.z), "=r"(hp.w) : "r"(a));
+                        if (GAP != LG) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ep1.x), "=r"(ep1.y), "=r"(ep1.z), "=r"(ep1.w) : "r"(a + ring_plane_bytes));
+                        if (GAP == CG) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ep2.x), "=r"(ep2.y), "=r"(ep2.z), "=r"(ep2.w) : "r"(a + 2 * ring_plane_bytes));
+                    }
+                    unsigned prev = __shfl_up_sync(FULL, hp.w, 1);
+                    if (fix_left) {                          /* uniform: the cell left of lane 0's group is inside the band */
+                        if (lane == 0) {
+                            int hm1 = NEGP;
+                            const int relm = rel - 1;
+                            if ((unsigned)relm < (unsigned)png) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(prs + (uint32_t)relm * 16u + 14u)); hm1 = (int)(short)v; }
+                            if (MODE == LOCAL && g == 0) hm1 = 0;
+                            prev = (unsigned)hm1 << 16;
+                        }
+                    } else if (lane == 0) prev = (MODE == LOCAL && g == 0) ? 0u : ((unsigned)NEGP << 16);
+                    const unsigned d0 = sh1(prev, hp.x), d1 = sh1(hp.x, hp.y), d2 = sh1(hp.y, hp.z), d3 = sh1(hp.z, hp.w);
+                    if (GAP == LG) {
+                        hp.x = __viaddmax_s16x2(hp.x, NE1, NEGP2); hp.y = __viaddmax_s16x2(hp.y, NE1, NEGP2); hp.z = __viaddmax_s16x2(hp.z, NE1, NEGP2); hp.w = __viaddmax_s16x2(hp.w, NE1, NEGP2);
+                    }
+                    const uint4 x1 = GAP == LG ? hp : ep1;
+                    if (k == 0) {
+                        M[0] = d0; M[1] = d1; M[2] = d2; M[3] = d3;
+                        X1[0] = x1.x; X1[1] = x1.y; X1[2] = x1.z; X1[3] = x1.w;
+                        if (GAP == CG) { X2[0] = ep2.x; X2[1] = ep2.y; X2[2] = ep2.z; X2[3] = ep2.w; }
+                    } else {
+                        M[0] = __vmaxs2(M[0], d0); M[1] = __vmaxs2(M[1], d1); M[2] = __vmaxs2(M[2], d2); M[3] = __vmaxs2(M[3], d3);
+                        X1[0] = __vmaxs2(X1[0], x1.x); X1[1] = __vmaxs2(X1[1], x1.y); X1[2] = __vmaxs2(X1[2], x1.z); X1[3] = __vmaxs2(X1[3], x1.w);
+                        if (GAP == CG) { X2[0] = __vmaxs2(X2[0], ep2.x); X2[1] = __vmaxs2(X2[1], ep2.y); X2[2] = __vmaxs2(X2[2], ep2.z); X2[3] = __vmaxs2(X2[3], ep2.w); }
+                    }
+                }
+            } else
             for (int kb = 0; kb < np; kb += 32) {
                 unsigned cA = wA, cB = wB; int c_ps = myps;
                 if (kb > 0) {
@@ -1214,6 +1280,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         __syncwarp();
         }   /* live row */
         pb = pe; pe = n_pe; rbase = n_rbase; rem = n_rem; mypred = n_mypred; myps = n_myps;
+        if (LEAN) { p0 = n_p0; p1 = n_p1; }
     }
     cursor = cur32;
     KP_OUT(res)
@@ -1258,7 +1325,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 #else
 #define POA_P16_BOUNDS __launch_bounds__(32)
 #endif
-template <int GAP, int MODE>
+template <int GAP, int MODE, bool LEAN>
 __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
                                                            int n_jobs, int ring_rows, int ring_cells) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -1267,7 +1334,7 @@ __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict
     if (job >= n_jobs) return;
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
     const PoaJobDesc jd = jobs[job];
-    p16_run_job<GAP, MODE>(jd, prm, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, MODE, LEAN>(jd, prm, sm, ring_rows, ring_cells, lane);
     __syncwarp();
     if (lane == 0) signal_done(jd);
 }
@@ -1291,7 +1358,7 @@ __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__
     const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
     if (sl->failed || sl->fused != round || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
-    p16_run_job<GAP, GLOBAL>(jd, prm, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, GLOBAL, true>(jd, prm, sm, ring_rows, ring_cells, lane);
 }
 
 template <int GAP>
@@ -1320,14 +1387,10 @@ static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_
 template <int GAP, typename ST, int MODE>
 static cudaError_t launch_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
     const size_t smem = ring_smem_bytes(GAP, (int)sizeof(ST) * 8, ring_rows, ring_cells);
-    static size_t configured = 0;                         /* per instantiation */
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-        if (e != cudaSuccess) return e;
-        const char *cv = getenv("ABPOA_GPU_CARVEOUT");
-        if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-        configured = 227 * 1024;
-    }
+    cudaError_t e = cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    const char *cv = getenv("ABPOA_GPU_CARVEOUT");
+    if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel<GAP, ST, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
     poa_align_kernel<GAP, ST, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
     return cudaGetLastError();
 }
@@ -1352,35 +1415,36 @@ extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t sme
     *ring_rows = rr; *ring_cells = rc;
 }
 
-template <int GAP, int MODE>
+template <int GAP, int MODE, bool LEAN>
 static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
     const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-        if (e != cudaSuccess) return e;
-        const char *cv = getenv("ABPOA_GPU_CARVEOUT");          /* shared-memory share of the L1/shared array, percent */
-        if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-        configured = 227 * 1024;
-    }
-    poa_align_kernel_p16<GAP, MODE><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
+    /* per device and instantiation; cudaFuncSetAttribute is cheap and idempotent, so no process-wide cache (a second
+     * GPU in the same process needs its own call) */
+    cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    const char *cv = getenv("ABPOA_GPU_CARVEOUT");          /* shared-memory share of the L1/shared array, percent */
+    if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+    poa_align_kernel_p16<GAP, MODE, LEAN><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
     return cudaGetLastError();
 }
 template <int GAP>
-static cudaError_t launch_p16_mode(int mode, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, cudaStream_t st) {
+static cudaError_t launch_p16_mode(int mode, int lean, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, cudaStream_t st) {
     switch (mode) {
-    case GLOBAL: return launch_p16_one<GAP, GLOBAL>(jobs, prm, n_jobs, rr, rc, st);
-    case LOCAL:  return launch_p16_one<GAP, LOCAL>(jobs, prm, n_jobs, rr, rc, st);
-    default:     return launch_p16_one<GAP, EXTEND>(jobs, prm, n_jobs, rr, rc, st);
+    case GLOBAL: return lean ? launch_p16_one<GAP, GLOBAL, true>(jobs, prm, n_jobs, rr, rc, st) : launch_p16_one<GAP, GLOBAL, false>(jobs, prm, n_jobs, rr, rc, st);
+    case LOCAL:  return launch_p16_one<GAP, LOCAL, false>(jobs, prm, n_jobs, rr, rc, st);
+    default:     return launch_p16_one<GAP, EXTEND, false>(jobs, prm, n_jobs, rr, rc, st);
     }
 }
-/* bits == 15 selects the packed int16x2 kernel (int16 planes, DPX pair arithmetic) */
-extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, const PoaJobDesc *jobs,
+/* the packed int16x2 kernel (int16 planes, DPX pair arithmetic).  lean != 0: every job aligns to the whole graph and
+ * carries no -G path scores (the straight-line predecessor path of p16_run_job may be used; global mode only) */
+extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, int lean, const PoaJobDesc *jobs,
                                             const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
-    if (gap_mode == LG) return launch_p16_mode<LG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
-    if (gap_mode == AG) return launch_p16_mode<AG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
-    return launch_p16_mode<CG>(align_mode, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    static const int no_lean = [] { const char *e = getenv("ABPOA_GPU_NO_LEAN"); return e && *e == '1'; }();
+    if (no_lean) lean = 0;
+    if (gap_mode == LG) return launch_p16_mode<LG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    if (gap_mode == AG) return launch_p16_mode<AG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    return launch_p16_mode<CG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
 }
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,

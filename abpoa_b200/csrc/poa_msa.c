@@ -93,11 +93,38 @@ int abpoa_msa(abpoa_t *ab, abpoa_para_t *abpt, int n_seq, char **seq_names, int 
     return 0;
 }
 
-/* ---- entry points kept for link compatibility; their subsystems (file IO, GFA restore,
- *      sub-graph windows for seeding) are outside the hot-path scope ---- */
+/* One MSA from a FASTA/FASTQ file (reference abpoa_msa1, src/abpoa_align.c:473-539): read, encode with the
+ * alphabet table chosen by abpoa_post_set_para, quality weights = phred + 1 when -Q, progressive POA, output. */
+extern char ab_char26_table[256];
 int abpoa_msa1(abpoa_t *ab, abpoa_para_t *abpt, char *read_fn, FILE *out_fp) {
-    (void)ab; (void)abpt; (void)read_fn; (void)out_fp;
-    poa_die(__func__, "FASTA/FASTQ file input is outside the scope of the B200 hot-path library; encode reads and call abpoa_msa().");
+    if (!abpt->out_msa && !abpt->out_cons && !abpt->out_gfa) return 0;
+    if (abpt->sort_input_seq) poa_die(__func__, "sorting the input by length (-L) is outside the scope of the B200 hot-path library.");
+    abpoa_reset(ab, abpt, 1024);
+    if (abpt->incr_fn) abpoa_restore_graph(ab, abpt);
+    abpoa_seq_t *abs = ab->abs;
+    const int exist_n_seq = abs->n_seq;
+    const int n_seq = poa_read_fastx(read_fn, abs);
+    if (n_seq < 0) poa_die(__func__, "fail to open file \'%s\'", read_fn);
+    if (n_seq == 0) return 0;
+    uint8_t **seqs = (uint8_t **)poa_xmalloc((size_t)n_seq * sizeof(uint8_t *));
+    int *lens = (int *)poa_xmalloc((size_t)n_seq * sizeof(int)), **weights = (int **)poa_xmalloc((size_t)n_seq * sizeof(int *));
+    char **names = (char **)poa_xmalloc((size_t)n_seq * sizeof(char *));
+    for (int i = 0; i < n_seq; ++i) {
+        const abpoa_str_t *sq = &abs->seq[exist_n_seq + i], *ql = &abs->qual[exist_n_seq + i];
+        lens[i] = sq->l;
+        seqs[i] = (uint8_t *)poa_xmalloc((size_t)POA_MAX(sq->l, 1));
+        weights[i] = (int *)poa_xmalloc((size_t)POA_MAX(sq->l, 1) * sizeof(int));
+        for (int j = 0; j < sq->l; ++j) seqs[i][j] = (uint8_t)ab_char26_table[(int)(unsigned char)sq->s[j]];
+        const int use_q = abpt->use_qv && ql->l > 0;
+        for (int j = 0; j < sq->l; ++j) weights[i][j] = use_q ? (int)ql->s[j] - 32 : 1;
+        names[i] = abs->name[exist_n_seq + i].l > 0 ? strdup(abs->name[exist_n_seq + i].s) : strdup("");
+    }
+    /* abpoa_msa appends to abs itself: hand the records over instead of keeping them twice */
+    abs->n_seq = exist_n_seq;
+    abpoa_msa(ab, abpt, n_seq, names, lens, seqs, abpt->use_qv ? weights : NULL, out_fp);
+    for (int i = 0; i < n_seq; ++i) { free(seqs[i]); free(weights[i]); free(names[i]); }
+    free(seqs); free(weights); free(lens); free(names);
+    return 0;
 }
 abpoa_t *abpoa_restore_graph(abpoa_t *ab, abpoa_para_t *abpt) {
     (void)ab; (void)abpt;

@@ -311,17 +311,20 @@ def main():
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
-    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-    c = torch.tensor([float(cells), float(packed.total_reads * args.steps), float(st["launches"]), float(st["h2d_bytes"]), float(st["d2h_bytes"])],
+    t = torch.tensor([elapsed, st["chain_device_ms"]], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(cells), float(packed.total_reads * args.steps), float(st["launches"]), float(st["h2d_bytes"]), float(st["d2h_bytes"]),
+                      float(st["chain_cells"]), float(st["chain_groups"]), float(st["chain_fallback_groups"]), st["chain_dp_ms"], st["chain_fuse_ms"]],
                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    elapsed = float(t.item())
-    tot_cells, tot_reads, launches, h2d, d2h = [float(x) for x in c.tolist()]
+    elapsed, chain_ms = [float(x) for x in t.tolist()]
+    tot_cells, tot_reads, launches, h2d, d2h, chain_cells, chain_groups, chain_fallback, chain_dp_ms, chain_fuse_ms = [float(x) for x in c.tolist()]
     e2e_gcups = tot_cells / elapsed / 1e9
+    used_chain = chain_groups > 0 and chain_ms > 0
 
-    # device-resident pass: capture one step's jobs, upload once, replay with CUDA-event timing
+    # device-resident measurement of the DP + backtrace kernel ALONE: capture one step's alignment jobs through the launch
+    # engine, upload once, replay back to back with CUDA-event timing (per-launch numbers for the roofline)
     eng.run_packed(abpt, packed, keep_results=False, capture=True)
     barrier()
     rp = eng.replay(abpt, warmup=1, repeats=max(args.steps, 2))
@@ -332,7 +335,19 @@ def main():
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
         dist.all_reduce(kc, op=dist.ReduceOp.SUM)
     kernel_s = float(kt.item()) / 1e3
-    value = float(kc.item()) / kernel_s / 1e9
+    kernel_only_gcups = float(kc.item()) / kernel_s / 1e9
+    # `value`: whole-job throughput with the inputs resident in HBM when the timed region starts.  With the chain engine that
+    # is the complete progressive MSA on the device (every alignment AND every graph fusion, chain dependencies included),
+    # CUDA events from "reads uploaded" to "last group fused", max over ranks.  Workloads outside the chain's scope (local
+    # mode) keep the replay of all captured alignment jobs.
+    value = chain_cells / (chain_ms / 1e3) / 1e9 if used_chain else kernel_only_gcups
+
+    # parity sample: consensus of the first groups of rank 0 against the reference's (computed in the cpu_baseline leg)
+    sample_cons = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        k = min(n_groups, args.ref_groups or len([c_ for v in socket_cpus().values() for c_ in v]))
+        sub = PackedGroups(groups[:k])
+        sample_cons = [bytes(r.cons[0]) if r.cons else b"" for r in eng.run_packed(abpt, sub, keep_results=True)]
 
     if rank != 0:
         eng.close()
@@ -340,7 +355,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (poa_align_kernel): algorithmic bytes per cell = S * (P + R * d)
+    # roofline of the dominant kernel (the DP + backtrace kernel): algorithmic bytes per cell = S * (P + R * d), SURVEY 8d
     gap = {0: (1, 1), 1: (3, 2), 2: (5, 3)}[2 if (w.cfg.gap_open1 and w.cfg.gap_open2) else (1 if w.cfg.gap_open1 else 0)]
     P, R = gap
     d = rp["preds"] / max(rp["rows"], 1)
@@ -354,33 +369,56 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
-    traffic, traffic_note = None, None
-    tf = ROOT / "profiles" / "r01_ncu_traffic.json"
-    if tf.exists():
-        t_ = json.loads(tf.read_text())
-        traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
-        traffic_note = (f"ncu capture of one replay launch ({t_['jobs']} jobs, {t_['duration_ms']:.1f} ms): "
-                        f"{t_['dram_bytes_write'] / 1e9:.1f} GB written + {t_['dram_bytes_read'] / 1e9:.1f} GB read; see {t_['source']}")
+    traffic, traffic_note, dram_frac = None, None, None
+    gapname = {1: "linear", 3: "affine", 5: "convex"}[P]
+    for cand in (ROOT / "profiles" / f"r02_ncu_traffic_{gapname}.json", ROOT / "profiles" / "r01_ncu_traffic.json"):
+        if cand.exists():
+            t_ = json.loads(cand.read_text())
+            if gapname not in t_.get("kernel", gapname) and "r01" not in cand.name:
+                continue
+            if cand.name.startswith("r01") and P != 5:
+                continue
+            traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
+            dram_frac = traffic / (t_["duration_ms"] / 1e3) / 1e9 / peak
+            traffic_note = (f"ncu capture of one replay launch ({t_['jobs']} jobs, {t_['duration_ms']:.1f} ms): "
+                            f"{t_['dram_bytes_write'] / 1e9:.1f} GB written + {t_['dram_bytes_read'] / 1e9:.1f} GB read; see {t_['source']}")
+            break
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                "kernel": "poa_align_kernel_p16", "bytes_per_cell": (bytes16 + bytes32) / max(rp["cells"], 1), "mean_in_degree": d,
+                "dram_frac_measured": dram_frac,
+                "kernel": "poa_align_kernel_p16 / poa_chain_align_kernel_p16 (same job function)", "bytes_per_cell": (bytes16 + bytes32) / max(rp["cells"], 1), "mean_in_degree": d,
                 "peak_source": peak_src, "launches_per_pass": rp["launches"], "replay_mismatches": rp["mismatches"],
-                "int16_cell_fraction": rp["cells16"] / max(rp["cells"], 1)}
+                "int16_cell_fraction": rp["cells16"] / max(rp["cells"], 1), "kernel_alone_gcups": kernel_only_gcups,
+                "timing": "CUDA events around back-to-back replay launches of all captured alignment jobs of one step (kernel alone on the device)"}
 
     cpu = None
+    parity = None
     if not args.no_cpu_baseline and world == 1:        # N=1 only (the contract); workers are pinned over ALL cores of the box
-        cpu, _ = cpu_baseline_block(args.workload, w, args.ref_groups, 1000)
+        cpu, ref_run = cpu_baseline_block(args.workload, w, args.ref_groups, 1000)
+        if sample_cons is not None:                    # rank 0's groups g = seed 1000 + g: the very groups the reference just ran
+            same = sum(1 for g, cb in enumerate(sample_cons) if ref_run["cons"].get(1000 + g) == cb)
+            parity = {"groups_compared": len(sample_cons), "consensus_identical": same,
+                      "what": "consensus of the first groups of the timed workload, product (this run) vs the unmodified reference (cpu_baseline leg)"}
 
+    chain = None
+    if used_chain:
+        chain = {"device_ms_per_step": chain_ms / args.steps, "groups_on_device": int(chain_groups / args.steps), "groups_handed_back": int(chain_fallback / args.steps),
+                 "dp_kernel_ms_sum_over_streams": chain_dp_ms / args.steps, "fuse_kernel_ms_sum_over_streams": chain_fuse_ms / args.steps,
+                 "dp_share_of_kernel_time": chain_dp_ms / max(chain_dp_ms + chain_fuse_ms, 1e-9)}
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16 (packed int16x2 DPX arithmetic; int32 kernel only as overflow fallback)", "data": "synthetic", "config": cfgdesc,
         "clocks": clocks, "reads_per_s": tot_reads / elapsed,
+        "value_definition": ("device-resident progressive MSA (chain engine): every alignment and every graph fusion of the step on the GPU, reads resident in HBM, CUDA events"
+                             if used_chain else "replay of all captured alignment jobs from HBM, CUDA events"),
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
-                "reads_per_s": tot_reads / elapsed, "host_threads_per_gpu": workers, "groups_per_launch": gpl or "auto",
-                "engine": "resident kernel (ABPOA_GPU_RESIDENT=1)" if os.environ.get("ABPOA_GPU_RESIDENT") == "1" else "pipelined launches, one per half-chunk round"},
+                "reads_per_s": tot_reads / elapsed, "per_gpu": e2e_gcups / world, "host_threads_per_gpu": workers,
+                "engine": "device-resident chain (align + fuse kernels per round, host only for upload / final consensus)" if used_chain
+                          else "launch engine: pipelined launches, one per half-chunk round, host graph fusion"},
         "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"]},
+        "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "chain": chain,
+        "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"],
+                        "gcups": kernel_only_gcups},
     }))
     eng.close()
     if world > 1:

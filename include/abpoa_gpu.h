@@ -62,6 +62,8 @@ typedef struct {
     /* device-resident chain engine: CUDA-event time from "reads resident in HBM" to "last group fused" (summed over
      * waves), the DP cells computed inside it, groups it finished / handed back to the launch engine */
     double chain_device_ms; int64_t chain_cells; int chain_groups, chain_fallback_groups;
+    /* per-launch CUDA-event times of its two kernels summed over rounds and over the concurrent cohort streams */
+    double chain_dp_ms, chain_fuse_ms; int64_t chain_dp_launches;
 } abpoa_gpu_stats_t;
 
 #define ABPOA_GPU_RECORD_READS 0x1
@@ -79,6 +81,13 @@ void abpoa_gpu_batch_free(abpoa_gpu_batch_t *eng);
 int abpoa_gpu_msa_batch(abpoa_gpu_batch_t *eng, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
                         abpoa_gpu_group_result_t *results, int flags);
 void abpoa_gpu_group_result_free(abpoa_gpu_group_result_t *r);
+
+/* The same, plus the text `abpoa -l` prints: for every group, in group order, what abpoa_output() writes
+ * (consensus FASTA / FASTQ or RC-MSA according to abpt, consensus headers numbered by group as the reference
+ * CLI does in list mode, src/abpoa.c:148-168).  names[g][i]: name of read i of group g (names or names[g]
+ * may be NULL: rows are called Seq_1 ...).  results may be NULL. */
+int abpoa_gpu_msa_batch_write(abpoa_gpu_batch_t *eng, abpoa_para_t *abpt, int n_groups, const abpoa_gpu_group_t *groups,
+                              const char *const *const *names, FILE *out_fp, abpoa_gpu_group_result_t *results, int flags);
 
 /* Device-resident measurement of the hot path: the jobs captured by the last
  * abpoa_gpu_msa_batch(..., ABPOA_GPU_CAPTURE_JOBS) call (flattened graphs + reads) are uploaded to
