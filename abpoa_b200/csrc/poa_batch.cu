@@ -192,6 +192,7 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
     /* groups that ran on the device chain */
     out->cells += e->chain.cells; out->alignments += e->chain.alignments; out->launches += e->chain.launches;
     out->h2d_bytes += e->chain.h2d_bytes; out->d2h_bytes += e->chain.d2h_bytes; out->kernel_ms += e->chain.device_ms;
+    out->fwd_clk += e->chain.fwd_clk; out->bt_clk += e->chain.bt_clk;
     out->chain_device_ms = e->chain.device_ms; out->chain_cells = e->chain.cells; out->chain_groups = e->chain.groups_done; out->chain_fallback_groups = e->chain.groups_failed;
     out->chain_dp_ms = e->chain.dp_ms; out->chain_fuse_ms = e->chain.fuse_ms; out->chain_dp_launches = e->chain.dp_launches;
 }

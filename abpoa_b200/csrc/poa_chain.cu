@@ -37,7 +37,7 @@
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     poa_die("libabpoa_b200/chain", "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 
-extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
+extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const int *gaps, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
                                                   const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st);
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
 
@@ -314,6 +314,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         int ring_rows = 2, ring_cells = 64;
         poa_pick_ring(abpt->gap_mode, 16, band_cells, smem_budget, &ring_rows, &ring_cells);
         int64_t launches = 1;
+        const int gaps[4] = { abpt->gap_ext1, abpt->gap_open1 + abpt->gap_ext1, abpt->gap_ext2, abpt->gap_open2 + abpt->gap_ext2 };
         for (size_t c = 0; c < coh.size(); ++c) {
             cudaStream_t st = coh[c].st;
             if (c > 0) CK(cudaStreamWaitEvent(st, ev_up, 0));
@@ -323,7 +324,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                 cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
                 coh[c].marks.push_back(e0); coh[c].marks.push_back(e1); coh[c].marks.push_back(e2);
                 CK(cudaEventRecord(e0, st));
-                CK(poa_launch_chain_align_p16(abpt->gap_mode, d_slots, d_idx + ro.first, ro.second, r, d_prm, ring_rows, ring_cells, st));
+                CK(poa_launch_chain_align_p16(abpt->gap_mode, gaps, d_slots, d_idx + ro.first, ro.second, r, d_prm, ring_rows, ring_cells, st));
                 CK(cudaEventRecord(e1, st));
                 poa_chain_fuse_kernel<<<ro.second, POA_CHAIN_T, 0, st>>>(d_slots, d_idx + ro.first, d_cp, ro.second);
                 CK(cudaGetLastError());
@@ -390,8 +391,8 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         /* ---- host: rebuild each graph, consensus ---- */
         std::atomic<int> next(0); std::atomic<int> n_failed(0);
         std::vector<int> failed_groups; std::mutex fmu;
-        int64_t cells = 0, alns = 0;
-        for (int t = 0; t < nw; ++t) if (!fin[t].failed && words[t]) { cells += fin[t].cells; alns += plans[pos + t].n_reads - 1; }
+        int64_t cells = 0, alns = 0, fwd_clk = 0, bt_clk = 0;
+        for (int t = 0; t < nw; ++t) if (!fin[t].failed && words[t]) { cells += fin[t].cells; alns += plans[pos + t].n_reads - 1; fwd_clk += fin[t].fwd_clk; bt_clk += fin[t].bt_clk; }
         const int nth = std::max(1, std::min(n_workers, nw));
         std::vector<std::thread> th;
         for (int w = 0; w < nth; ++w)
@@ -434,6 +435,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         if (stats) {
             stats->device_ms += dev_ms; stats->cells += cells; stats->alignments += alns; stats->launches += launches;
             stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; stats->groups_done += nw - n_failed.load(); stats->groups_failed += n_failed.load();
+            stats->fwd_clk += fwd_clk; stats->bt_clk += bt_clk;
             stats->dp_ms += dp_ms; stats->fuse_ms += fuse_ms; stats->dp_launches += n_marks; stats->fuse_launches += n_marks;
         }
         if (verbose)

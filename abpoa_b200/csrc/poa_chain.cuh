@@ -70,6 +70,7 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
     int32_t n_reads, fused;             /* reads of the group / reads already in the graph  */
     int32_t cur;                        /* which of order[2] is current                     */
     int64_t cells;                      /* DP cells of all alignments so far                */
+    int64_t fwd_clk, bt_clk;            /* SM cycles of the forward DP / the backtrace, summed over the alignments */
     uint8_t *base;
     int32_t *in_cnt, *out_cnt, *aln_cnt, *n_read;
     int32_t *in_id, *in_w, *out_id, *out_w;             /* [n_cap * K] */
@@ -360,7 +361,7 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp) {
     /* ---- record mode: score, CIGAR length and the FNV-1a hash of the words the host API would return
      *      (forward order, DP rows translated to node ids; poa_job_to_res in poa_cuda.cu) ---- */
     if (POA_TID0) {
-        s->cells += res->cells;
+        s->cells += res->cells; s->fwd_clk += res->fwd_clk; s->bt_clk += res->bt_clk;
         if (cp->record) {
             s->rec_score[r] = res->best_score; s->rec_nops[r] = n_ops;
             uint64_t hsh = 1469598103934665603ull;

@@ -13,6 +13,7 @@ typedef struct {
     double dp_ms, fuse_ms;              /* per-launch CUDA-event times of the two kernels, summed over rounds AND cohort streams
                                            (cohorts run concurrently: dp_ms + fuse_ms ~ n_cohorts x device_ms) */
     int64_t dp_launches, fuse_launches;
+    int64_t fwd_clk, bt_clk;            /* SM cycles inside the forward DP / the backtrace, summed over alignments */
 } PoaChainStats;
 
 /* may this parameter set run on the device chain at all? */

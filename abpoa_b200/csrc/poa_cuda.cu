@@ -28,7 +28,7 @@
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,
                                         const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st);
-extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, int lean, const PoaJobDesc *jobs,
+extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, int lean, const int *gaps, const PoaJobDesc *jobs,
                                             const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st);
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
 
@@ -355,7 +355,8 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     poa_pick_ring(abpt->gap_mode, bits == 32 ? 32 : 16, band_cells, smem_budget, &ring_rows, &ring_cells);
     int lean = !abpt->inc_path_score && abpt->align_mode == ABPOA_GLOBAL_MODE;
     for (int t = 0; t < n && lean; ++t) if (!jobs[idx[t]].plan.whole_graph) lean = 0;
-    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, lean, (const PoaJobDesc *)(c->d_in + off_desc),
+    const int gaps[4] = { abpt->gap_ext1, abpt->gap_open1 + abpt->gap_ext1, abpt->gap_ext2, abpt->gap_open2 + abpt->gap_ext2 };
+    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, lean, gaps, (const PoaJobDesc *)(c->d_in + off_desc),
                                             (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
                              (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
@@ -703,7 +704,8 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
     CK(cudaStreamSynchronize(c->st));
     CK(cudaEventRecord(c->ev_k0, c->st));
     /* captured jobs are whole-graph alignments (the batch engine's) */
-    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, !abpt->inc_path_score && abpt->align_mode == ABPOA_GLOBAL_MODE,
+    const int gaps[4] = { abpt->gap_ext1, abpt->gap_open1 + abpt->gap_ext1, abpt->gap_ext2, abpt->gap_open2 + abpt->gap_ext2 };
+    if (bits == 15) CK(poa_launch_align_p16(abpt->gap_mode, abpt->align_mode, !abpt->inc_path_score && abpt->align_mode == ABPOA_GLOBAL_MODE, gaps,
                                             (const PoaJobDesc *)(c->d_in + off_desc), (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));
     else CK(poa_launch_align(abpt->gap_mode, bits, abpt->align_mode, (const PoaJobDesc *)(c->d_in + off_desc),
                              (const PoaParamsDev *)c->d_in, n, ring_rows, ring_cells, c->st));

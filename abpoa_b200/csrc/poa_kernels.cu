@@ -795,6 +795,27 @@ __device__ __forceinline__ int lane_max8(const unsigned a[4]) {
     return max(lo16(m), hi16(m));
 }
 
+/* Lane-independent packed constants of the row arithmetic.  Passed to the kernels BY VALUE (__grid_constant__): they
+ * then live in the constant bank and are used as instruction operands directly -- kept in registers they were
+ * rematerialised by ~30 integer instructions every row (register pressure), see profiles/r02_sass_*.txt. */
+struct P16Consts {
+    unsigned K1[4], K2[4];          /* e * (2k), e * (2k+1): A[c] = T[c] + e*c                     */
+    unsigned KF1[4], KF2[4];        /* -(oe + e*(2k-1)), -(oe + e*2k): F from the exclusive prefix  */
+    unsigned KLG[4];                /* -e1*(2k), -e1*(2k+1): linear-gap H from the inclusive prefix */
+    unsigned NE1, NOE1, NE2, NOE2;  /* -e, -oe in both halves                                       */
+};
+static inline unsigned pk_host(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+static P16Consts make_p16_consts(int e1, int oe1, int e2, int oe2) {
+    P16Consts c;
+    for (int k = 0; k < 4; ++k) {
+        c.K1[k] = pk_host(e1 * (2 * k), e1 * (2 * k + 1)); c.K2[k] = pk_host(e2 * (2 * k), e2 * (2 * k + 1));
+        c.KF1[k] = pk_host(-(oe1 + e1 * (2 * k - 1)), -(oe1 + e1 * (2 * k))); c.KF2[k] = pk_host(-(oe2 + e2 * (2 * k - 1)), -(oe2 + e2 * (2 * k)));
+        c.KLG[k] = pk_host(-e1 * (2 * k), -e1 * (2 * k + 1));
+    }
+    c.NE1 = pk_host(-e1, -e1); c.NOE1 = pk_host(-oe1, -oe1); c.NE2 = pk_host(-e2, -e2); c.NOE2 = pk_host(-oe2, -oe2);
+    return c;
+}
+
 /* shared-memory layout of one packed-kernel CTA (one warp) */
 struct P16Smem {
     int *mat_s; uint4 *cap_lo, *cap_hi, *ring_meta; int16_t *ring_data;
@@ -829,7 +850,7 @@ __device__ __forceinline__ P16Smem p16_smem_init(uint8_t *dyn_smem, const PoaPar
  * ring records itself (uniform-address shared loads) instead of lane k owning predecessor k and publishing it
  * through reductions and shuffles, and the predecessor planes are folded in without a loop. */
 template <int GAP, int MODE, bool LEAN = false>
-__device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParamsDev *__restrict__ prm, const P16Smem &sm,
+__device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParamsDev *__restrict__ prm, const P16Consts &kc, const P16Smem &sm,
                                             int ring_rows, int ring_cells, int lane) {
     typedef int16_t ST;
     typedef Planes<GAP> PL;
@@ -860,17 +881,6 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         for (int j = lane; j < qstride; j += 32)
             qp[(size_t)r * qstride + j] = (j == 0 || j > qlen) ? (int16_t)0 : (int16_t)mat_s[r * m + jv.qs[j]];
     __syncwarp();
-
-    /* lane-independent packed constants */
-    unsigned K1[4], K2[4], KF1[4], KF2[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        K1[k] = pk(e1 * (2 * k), e1 * (2 * k + 1));
-        K2[k] = pk(e2 * (2 * k), e2 * (2 * k + 1));
-        KF1[k] = pk(-(oe1 + e1 * (2 * k - 1)), -(oe1 + e1 * (2 * k)));
-        KF2[k] = pk(-(oe2 + e2 * (2 * k - 1)), -(oe2 + e2 * (2 * k)));
-    }
-    const unsigned NE1 = pk(-e1, -e1), NOE1 = pk(-oe1, -oe1), NE2 = pk(-e2, -e2), NOE2 = pk(-oe2, -oe2);
 
     uint64_t cursor = 0;
     int64_t cells = 0; int max_band = 0;
@@ -1062,7 +1072,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                     } else if (lane == 0) prev = (MODE == LOCAL && g == 0) ? 0u : ((unsigned)NEGP << 16);
                     const unsigned d0 = sh1(prev, hp.x), d1 = sh1(hp.x, hp.y), d2 = sh1(hp.y, hp.z), d3 = sh1(hp.z, hp.w);
                     if (GAP == LG) {
-                        hp.x = __viaddmax_s16x2(hp.x, NE1, NEGP2); hp.y = __viaddmax_s16x2(hp.y, NE1, NEGP2); hp.z = __viaddmax_s16x2(hp.z, NE1, NEGP2); hp.w = __viaddmax_s16x2(hp.w, NE1, NEGP2);
+                        hp.x = __viaddmax_s16x2(hp.x, kc.NE1, NEGP2); hp.y = __viaddmax_s16x2(hp.y, kc.NE1, NEGP2); hp.z = __viaddmax_s16x2(hp.z, kc.NE1, NEGP2); hp.w = __viaddmax_s16x2(hp.w, kc.NE1, NEGP2);
                     }
                     const uint4 x1 = GAP == LG ? hp : ep1;
                     if (k == 0) {
@@ -1143,8 +1153,8 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                     }
                     M[0] = __vmaxs2(M[0], d0); M[1] = __vmaxs2(M[1], d1); M[2] = __vmaxs2(M[2], d2); M[3] = __vmaxs2(M[3], d3);
                     if (GAP == LG) {        /* vertical term H[p][j] - e1 */
-                        X1[0] = __vmaxs2(X1[0], __viaddmax_s16x2(hp.x, NE1, NEGP2)); X1[1] = __vmaxs2(X1[1], __viaddmax_s16x2(hp.y, NE1, NEGP2));
-                        X1[2] = __vmaxs2(X1[2], __viaddmax_s16x2(hp.z, NE1, NEGP2)); X1[3] = __vmaxs2(X1[3], __viaddmax_s16x2(hp.w, NE1, NEGP2));
+                        X1[0] = __vmaxs2(X1[0], __viaddmax_s16x2(hp.x, kc.NE1, NEGP2)); X1[1] = __vmaxs2(X1[1], __viaddmax_s16x2(hp.y, kc.NE1, NEGP2));
+                        X1[2] = __vmaxs2(X1[2], __viaddmax_s16x2(hp.z, kc.NE1, NEGP2)); X1[3] = __vmaxs2(X1[3], __viaddmax_s16x2(hp.w, kc.NE1, NEGP2));
                     } else {
                         X1[0] = __vmaxs2(X1[0], ep1.x); X1[1] = __vmaxs2(X1[1], ep1.y); X1[2] = __vmaxs2(X1[2], ep1.z); X1[3] = __vmaxs2(X1[3], ep1.w);
                         if (GAP == CG) { X2[0] = __vmaxs2(X2[0], ep2.x); X2[1] = __vmaxs2(X2[1], ep2.y); X2[2] = __vmaxs2(X2[2], ep2.z); X2[3] = __vmaxs2(X2[3], ep2.w); }
@@ -1173,7 +1183,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             const int jr0 = (g - g0) * 8;
             unsigned a1[4], a2[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { a1[k] = __vadd2(T[k], K1[k]); if (GAP == CG) a2[k] = __vadd2(T[k], K2[k]); }
+            for (int k = 0; k < 4; ++k) { a1[k] = __vadd2(T[k], kc.K1[k]); if (GAP == CG) a2[k] = __vadd2(T[k], kc.K2[k]); }
             const int off1 = e1 * jr0 - (GAP == LG ? 0 : oe1), off2 = e2 * jr0 - oe2;
             int tot1, tot2 = 0;
             int x1 = max(warp_excl_max(lane_max8(a1) + off1, lane, tot1), carry1);
@@ -1191,27 +1201,27 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             for (int k = 0; k < 4; ++k) {
                 if (GAP == LG) {
                     /* inclusive: H[c] = max(P[c], a[c]) - e1*c */
-                    unsigned h = __viaddmax_s16x2(__vmaxs2(P1[k], a1[k]), pk(-e1 * (2 * k), -e1 * (2 * k + 1)), NEGP2);
+                    unsigned h = __viaddmax_s16x2(__vmaxs2(P1[k], a1[k]), kc.KLG[k], NEGP2);
                     if (MODE == LOCAL) h = __vmaxs2(h, zr2);
                     H[k] = __vmins2(h, CAP[k]);
                 } else {
-                    F1[k] = __viaddmax_s16x2(P1[k], KF1[k], NEGP2);
+                    F1[k] = __viaddmax_s16x2(P1[k], kc.KF1[k], NEGP2);
                     if (GAP == AG) {
                         const unsigned t = __vmaxs2(M[k], X1[k]);
                         unsigned fz = F1[k];
                         if (MODE == LOCAL) fz = __vmaxs2(fz, zr2);
                         const unsigned h = __vmaxs2(t, fz);
                         const unsigned from_t = __vcmpges2(t, fz);            /* h == t, per cell */
-                        const unsigned ev = __viaddmax_s16x2(X1[k], NE1, __viaddmax_s16x2(h, NOE1, NEGP2));
+                        const unsigned ev = __viaddmax_s16x2(X1[k], kc.NE1, __viaddmax_s16x2(h, kc.NOE1, NEGP2));
                         const unsigned alt = (MODE == LOCAL) ? zr2 : NEGP2;
                         E1o[k] = __vmins2((ev & from_t) | (alt & ~from_t), CAP[k]);
                         H[k] = __vmins2(h, CAP[k]);
                     } else {
-                        F2[k] = __viaddmax_s16x2(P2[k], KF2[k], NEGP2);
+                        F2[k] = __viaddmax_s16x2(P2[k], kc.KF2[k], NEGP2);
                         unsigned h = __vimax3_s16x2(T[k], F1[k], F2[k]);
                         if (MODE == LOCAL) h = __vmaxs2(h, zr2);
-                        unsigned eo1 = __viaddmax_s16x2(X1[k], NE1, __viaddmax_s16x2(h, NOE1, NEGP2));
-                        unsigned eo2 = __viaddmax_s16x2(X2[k], NE2, __viaddmax_s16x2(h, NOE2, NEGP2));
+                        unsigned eo1 = __viaddmax_s16x2(X1[k], kc.NE1, __viaddmax_s16x2(h, kc.NOE1, NEGP2));
+                        unsigned eo2 = __viaddmax_s16x2(X2[k], kc.NE2, __viaddmax_s16x2(h, kc.NOE2, NEGP2));
                         if (MODE == LOCAL) { eo1 = __vmaxs2(eo1, zr2); eo2 = __vmaxs2(eo2, zr2); }
                         H[k] = __vmins2(h, CAP[k]); E1o[k] = __vmins2(eo1, CAP[k]); E2o[k] = __vmins2(eo2, CAP[k]);
                     }
@@ -1327,14 +1337,14 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 #endif
 template <int GAP, int MODE, bool LEAN>
 __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
-                                                           int n_jobs, int ring_rows, int ring_cells) {
+                                                           int n_jobs, int ring_rows, int ring_cells, const __grid_constant__ P16Consts kc) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const int lane = threadIdx.x;
     const int job = blockIdx.x;
     if (job >= n_jobs) return;
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
     const PoaJobDesc jd = jobs[job];
-    p16_run_job<GAP, MODE, LEAN>(jd, prm, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, MODE, LEAN>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
     __syncwarp();
     if (lane == 0) signal_done(jd);
 }
@@ -1347,7 +1357,8 @@ static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_
  * cursor the coming fuse kernel will fill (see PoaChainSlot). */
 template <int GAP>
 __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__restrict__ slots, const int32_t *__restrict__ idx,
-                                                           const PoaParamsDev *__restrict__ prm, int n_jobs, int round, int ring_rows, int ring_cells) {
+                                                           const PoaParamsDev *__restrict__ prm, int n_jobs, int round, int ring_rows, int ring_cells,
+                                                           const __grid_constant__ P16Consts kc) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const int lane = threadIdx.x;
     const int job = blockIdx.x;
@@ -1358,23 +1369,26 @@ __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__
     const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
     if (sl->failed || sl->fused != round || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
-    p16_run_job<GAP, GLOBAL, true>(jd, prm, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, GLOBAL, true>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
 }
 
 template <int GAP>
-static cudaError_t launch_chain_one(const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round, const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
+static cudaError_t launch_chain_one(const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round, const PoaParamsDev *prm, int ring_rows, int ring_cells,
+                                    const P16Consts &kc, cudaStream_t st) {
     const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
     cudaError_t e = cudaFuncSetAttribute(poa_chain_align_kernel_p16<GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    poa_chain_align_kernel_p16<GAP><<<n_jobs, 32, smem, st>>>(slots, idx, prm, n_jobs, round, ring_rows, ring_cells);
+    poa_chain_align_kernel_p16<GAP><<<n_jobs, 32, smem, st>>>(slots, idx, prm, n_jobs, round, ring_rows, ring_cells, kc);
     return cudaGetLastError();
 }
-extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
+/* gaps[4] = { e1, oe1, e2, oe2 } (host copy of what prm holds on the device) */
+extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const int *gaps, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
                                                   const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
-    if (gap_mode == LG) return launch_chain_one<LG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
-    if (gap_mode == AG) return launch_chain_one<AG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
-    return launch_chain_one<CG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, st);
+    const P16Consts kc = make_p16_consts(gaps[0], gaps[1], gaps[2], gaps[3]);
+    if (gap_mode == LG) return launch_chain_one<LG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    if (gap_mode == AG) return launch_chain_one<AG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    return launch_chain_one<CG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
 }
 
 /* ------------------------------------------------------------------ launcher */
@@ -1416,7 +1430,7 @@ extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t sme
 }
 
 template <int GAP, int MODE, bool LEAN>
-static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
+static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, const P16Consts &kc, cudaStream_t st) {
     const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
     /* per device and instantiation; cudaFuncSetAttribute is cheap and idempotent, so no process-wide cache (a second
      * GPU in the same process needs its own call) */
@@ -1424,27 +1438,28 @@ static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *pr
     if (e != cudaSuccess) return e;
     const char *cv = getenv("ABPOA_GPU_CARVEOUT");          /* shared-memory share of the L1/shared array, percent */
     if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-    poa_align_kernel_p16<GAP, MODE, LEAN><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells);
+    poa_align_kernel_p16<GAP, MODE, LEAN><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells, kc);
     return cudaGetLastError();
 }
 template <int GAP>
-static cudaError_t launch_p16_mode(int mode, int lean, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, cudaStream_t st) {
+static cudaError_t launch_p16_mode(int mode, int lean, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, const P16Consts &kc, cudaStream_t st) {
     switch (mode) {
-    case GLOBAL: return lean ? launch_p16_one<GAP, GLOBAL, true>(jobs, prm, n_jobs, rr, rc, st) : launch_p16_one<GAP, GLOBAL, false>(jobs, prm, n_jobs, rr, rc, st);
-    case LOCAL:  return launch_p16_one<GAP, LOCAL, false>(jobs, prm, n_jobs, rr, rc, st);
-    default:     return launch_p16_one<GAP, EXTEND, false>(jobs, prm, n_jobs, rr, rc, st);
+    case GLOBAL: return lean ? launch_p16_one<GAP, GLOBAL, true>(jobs, prm, n_jobs, rr, rc, kc, st) : launch_p16_one<GAP, GLOBAL, false>(jobs, prm, n_jobs, rr, rc, kc, st);
+    case LOCAL:  return launch_p16_one<GAP, LOCAL, false>(jobs, prm, n_jobs, rr, rc, kc, st);
+    default:     return launch_p16_one<GAP, EXTEND, false>(jobs, prm, n_jobs, rr, rc, kc, st);
     }
 }
 /* the packed int16x2 kernel (int16 planes, DPX pair arithmetic).  lean != 0: every job aligns to the whole graph and
  * carries no -G path scores (the straight-line predecessor path of p16_run_job may be used; global mode only) */
-extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, int lean, const PoaJobDesc *jobs,
+extern "C" cudaError_t poa_launch_align_p16(int gap_mode, int align_mode, int lean, const int *gaps, const PoaJobDesc *jobs,
                                             const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
+    const P16Consts kc = make_p16_consts(gaps[0], gaps[1], gaps[2], gaps[3]);
     static const int no_lean = [] { const char *e = getenv("ABPOA_GPU_NO_LEAN"); return e && *e == '1'; }();
     if (no_lean) lean = 0;
-    if (gap_mode == LG) return launch_p16_mode<LG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
-    if (gap_mode == AG) return launch_p16_mode<AG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
-    return launch_p16_mode<CG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, st);
+    if (gap_mode == LG) return launch_p16_mode<LG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, kc, st);
+    if (gap_mode == AG) return launch_p16_mode<AG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, kc, st);
+    return launch_p16_mode<CG>(align_mode, lean, jobs, prm, n_jobs, ring_rows, ring_cells, kc, st);
 }
 
 extern "C" cudaError_t poa_launch_align(int gap_mode, int bits, int align_mode, const PoaJobDesc *jobs,

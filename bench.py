@@ -403,7 +403,8 @@ def main():
     if used_chain:
         chain = {"device_ms_per_step": chain_ms / args.steps, "groups_on_device": int(chain_groups / args.steps), "groups_handed_back": int(chain_fallback / args.steps),
                  "dp_kernel_ms_sum_over_streams": chain_dp_ms / args.steps, "fuse_kernel_ms_sum_over_streams": chain_fuse_ms / args.steps,
-                 "dp_share_of_kernel_time": chain_dp_ms / max(chain_dp_ms + chain_fuse_ms, 1e-9)}
+                 "dp_share_of_kernel_time": chain_dp_ms / max(chain_dp_ms + chain_fuse_ms, 1e-9),
+                 "backtrace_share_of_dp_kernel_cycles": st["bt_clk"] / max(st["fwd_clk"] + st["bt_clk"], 1)}
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
