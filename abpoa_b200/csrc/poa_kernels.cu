@@ -849,7 +849,11 @@ __device__ __forceinline__ P16Smem p16_smem_init(uint8_t *dyn_smem, const PoaPar
  * shared-memory ring -- practically every row -- take a straight-line path: every lane reads the predecessors'
  * ring records itself (uniform-address shared loads) instead of lane k owning predecessor k and publishing it
  * through reductions and shuffles, and the predecessor planes are folded in without a loop. */
-template <int GAP, int MODE, bool LEAN = false>
+/* TMA (with LEAN): the finished row is staged with ALL its planes in the row's ring slot and drained to HBM by the
+ * bulk-copy engine (cp.async.bulk shared -> global, one copy per plane, issued by one lane) instead of five 16-byte
+ * stores per lane; a slot is reused ring_rows rows later, after cp.async.bulk.wait_group.read says the engine has
+ * finished reading it.  Rows wider than a ring slot keep the plain stores. */
+template <int GAP, int MODE, bool LEAN = false, bool TMA = false>
 __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParamsDev *__restrict__ prm, const P16Consts &kc, const P16Smem &sm,
                                             int ring_rows, int ring_cells, int lane) {
     typedef int16_t ST;
@@ -936,7 +940,8 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
      * owns predecessor k and publishes what the other lanes need about it in two packed words
      * (two shuffles per predecessor); the ring is addressed with 32-bit shared-memory offsets. */
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_data);
-    const uint32_t ring_row_bytes = (uint32_t)(RN * ring_cells * 2), ring_plane_bytes = (uint32_t)(ring_cells * 2);
+    constexpr int RS = TMA ? PL::N : RN;                  /* planes kept per ring row: what successors read, or (TMA) everything */
+    const uint32_t ring_row_bytes = (uint32_t)(RS * ring_cells * 2), ring_plane_bytes = (uint32_t)(ring_cells * 2);
     const int pn_shift = pnv == 16 ? 4 : 3;
     const uint32_t cap32 = jd.plane_cap_units > 0xffffffffull ? 0xffffffffu : (uint32_t)jd.plane_cap_units;
     uint32_t cur32 = (uint32_t)cursor;
@@ -1016,9 +1021,11 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
         const uint32_t need = (uint32_t)ngrp * PL::N;
         if (need > cap32 - cur32) {
+            if (TMA) { if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); __syncwarp(); }     /* nothing may still read this CTA's smem */
             if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cur32; *jd.result = res; }
             return;
         }
+        const bool tma_row = TMA && ngrp <= ring_groups;
         const uint32_t my_off = cur32;
         cur32 += need;
         ST *rowp = planes + (size_t)my_off * POA_GROUP;
@@ -1229,6 +1236,24 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             }
 
             KP(2)
+            if (TMA && tma_row) {
+                if (gp == g0) {                              /* the slot's previous tenant (ring_rows rows ago) must have been read out */
+                    if (lane == 0) { if (ring_rows >= 8) asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+                    __syncwarp();
+                }
+                if (active) {
+                    const uint32_t a = my_ring_s + (uint32_t)(g - g0) * 16u;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]) : "memory");
+                    if (GAP != LG) {
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + (uint32_t)PL::E1 * ring_plane_bytes), "r"(E1o[0]), "r"(E1o[1]), "r"(E1o[2]), "r"(E1o[3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + (uint32_t)PL::F1 * ring_plane_bytes), "r"(F1[0]), "r"(F1[1]), "r"(F1[2]), "r"(F1[3]) : "memory");
+                    }
+                    if (GAP == CG) {
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + (uint32_t)PL::E2 * ring_plane_bytes), "r"(E2o[0]), "r"(E2o[1]), "r"(E2o[2]), "r"(E2o[3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + (uint32_t)PL::F2 * ring_plane_bytes), "r"(F2[0]), "r"(F2[1]), "r"(F2[2]), "r"(F2[3]) : "memory");
+                    }
+                }
+            } else
             if (active) {
                 const int rel = g - g0;
                 if (rel < ring_groups) {
@@ -1272,6 +1297,18 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             }
         }
         KP(4)
+        if (TMA && tma_row) {                                /* drain the row: one bulk copy per plane, shared -> global */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)ngrp * 16u;
+#pragma unroll
+                for (int pl = 0; pl < PL::N; ++pl)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(rowp + (size_t)pl * gplane), "r"(my_ring_s + (uint32_t)pl * ring_plane_bytes), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
         if (lane == 0) {
             ring_meta[i & rmask] = make_uint4((unsigned)beg, (unsigned)end, (unsigned)(row_left + 1) | ((unsigned)(row_right + 1) << 16), my_off);
             PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
@@ -1294,6 +1331,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     }
     cursor = cur32;
     KP_OUT(res)
+    if (TMA) {                                               /* the end-cell lookup and the backtrace read the planes from HBM */
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
 
     if (MODE == GLOBAL) {
         const int sb = jv.predoff(n_rows - 1), sn = jv.predoff(n_rows) - sb;
@@ -1335,7 +1376,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 #else
 #define POA_P16_BOUNDS __launch_bounds__(32)
 #endif
-template <int GAP, int MODE, bool LEAN>
+template <int GAP, int MODE, bool LEAN, bool TMA>
 __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
                                                            int n_jobs, int ring_rows, int ring_cells, const __grid_constant__ P16Consts kc) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -1344,18 +1385,18 @@ __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict
     if (job >= n_jobs) return;
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
     const PoaJobDesc jd = jobs[job];
-    p16_run_job<GAP, MODE, LEAN>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, MODE, LEAN, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
     __syncwarp();
     if (lane == 0) signal_done(jd);
 }
 
-static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells);
+static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells, int all_planes = 0);
 
 /* ------------------------------------------------------------------ chain engine entry
  * The same job function, fed from device-resident slots (poa_chain.cuh): the job blob of a slot is written
  * by the fuse kernel of the previous round, nothing comes from the host.  Block 0 also zeroes the plane-pool
  * cursor the coming fuse kernel will fill (see PoaChainSlot). */
-template <int GAP>
+template <int GAP, bool TMA>
 __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__restrict__ slots, const int32_t *__restrict__ idx,
                                                            const PoaParamsDev *__restrict__ prm, int n_jobs, int round, int ring_rows, int ring_cells,
                                                            const __grid_constant__ P16Consts kc) {
@@ -1369,31 +1410,38 @@ __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__
     const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
     if (sl->failed || sl->fused != round || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
-    p16_run_job<GAP, GLOBAL, true>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
+    p16_run_job<GAP, GLOBAL, true, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
 }
 
-template <int GAP>
+template <int GAP, bool TMA>
 static cudaError_t launch_chain_one(const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round, const PoaParamsDev *prm, int ring_rows, int ring_cells,
                                     const P16Consts &kc, cudaStream_t st) {
-    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
-    cudaError_t e = cudaFuncSetAttribute(poa_chain_align_kernel_p16<GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells, TMA) + 18 * sizeof(uint4);
+    cudaError_t e = cudaFuncSetAttribute(poa_chain_align_kernel_p16<GAP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    poa_chain_align_kernel_p16<GAP><<<n_jobs, 32, smem, st>>>(slots, idx, prm, n_jobs, round, ring_rows, ring_cells, kc);
+    poa_chain_align_kernel_p16<GAP, TMA><<<n_jobs, 32, smem, st>>>(slots, idx, prm, n_jobs, round, ring_rows, ring_cells, kc);
     return cudaGetLastError();
 }
 /* gaps[4] = { e1, oe1, e2, oe2 } (host copy of what prm holds on the device) */
+extern "C" int poa_tma_enabled(void);
 extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const int *gaps, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
                                                   const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
     const P16Consts kc = make_p16_consts(gaps[0], gaps[1], gaps[2], gaps[3]);
-    if (gap_mode == LG) return launch_chain_one<LG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
-    if (gap_mode == AG) return launch_chain_one<AG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
-    return launch_chain_one<CG>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    if (poa_tma_enabled() && ring_rows >= 2) {
+        if (gap_mode == LG) return launch_chain_one<LG, true>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+        if (gap_mode == AG) return launch_chain_one<AG, true>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+        return launch_chain_one<CG, true>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    }
+    if (gap_mode == LG) return launch_chain_one<LG, false>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    if (gap_mode == AG) return launch_chain_one<AG, false>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
+    return launch_chain_one<CG, false>(slots, idx, n_jobs, round, prm, ring_rows, ring_cells, kc, st);
 }
 
 /* ------------------------------------------------------------------ launcher */
-static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells) {
-    const int rn = gap == LG ? 1 : (gap == AG ? 2 : 3);
+/* all_planes: the TMA variant stages every plane of a row in its ring slot, not only the ones successors read */
+static inline size_t ring_smem_bytes(int gap, int bits, int ring_rows, int ring_cells, int all_planes) {
+    const int rn = all_planes ? (gap == LG ? 1 : (gap == AG ? 3 : 5)) : (gap == LG ? 1 : (gap == AG ? 2 : 3));
     return (size_t)POA_MAX_M * POA_MAX_M * sizeof(int) + (size_t)ring_rows * sizeof(PoaRowInfo) + (((size_t)ring_rows * 4 + 15) & ~(size_t)15)
            + (size_t)ring_rows * rn * ring_cells * (bits / 8);
 }
@@ -1420,33 +1468,38 @@ static cudaError_t launch_mode(int mode, const PoaJobDesc *jobs, const PoaParams
 
 /* Pick the shared-memory ring geometry for a launch: slots wide enough for the expected band
  * (`band_cells`, already a multiple of 8) and as many rows as fit the per-CTA budget. */
+extern "C" int poa_tma_enabled(void) { static const int on = [] { const char *e = getenv("ABPOA_GPU_TMA"); return e && *e == '1'; }(); return on; }
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells) {
     int rc = band_cells < 64 ? 64 : band_cells;
     int rr = 64;
+    const int all = bits == 16 && poa_tma_enabled();
+    if (all) smem_budget += 12 * 1024;                                        /* two more planes per ring row */
     smem_budget = smem_budget > 512 ? smem_budget - 512 : smem_budget;      /* mask tables of the packed kernel */
-    while (rr > 2 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rr >>= 1;
-    while (rc > 64 && ring_smem_bytes(gap_mode, bits, rr, rc) > smem_budget) rc -= 64;   /* very wide rows: cache a prefix */
+    while (rr > 2 && ring_smem_bytes(gap_mode, bits, rr, rc, all) > smem_budget) rr >>= 1;
+    while (rc > 64 && ring_smem_bytes(gap_mode, bits, rr, rc, all) > smem_budget) rc -= 64;   /* very wide rows: cache a prefix */
     *ring_rows = rr; *ring_cells = rc;
 }
 
-template <int GAP, int MODE, bool LEAN>
+template <int GAP, int MODE, bool LEAN, bool TMA>
 static cudaError_t launch_p16_one(const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int ring_rows, int ring_cells, const P16Consts &kc, cudaStream_t st) {
-    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells) + 18 * sizeof(uint4);
+    const size_t smem = ring_smem_bytes(GAP, 16, ring_rows, ring_cells, TMA) + 18 * sizeof(uint4);
     /* per device and instantiation; cudaFuncSetAttribute is cheap and idempotent, so no process-wide cache (a second
      * GPU in the same process needs its own call) */
-    cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     const char *cv = getenv("ABPOA_GPU_CARVEOUT");          /* shared-memory share of the L1/shared array, percent */
-    if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-    poa_align_kernel_p16<GAP, MODE, LEAN><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells, kc);
+    if (cv && *cv) cudaFuncSetAttribute(poa_align_kernel_p16<GAP, MODE, LEAN, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+    poa_align_kernel_p16<GAP, MODE, LEAN, TMA><<<n_jobs, 32, smem, st>>>(jobs, prm, n_jobs, ring_rows, ring_cells, kc);
     return cudaGetLastError();
 }
 template <int GAP>
 static cudaError_t launch_p16_mode(int mode, int lean, const PoaJobDesc *jobs, const PoaParamsDev *prm, int n_jobs, int rr, int rc, const P16Consts &kc, cudaStream_t st) {
     switch (mode) {
-    case GLOBAL: return lean ? launch_p16_one<GAP, GLOBAL, true>(jobs, prm, n_jobs, rr, rc, kc, st) : launch_p16_one<GAP, GLOBAL, false>(jobs, prm, n_jobs, rr, rc, kc, st);
-    case LOCAL:  return launch_p16_one<GAP, LOCAL, false>(jobs, prm, n_jobs, rr, rc, kc, st);
-    default:     return launch_p16_one<GAP, EXTEND, false>(jobs, prm, n_jobs, rr, rc, kc, st);
+    case GLOBAL:
+        if (lean && poa_tma_enabled()) return launch_p16_one<GAP, GLOBAL, true, true>(jobs, prm, n_jobs, rr, rc, kc, st);
+        return lean ? launch_p16_one<GAP, GLOBAL, true, false>(jobs, prm, n_jobs, rr, rc, kc, st) : launch_p16_one<GAP, GLOBAL, false, false>(jobs, prm, n_jobs, rr, rc, kc, st);
+    case LOCAL:  return launch_p16_one<GAP, LOCAL, false, false>(jobs, prm, n_jobs, rr, rc, kc, st);
+    default:     return launch_p16_one<GAP, EXTEND, false, false>(jobs, prm, n_jobs, rr, rc, kc, st);
     }
 }
 /* the packed int16x2 kernel (int16 planes, DPX pair arithmetic).  lean != 0: every job aligns to the whole graph and

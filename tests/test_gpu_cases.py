@@ -73,15 +73,15 @@ def run_group_counting_retries(lib, cfg, reads):
         return {"alns": alns, "cons": s.consensus(), "cov": s.consensus_cov(), "msa": s.msa_rows(), "order_stats": None}, _retries(s)
 
 
-def test_range_guard_redo(product_lib, monkeypatch):
-    """Scores that need 32 bits, forced onto the packed int16 kernel: its run-time guard must report
-    POA_ST_RANGE for every such alignment and the 32-bit redo must give the golden result."""
+def test_range_guard_redo(product_lib, reference_lib, monkeypatch):
+    """Scores that really leave the int16 window (2 kbp x match 20 = 40 000), forced onto the packed int16 kernel: its
+    run-time guard must report POA_ST_RANGE and the 32-bit redo must give the reference's result."""
     monkeypatch.setenv("ABPOA_GPU_FORCE_P16", "1")
-    case = CASES["syn_convex_int32"]
-    cfg = PoaConfig(**case["cfg"])
-    got, retries = run_group_counting_retries(product_lib, cfg, case_reads(case))
+    cfg = PoaConfig(**CASES["syn_convex_int32"]["cfg"])
+    reads = synth.make_group(31, 6, 2000, 0.05)
+    got, retries = run_group_counting_retries(product_lib, cfg, reads)
     assert retries > 0, "the packed kernel never reported RANGE on scores beyond int16"
-    assert_digest_equal(group_digest(got, cfg.m), GOLDEN["cases"]["syn_convex_int32"], "range-redo")
+    assert_group_equal(got, run_group(reference_lib, cfg, reads), "range-redo")
 
 
 @pytest.mark.parametrize("name", ["syn_convex_2k", "syn_affine_1k", "syn_high_error"])
