@@ -1034,6 +1034,16 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         cells += (end >= beg) ? (end - beg + 1) : 0;
         max_band = max(max_band, end - beg + 1);
         const int16_t *qrow = qp + (size_t)rbase * qstride;
+        /* The query profile of a job (m x qlen x 2 B, ~100 KB at 10 kbp) does not stay in L1 with several jobs per SM, so a
+         * row's 16-byte profile load used to be an L2 round trip on the row-to-row chain (ncu: long-scoreboard stall 1.7 per
+         * issue).  The NEXT row's residue is known already: pull its profile lines into L1 one row ahead.  Its band starts at
+         * this row's g0 or one group later, which the 16-byte-per-lane footprint plus one extra line covers. */
+        if (i + 1 < n_rows - 1) {
+            const int16_t *nrow = qp + (size_t)n_rbase * qstride;
+            const int c0 = min((g0 + lane) * 8, qstride - 8);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(nrow + c0));
+            if (lane >= 24) asm volatile("prefetch.global.L1 [%0];" :: "l"(nrow + min(c0 + 64, qstride - 8)));
+        }
 
         int carry1 = 2 * NEG, carry2 = 2 * NEG;
         int row_max = NEG, row_left = -1, row_right = -1;
