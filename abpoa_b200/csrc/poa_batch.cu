@@ -220,7 +220,8 @@ extern "C" { extern __thread double poa_prof_ms[8]; }
  * Kahn order, whatever order the alignments ran in. */
 void poa_finish_group_result(abpoa_t *ab, abpoa_para_t *abpt, abpoa_gpu_group_result_t *o, struct PoaEmit *emit, int gidx) {
     poa_graph_set_fast_order(ab->abg, 0);
-    if (ab->abg->node_n > 2) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
+    /* (a consensus installed by poa_cons_install needs no graph) */
+    if (ab->abg->node_n > 2 && !ab->abg->is_called_cons) { ab->abg->is_topological_sorted = 0; abpoa_topological_sort(ab->abg, abpt); }
     if (emit) {
         const int g = emit->map ? emit->map[gidx] : gidx;
         abpoa_seq_t *abs = ab->abs;

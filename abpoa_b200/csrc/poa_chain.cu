@@ -86,6 +86,22 @@ __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_export_kernel(PoaChainS
     }
 }
 
+/* consensus of every finished group (chain_consensus: heaviest bundling on one thread per group); records are packed
+ * back to back into `out` through an atomic cursor: rec_off[g] = first word of group g's record, -1 if none */
+__global__ void __launch_bounds__(32) poa_chain_consensus_kernel(PoaChainSlot *slots, const PoaChainParams *cp, int n,
+                                                                 int32_t *out, unsigned long long *cursor, unsigned long long out_words, int64_t *rec_off) {
+    if ((int)blockIdx.x >= n || threadIdx.x != 0) return;
+    PoaChainSlot *s = &slots[blockIdx.x];
+    int32_t *tmp = s->scr[2];                               /* [n_cap]: the consensus is never longer than the graph */
+    chain_consensus(s, cp, tmp, s->n_cap);
+    const int len = tmp[0];
+    if (len < 0) { rec_off[blockIdx.x] = -1; return; }
+    const unsigned long long at = atomicAdd(cursor, (unsigned long long)(len + 1));
+    if (at + (unsigned long long)(len + 1) > out_words) { rec_off[blockIdx.x] = -1; return; }
+    for (int k = 0; k <= len; ++k) out[at + k] = tmp[k];
+    rec_off[blockIdx.x] = (int64_t)at;
+}
+
 /* ------------------------------------------------------------------ host side */
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -335,8 +351,17 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         }
         for (size_t c = 1; c < coh.size(); ++c) CK(cudaStreamWaitEvent(s0, coh[c].ev_end, 0));
         CK(cudaEventRecord(ev_t1, s0));
-        /* ---- export: slot headers first (sizes), then the compact graphs ---- */
-        poa_chain_export_kernel<<<nw, POA_CHAIN_T, 0, s0>>>(d_slots, d_cp, nw, d_ex, d_exoff, d_excap);
+        /* ---- results.  Default: heaviest-bundling consensus on the device, only consensus bytes come back.
+         *      ABPOA_GPU_CHAIN_EXPORT_GRAPH=1: the whole graph comes back (compact export) and the host layer computes the
+         *      consensus on it -- the cross-check of the device graph against the host code. ---- */
+        const bool export_graph = [] { const char *e = getenv("ABPOA_GPU_CHAIN_EXPORT_GRAPH"); return e && *e == '1'; }();
+        unsigned long long *d_ccur = d_cursors;               /* the pool cursors are idle now: reuse the first as the record cursor */
+        int64_t *d_recoff = d_exoff;                          /* and the export offsets as record offsets */
+        if (export_graph) poa_chain_export_kernel<<<nw, POA_CHAIN_T, 0, s0>>>(d_slots, d_cp, nw, d_ex, d_exoff, d_excap);
+        else {
+            CK(cudaMemsetAsync(d_ccur, 0, sizeof(unsigned long long), s0));
+            poa_chain_consensus_kernel<<<nw, 32, 0, s0>>>(d_slots, d_cp, nw, d_ex, d_ccur, (unsigned long long)(pool_bytes / 4), d_recoff);
+        }
         CK(cudaGetLastError());
         ++launches;
         std::vector<PoaChainSlot> fin((size_t)nw);
@@ -357,9 +382,22 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         memcpy(fin.data(), h_fin, (size_t)nw * sizeof(PoaChainSlot));
         CK(cudaFreeHost(h_fin));
         const double t_dev_done = now_ms();
+        /* ---- device consensus: record offsets, then one copy of all records ---- */
+        std::vector<int64_t> recoff((size_t)nw, -1); int32_t *h_cons = NULL; unsigned long long cons_words = 0;
+        if (!export_graph) {
+            int64_t *h_ro = NULL; CK(cudaHostAlloc((void **)&h_ro, (size_t)nw * 8 + 8, cudaHostAllocDefault));
+            CK(cudaMemcpyAsync(h_ro, d_recoff, (size_t)nw * 8, cudaMemcpyDeviceToHost, s0));
+            CK(cudaMemcpyAsync(h_ro + nw, d_ccur, 8, cudaMemcpyDeviceToHost, s0));
+            CK(cudaStreamSynchronize(s0));
+            memcpy(recoff.data(), h_ro, (size_t)nw * 8); cons_words = (unsigned long long)h_ro[nw];
+            CK(cudaFreeHost(h_ro));
+            if (cons_words > pool_bytes / 4) cons_words = pool_bytes / 4;
+            CK(cudaHostAlloc((void **)&h_cons, (size_t)std::max<unsigned long long>(cons_words, 1) * 4, cudaHostAllocDefault));
+            if (cons_words) CK(cudaMemcpyAsync(h_cons, d_ex, (size_t)cons_words * 4, cudaMemcpyDeviceToHost, s0));
+        }
         /* word counts: header words 0..3 of every record */
         std::vector<int32_t> hdr4((size_t)nw * 4);
-        {
+        if (export_graph) {
             int32_t *h_hdr = NULL; CK(cudaHostAlloc((void **)&h_hdr, (size_t)nw * 16, cudaHostAllocDefault));
             for (int t = 0; t < nw; ++t) CK(cudaMemcpyAsync(h_hdr + 4 * t, d_ex + h_exoff[t], 16, cudaMemcpyDeviceToHost, s0));
             CK(cudaStreamSynchronize(s0));
@@ -368,12 +406,13 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         }
         std::vector<int64_t> words((size_t)nw, 0), hoff2((size_t)nw, 0); int64_t tot_words = 0;
         for (int t = 0; t < nw; ++t) {
+            if (!export_graph) { words[t] = (!fin[t].failed && recoff[t] >= 0) ? 1 : 0; continue; }
             if (fin[t].failed || hdr4[4 * t] < 2) continue;
             words[t] = 4 + 5ll * hdr4[4 * t] + 4ll * hdr4[4 * t + 1] + hdr4[4 * t + 2];
             hoff2[t] = tot_words; tot_words += words[t];
         }
         int32_t *h_ex = NULL; CK(cudaHostAlloc((void **)&h_ex, (size_t)std::max<int64_t>(tot_words, 1) * 4, cudaHostAllocDefault));
-        for (int t = 0; t < nw; ++t) if (words[t]) CK(cudaMemcpyAsync(h_ex + hoff2[t], d_ex + h_exoff[t], (size_t)words[t] * 4, cudaMemcpyDeviceToHost, s0));
+        if (export_graph) for (int t = 0; t < nw; ++t) if (words[t]) CK(cudaMemcpyAsync(h_ex + hoff2[t], d_ex + h_exoff[t], (size_t)words[t] * 4, cudaMemcpyDeviceToHost, s0));
         /* per-read records */
         std::vector<std::vector<int32_t>> rs((size_t)nw), rn((size_t)nw); std::vector<std::vector<uint64_t>> rh((size_t)nw);
         if (record) for (int t = 0; t < nw; ++t) {
@@ -384,7 +423,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             CK(cudaMemcpyAsync(rh[t].data(), fin[t].rec_hash, (size_t)nr * 8, cudaMemcpyDeviceToHost, s0));
         }
         CK(cudaStreamSynchronize(s0));
-        const uint64_t d2h = (uint64_t)tot_words * 4 + (uint64_t)nw * (sizeof(PoaChainSlot) + 16);
+        const uint64_t d2h = (uint64_t)tot_words * 4 + (uint64_t)cons_words * 4 + (uint64_t)nw * (sizeof(PoaChainSlot) + 16);
         poa_arena_return(arena, d_base, total);
         const double t_copied = now_ms();
 
@@ -413,7 +452,14 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                     abpoa_seq_t *abs = ab->abs;
                     abs->n_seq = p.n_reads; poa_seq_reserve(abs);
                     for (int i = 0; i < p.n_reads; ++i) { abs->is_rc[i] = 0; abs->name[i].l = 0; }
-                    poa_graph_import(ab, abpt, h_ex + hoff2[t]);
+                    if (export_graph) poa_graph_import(ab, abpt, h_ex + hoff2[t]);
+                    else {                                     /* the device's consensus: base | coverage << 8 per position */
+                        const int32_t *rec = h_cons + recoff[t];
+                        const int len = rec[0];
+                        std::vector<uint8_t> cb((size_t)(len > 0 ? len : 1)); std::vector<int> cc((size_t)(len > 0 ? len : 1));
+                        for (int j = 0; j < len; ++j) { cb[j] = (uint8_t)(rec[1 + j] & 0xff); cc[j] = rec[1 + j] >> 8; }
+                        poa_cons_install(ab, p.n_reads, len, cb.data(), cc.data());
+                    }
                     poa_finish_group_result(ab, abpt, o, emit, p.g);
                     o->dp_cells = fin[t].cells; o->n_aligned = p.n_reads - 1;
                     if (record) {
@@ -429,7 +475,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             });
         for (auto &x : th) x.join();
         for (int g : failed_groups) fallback.push_back(g);
-        CK(cudaFreeHost(h_ex)); CK(cudaFreeHost(h_reads));
+        CK(cudaFreeHost(h_ex)); CK(cudaFreeHost(h_reads)); if (h_cons) CK(cudaFreeHost(h_cons));
         for (Cohort &c : coh) { cudaEventDestroy(c.ev_begin); cudaEventDestroy(c.ev_end); cudaStreamDestroy(c.st); }
         cudaEventDestroy(ev_up); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
         if (stats) {

@@ -539,4 +539,49 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp) {
     POA_CTA_SYNC();
 }
 
+/* ------------------------------------------------------------------ consensus on the device
+ * Heaviest bundling, single cluster (reference src/abpoa_output.c:477-547; host twin: heaviest_bundling in
+ * poa_cons.c): score[v] = w(best out-edge) + score[its head], best = largest weight, among equal weights an inner
+ * node keeps the LAST edge whose head scores >= the current pick, SRC keeps the first unless strictly better.
+ * The reference visits nodes in reverse Kahn order; the values depend only on the out-neighbours, so one backward
+ * sweep over the (spliced) topological order gives the same picks.  It runs once per group, serially on one
+ * thread (every group has its own CTA; ~25 k dependent steps against ~1 M row steps of DP per group).
+ * out[0] = consensus length, out[1 + k] = base | coverage << 8 of consensus position k. */
+POA_DEV void chain_consensus(PoaChainSlot *s, const PoaChainParams *cp, int32_t *out, int out_cap) {
+    if (!POA_TID0) return;
+    const int K = cp->K, n = s->n_nodes;
+    const int32_t *order = s->order[s->cur];
+    int32_t *score = s->scr[0], *nxt = s->scr[1];
+    if (s->failed || n < 3) { out[0] = -1; return; }
+    for (int r = n - 1; r >= 0; --r) {
+        const int v = order[r];
+        const int ne = s->out_cnt[v];
+        const int32_t *oid = s->out_id + (size_t)v * K, *ow = s->out_w + (size_t)v * K;
+        if (v == 1) { score[v] = 0; nxt[v] = -1; }
+        else if (v == 0) {
+            int pick = -1, pick_score = -1, pick_w = -1;
+            for (int e = 0; e < ne; ++e) {
+                const int u = oid[e], w = ow[e];
+                if (w > pick_w || (w == pick_w && score[u] > pick_score)) { pick = u; pick_score = score[u]; pick_w = w; }
+            }
+            nxt[v] = pick;
+        } else {
+            int pick = -1, pick_w = INT32_MIN;
+            for (int e = 0; e < ne; ++e) {
+                const int u = oid[e], w = ow[e];
+                if (pick_w < w) { pick_w = w; pick = u; }
+                else if (pick_w == w && score[pick] <= score[u]) pick = u;
+            }
+            score[v] = pick_w + score[pick];
+            nxt[v] = pick;
+        }
+    }
+    int len = 0;
+    for (int cur = nxt[0]; cur != 1 && cur >= 0; cur = nxt[cur]) {
+        if (1 + len >= out_cap) { out[0] = -1; return; }
+        out[1 + len++] = (int32_t)s->base[cur] | (s->n_read[cur] << 8);
+    }
+    out[0] = len;
+}
+
 #endif

@@ -114,6 +114,23 @@ void abpoa_generate_consensus(abpoa_t *ab, abpoa_para_t *abpt) {
     abg->is_called_cons = 1;
 }
 
+/* A consensus that was computed elsewhere (the device chain, poa_chain.cuh: chain_consensus) installed as the handle's
+ * single-cluster result, so that abpoa_output() and the writers treat it like one they generated themselves. */
+void poa_cons_install(abpoa_t *ab, int n_seq, int len, const uint8_t *base, const int *cov) {
+    abpoa_cons_t *abc = ab->abc;
+    poa_cons_clear(abc);
+    cons_alloc(abc, len > 0 ? len : 1, n_seq, 1);
+    abc->clu_n_seq[0] = n_seq;
+    for (int i = 0; i < n_seq; ++i) abc->clu_read_ids[0][i] = i;
+    for (int j = 0; j < len; ++j) {
+        abc->cons_node_ids[0][j] = -1;                     /* node ids stay on the device */
+        abc->cons_base[0][j] = base[j]; abc->cons_cov[0][j] = cov[j];
+        abc->cons_phred_score[0][j] = column_phred(cov[j], n_seq);
+    }
+    abc->cons_len[0] = len;
+    ab->abg->is_called_cons = 1;
+}
+
 /* column of a node = max rank over its aligned group, 1-based */
 static int msa_column(const abpoa_graph_t *abg, int id) {
     int r = abg->node_id_to_msa_rank[id];

@@ -51,6 +51,7 @@ abpoa_cons_t *poa_cons_new(void);
 void poa_cons_clear(abpoa_cons_t *abc);            /* free members, keep the struct */
 void poa_cons_free(abpoa_cons_t *abc);
 void poa_set_msa_rank(abpoa_graph_t *abg, int src_id, int sink_id);
+void poa_cons_install(abpoa_t *ab, int n_seq, int len, const uint8_t *base, const int *cov);   /* a consensus computed on the device */
 int poa_edge_path_score(const abpoa_graph_t *abg, int node_id, int in_idx);  /* -G scores */
 /* dense, node-id-indexed views kept by poa_graph.c (see poa_graph_x) */
 void poa_graph_sync_public(abpoa_graph_t *abg);        /* fold dense n_read / n_span_read into node[] */

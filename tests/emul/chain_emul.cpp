@@ -73,3 +73,4 @@ extern "C" const uint8_t *chain_emul_bases(Emul *e) { return e->s.base; }
 extern "C" const uint8_t *chain_emul_blob(Emul *e) { return e->blob.data(); }
 extern "C" const uint64_t *chain_emul_hashes(Emul *e) { return e->rec_hash.data(); }
 extern "C" int64_t chain_emul_cells(Emul *e) { return e->s.cells; }
+extern "C" int chain_emul_consensus(Emul *e, int32_t *out, int cap) { chain_consensus(&e->s, &e->cp, out, cap); return out[0]; }

@@ -48,6 +48,8 @@ def emul():
     d.chain_emul_hashes.argtypes = [C.c_void_p]
     d.chain_emul_cells.restype = C.c_int64
     d.chain_emul_cells.argtypes = [C.c_void_p]
+    d.chain_emul_consensus.restype = C.c_int
+    d.chain_emul_consensus.argtypes = [C.c_void_p, c_int_p, C.c_int]
     return d
 
 
@@ -128,6 +130,15 @@ def drive(emul, product_lib, cfg: PoaConfig, reads, K=12, A=None, n_cap=None):
                     for name_, a, b in (("header", 0, 68), ("rowmeta", off_rm, off_rm + 8 * (n_rows + 1)), ("pred", off_pred, off_pred + 4 * n_pred), ("query", off_qs, nbytes)):
                         assert np.array_equal(got[a:b], want[a:b]), f"read {i}: job blob for read {i + 1}: section {name_} differs at byte {a + int(np.argmax(got[a:b] != want[a:b]))}"
             assert d.chain_emul_cells(e) == tot_cells
+            # ---- consensus computed by the device code vs the host's heaviest bundling on the same graph ----
+            s.lib.dll.poa_graph_set_fast_order(s.ab.contents.abg, 0)
+            s.ab.contents.abs.contents.n_seq = n
+            s.generate()
+            out = np.zeros(n_cap + 1, dtype=np.int32)
+            ln = d.chain_emul_consensus(e, out.ctypes.data_as(c_int_p), len(out))
+            cons, cov = s.consensus()[0], s.consensus_cov()[0]
+            assert ln == len(cons), f"device consensus length {ln} vs host {len(cons)}"
+            assert np.array_equal(out[1: 1 + ln] & 0xff, cons) and np.array_equal(out[1: 1 + ln] >> 8, cov), "device consensus / coverage differs from the host's"
         finally:
             d.chain_emul_free(e)
 

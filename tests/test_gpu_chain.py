@@ -105,3 +105,12 @@ def test_chain_and_launch_engine_agree(reference_lib):
         assert x.dp_cells == y.dp_cells
         assert np.array_equal(x.read_best_score[1:], y.read_best_score[1:]) and np.array_equal(x.read_cigar_hash[1:], y.read_cigar_hash[1:])
         assert all(np.array_equal(p, q) for p, q in zip(x.cons, y.cons)) and all(np.array_equal(p, q) for p, q in zip(x.cov, y.cov))
+
+
+def test_chain_graph_export_cross_check(reference_lib, monkeypatch):
+    """ABPOA_GPU_CHAIN_EXPORT_GRAPH=1: instead of the device's consensus the whole device-built graph comes back and the
+    host layer computes the consensus on it -- both routes must agree with the reference."""
+    groups = [synth.make_group(5900 + g, 9, 450, 0.08) for g in range(6)]
+    check(reference_lib, PoaConfig(), groups, expect_chain=6, expect_fallback=0)
+    monkeypatch.setenv("ABPOA_GPU_CHAIN_EXPORT_GRAPH", "1")
+    check(reference_lib, PoaConfig(), groups, expect_chain=6, expect_fallback=0)
