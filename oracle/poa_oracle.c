@@ -37,6 +37,10 @@
 typedef struct {
     int beg, end;          /* band of the row, inclusive                         */
     int *h, *e1, *e2, *f1, *f2;   /* planes, indexed by j - beg                  */
+    /* banded linear-gap rows (global / extend): everything the reference's VECTOR row holds, cells
+     * xbeg .. xend = whole vectors around the band (see lg_vector_row); h points into it */
+    int xbeg, xend; int *hx;
+    void *alloc;           /* what to free                                       */
 } orow_t;
 
 static void *xm(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "[poa_oracle] out of memory\n"); exit(1); } return p; }
@@ -45,6 +49,77 @@ static inline int cell(const int *plane, const orow_t *r, int j) {
     return (plane && j >= r->beg && j <= r->end) ? plane[j - r->beg] : NINF;
 }
 static inline int addinf(int v, int d) { return v <= NINF / 2 ? NINF : v + d; }   /* -inf stays -inf */
+/* stored value of a vector-exact linear-gap row at column j (inside or outside its band) */
+static inline int xcell(const orow_t *r, int j) { return (r->hx && j >= r->xbeg && j <= r->xend) ? r->hx[j - r->xbeg] : NINF; }
+
+/* The reference's in-vector max-plus scan SIMD_SET_F (src/abpoa_align_simd.c:691-725), lane for lane.  Table semantics
+ * (:480-495): PRE_MASK[c] keeps lanes 0..c, SUF_MIN[c] sets lanes > c to -inf, PRE_MIN[n] sets lanes < n to -inf.
+ * set_num == pn: full log-step scan.  set_num < pn ("suffix MIN_INF"): at step k only lanes <= cov_k receive, cov_0 =
+ * set_num, cov_k = cov_{k-1} + 2^k -- which is NOT a complete scan (set_num 0: lane 1 never receives, the last lane never
+ * does), and that is part of what the reference computes at the right edge of a band. */
+static void lg_set_f(int *F, int pn, int log_n, int set_num, int e1) {
+    int G[64];
+    int cov = set_num;
+    for (int k = 0; k < log_n; ++k) {
+        const int sh = 1 << k;
+        if (set_num != pn && k > 0) cov += sh;
+        for (int l = 0; l < pn; ++l) {
+            int v = (l >= sh) ? addinf(F[l - sh], -e1 * sh) : NINF;
+            if (set_num != pn && l > (cov < pn - 1 ? cov : pn - 1)) v = NINF;
+            G[l] = v;
+        }
+        for (int l = 0; l < pn; ++l) F[l] = MAX2(F[l], G[l]);
+    }
+}
+
+/* One banded linear-gap row in global / extend mode exactly as the reference's vector procedure leaves it
+ * (simd_abpoa_lg_dp, src/abpoa_align_simd.c:727-815; pn = lanes of the AVX2 vector for the score width the reference
+ * picks).  Differences from the textbook recurrence, all at band edges:
+ *   - predecessor p is read in whole vectors _beg_sn .. min((pre_end+1)/pn, end_sn): cells of p outside its band but
+ *     inside its stored vectors take part with whatever p left there;
+ *   - after the scan the cells end+1 .. end of the last vector are NOT re-masked: they hold H[end] - k*E1 and are
+ *     visible to successor rows;
+ *   - vectors beyond the predecessors' last vector are scanned with set_num 1 / 0 (lg_set_f). */
+static void lg_vector_row(orow_t *r, const orow_t *rows, const int *pre, int pre_n, const int *ps_of, const int *srow, const uint8_t *query,
+                          int qlen, int pn, int log_n, int e1) {
+    const int beg = r->beg, end = r->end, beg_sn = beg / pn, end_sn = end / pn, dp_sn = (qlen + 1 + pn - 1) / pn;
+    r->xbeg = beg_sn * pn; r->xend = (end_sn + 1) * pn - 1;
+    const int wd = r->xend - r->xbeg + 1;
+    int *hx = (int *)xm((size_t)wd * sizeof(int));
+    for (int x = 0; x < wd; ++x) hx[x] = NINF;
+    r->hx = hx; r->alloc = hx; r->h = hx + (beg - r->xbeg);
+    int max_pre_end_sn = -1;
+    for (int k = 0; k < pre_n; ++k) { const int es = rows[pre[k]].end / pn; if (es > max_pre_end_sn) max_pre_end_sn = es; }
+    for (int k = 0; k < pre_n; ++k) {
+        const orow_t *p = &rows[pre[k]];
+        const int ps = ps_of ? ps_of[k] : 0;
+        const int pre_beg_sn = p->beg / pn;
+        int _beg_sn, first;
+        if (pre_beg_sn < beg_sn) { _beg_sn = beg_sn; first = xcell(p, beg_sn * pn - 1); }
+        else { _beg_sn = pre_beg_sn; first = NINF; }
+        int _end_sn = (p->end + 1) / pn;
+        if (end_sn < _end_sn) _end_sn = end_sn;
+        if (dp_sn - 1 < _end_sn) _end_sn = dp_sn - 1;
+        for (int j = _beg_sn * pn; j < (_end_sn + 1) * pn; ++j) {
+            const int pm1 = (j == _beg_sn * pn) ? first : xcell(p, j - 1);
+            const int q = (j >= 1 && j <= qlen) ? srow[query[j - 1]] : 0;             /* query profile: qp[.][0] = 0, padding 0 */
+            const int cand = MAX2(addinf(pm1, q + ps), addinf(xcell(p, j), ps - e1));
+            int *c = &hx[j - r->xbeg];
+            *c = (k == 0) ? cand : MAX2(cand, *c);
+        }
+    }
+    for (int j = r->xbeg; j < beg; ++j) hx[j - r->xbeg] = NINF;
+    for (int j = end + 1; j <= r->xend; ++j) hx[j - r->xbeg] = NINF;
+    int first = hx[0];                                                                  /* lane 0 of the first vector */
+    for (int sn = beg_sn; sn <= end_sn; ++sn) {
+        int *F = hx + (sn * pn - r->xbeg);
+        const int set_num = sn > max_pre_end_sn ? (sn == max_pre_end_sn + 1 ? 1 : 0) : pn;
+        F[0] = MAX2(F[0], first);
+        if (sn == end_sn) for (int j = end + 1; j < (end_sn + 1) * pn; ++j) F[j - sn * pn] = NINF;
+        lg_set_f(F, pn, log_n, set_num, e1);
+        first = addinf(F[pn - 1], -e1);
+    }
+}
 
 /* -G path score of an in-edge: reference src/abpoa_graph.c:421-437 */
 static int path_score(const abpoa_graph_t *g, int node_id, int k) {
@@ -98,6 +173,9 @@ int poa_oracle_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int b
     const int w = banded ? abpt->wb + (int)(abpt->wf * qlen) : qlen;               /* :474 */
     const int pn = poa_oracle_score_bits(abpt, qlen, gn) == 16 ? 16 : 8;            /* AVX2 lanes */
     const int np_planes = gap == ABPOA_LINEAR_GAP ? 1 : (gap == ABPOA_AFFINE_GAP ? 3 : 5);
+    /* banded linear gaps outside local mode: the specification IS the reference's vector procedure */
+    const int lg_exact = gap == ABPOA_LINEAR_GAP && mode != ABPOA_LOCAL_MODE && banded;
+    const int log_n = pn == 16 ? 4 : 3;
 
     /* rows reachable from the begin node: reference :1257-1269 */
     uint8_t *live = (uint8_t *)calloc((size_t)g->node_n, 1);
@@ -152,6 +230,7 @@ int poa_oracle_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int b
             }
         }
         cells += wd;
+        if (lg_exact) { r0->hx = r0->h; r0->xbeg = 0; r0->xend = r0->end; }    /* beyond end0 the reference's first row holds -inf (:641-647) */
         if (info && info->row_cb) info->row_cb(info->row_user, 0, r0->beg, r0->end, r0->h, r0->e1, r0->e2, r0->f1, r0->f2);
     }
 
@@ -171,6 +250,14 @@ int poa_oracle_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int b
         }
         r->beg = beg; r->end = end;
         const int wd = end >= beg ? end - beg + 1 : 0;
+        if (lg_exact && wd > 0) {
+            int *ps_of = NULL;
+            if (abpt->inc_path_score) { ps_of = (int *)xm((size_t)MAX2(pre_n[i], 1) * sizeof(int)); for (int k = 0; k < pre_n[i]; ++k) ps_of[k] = path_score(g, id, pre_k[i][k]); }
+            lg_vector_row(r, rows, pre[i], pre_n[i], ps_of, mat + m * nd->base, query, qlen, pn, log_n, e1);
+            free(ps_of);
+            cells += wd;
+            goto row_done;
+        }
         int *buf = (int *)xm((size_t)np_planes * MAX2(wd, 1) * sizeof(int));
         r->h = buf;
         if (np_planes >= 3) { r->e1 = buf + wd; r->f1 = buf + 2 * wd; }
@@ -222,6 +309,7 @@ int poa_oracle_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int b
                 prevT = T;
             }
         }
+row_done:
         if (info && info->row_cb) info->row_cb(info->row_user, i, beg, end, r->h, r->e1, r->e2, r->f1, r->f2);
         /* row maximum, first / last arg-max: reference :1107-1119 */
         int mx = NINF, left = -1, right = -1;
@@ -338,7 +426,7 @@ int poa_oracle_align_sequence_to_subgraph(abpoa_t *ab, abpoa_para_t *abpt, int b
         if (info->dp_beg && info->dp_end)
             for (int i = 0; i < gn - 1 && i < info->band_cap; ++i) { info->dp_beg[i] = rows[i].beg; info->dp_end[i] = rows[i].end; }
     }
-    for (int i = 0; i < gn; ++i) { free(rows[i].h); free(pre[i]); free(pre_k[i]); }
+    for (int i = 0; i < gn; ++i) { free(rows[i].alloc ? rows[i].alloc : (void *)rows[i].h); free(pre[i]); free(pre_k[i]); }
     free(rows); free(pre); free(pre_k); free(pre_n); free(live);
     return 0;
 }
