@@ -109,6 +109,7 @@ int poa_chain_eligible(const abpoa_para_t *abpt) {
     const char *off = getenv("ABPOA_GPU_NO_CHAIN");
     if (off && *off == '1') return 0;
     if (abpt->align_mode != ABPOA_GLOBAL_MODE || abpt->wb < 0) return 0;
+    if (abpt->gap_mode == ABPOA_LINEAR_GAP) return 0;                      /* banded linear gaps: generic kernel only (lane-exact band edges) */
     if (abpt->use_read_ids || abpt->out_msa || abpt->out_gfa || abpt->max_n_cons > 1 || abpt->cons_algrm != ABPOA_HB) return 0;
     if (abpt->use_qv || abpt->amb_strand || abpt->inc_path_score || abpt->zdrop > 0 || abpt->rev_cigar || !abpt->ret_cigar) return 0;
     if (abpt->put_gap_on_right || abpt->put_gap_at_end) return 0;         /* handled by the kernels, but keep the chain on the common configuration */

@@ -246,6 +246,9 @@ void poa_fill_params(PoaParamsDev *p, const abpoa_para_t *abpt, int bits) {
  *   ABPOA_GPU_SLAB_PCT=n    give each job only n % of the estimated plane slab (forces the PLANE_OVF redo) */
 static inline int env_flag(const char *name) { const char *e = getenv(name); return e && *e == '1'; }
 static inline int use_p16_for(const abpoa_para_t *abpt, int qlen, int n_rows) {
+    /* banded linear gaps outside local mode follow the reference's vector procedure lane for lane (band edges depend on its
+     * vector width); only the generic kernel implements that ("lgx" in poa_kernels.cu) */
+    if (abpt->gap_mode == ABPOA_LINEAR_GAP && abpt->align_mode != ABPOA_LOCAL_MODE && abpt->wb >= 0) return 0;
     if (env_flag("ABPOA_GPU_NO_P16")) return 0;
     if (env_flag("ABPOA_GPU_FORCE_P16")) return abpt->max_mat <= 1000 && abpt->min_mis <= 1000;
     return poa_p16_ok(abpt, qlen, n_rows);

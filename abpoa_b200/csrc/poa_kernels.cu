@@ -135,14 +135,16 @@ template <typename ST> struct BtRow {
     const ST *ptr;                /* &H[row][0] (virtual: only cells beg..end exist)          */
     int pstride;                  /* elements between planes of the row                      */
     __device__ __forceinline__ bool has(int j) const { return j >= beg && j <= end; }      /* empty for end < beg (no candidate) */
-    __device__ __forceinline__ void locate(const ST *planes) {
-        const int g0 = beg >> 3;
-        pstride = ((end >> 3) - g0 + 1) * POA_GROUP;
+    /* xs: log2 of the storage granule of a row -- 3 (the 8-cell grid) everywhere except banded linear-gap rows of the
+     * generic kernel, which store whole reference vectors (16 / 8 cells) around the band (see "lgx" below) */
+    __device__ __forceinline__ void locate(const ST *planes, int xs = 3) {
+        const int g0 = ((beg >> xs) << xs) >> 3, g1 = ((((end >> xs) + 1) << xs) - 1) >> 3;
+        pstride = (g1 - g0 + 1) * POA_GROUP;
         ptr = planes + ((ptrdiff_t)off - g0) * POA_GROUP;
     }
 };
 template <typename ST>
-__device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, const ST *planes, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row) {
+__device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, const ST *planes, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row, int xs = 3) {
     r.row = row;
     const PoaRowInfo pi = rowinfo[row];
     const uint32_t off = rowoff[row];
@@ -152,7 +154,7 @@ __device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, con
     r.pb = m0.x; r.np = nx - m0.x; r.base = m0.y & 0xff;
     r.p0 = r.np > 0 ? ldb(jv.pred + r.pb) : -1;
     r.p1 = r.np > 1 ? ldb(jv.pred + r.pb + 1) : -1;
-    r.locate(planes);
+    r.locate(planes, xs);
 }
 
 struct CigarSink {
@@ -172,7 +174,7 @@ struct CigarSink {
 
 template <int GAP, typename ST, int MODE>
 __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const PoaParamsDev *prm, const int *mat_s,
-                              int lane, int best_i, int best_j, PoaResultDev &res) {
+                              int lane, int best_i, int best_j, PoaResultDev &res, int xs = 3) {
     typedef Planes<GAP> PL;
     const ST *planes = reinterpret_cast<const ST *>(jd.planes);
     const PoaRowInfo *rowinfo = jd.rowinfo; const uint32_t *rowoff = jd.rowoff;
@@ -186,7 +188,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     int gap_at_end = prm->put_gap_at_end; const int gap_on_right = prm->put_gap_on_right;
     if (best_j < qlen) cg.ins(qlen - best_j, qlen - 1);
 
-    BtRow<ST> me; bt_load_row<ST>(me, jv, planes, rowinfo, rowoff, i);
+    BtRow<ST> me; bt_load_row<ST>(me, jv, planes, rowinfo, rowoff, i, xs);
     BtRow<ST> pc; pc.row = -1; pc.beg = 0; pc.end = -1; pc.ptr = planes; pc.pstride = 0;
     int pc_ps = 0;
     bool cand_loaded = false;
@@ -215,7 +217,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         me.off = __shfl_sync(FULL, src.off, sel); me.pb = __shfl_sync(FULL, src.pb, sel);
         const int nb = __shfl_sync(FULL, (src.np << 8) | src.base, sel); me.np = nb >> 8; me.base = nb & 0xff;
         me.p0 = __shfl_sync(FULL, src.p0, sel); me.p1 = __shfl_sync(FULL, src.p1, sel);
-        me.locate(planes);
+        me.locate(planes, xs);
         i = me.row; cand_loaded = false;
         scout_sync(i);
     };
@@ -223,7 +225,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     auto load_chunk = [&](BtRow<ST> &px, int &px_ps, int kb) {
         px.row = -1; px.beg = 0; px.end = -1; px.ptr = planes; px.pstride = 0; px_ps = 0;
         if (kb + lane < me.np) {
-            bt_load_row<ST>(px, jv, planes, rowinfo, rowoff, ldb(jv.pred + me.pb + kb + lane));
+            bt_load_row<ST>(px, jv, planes, rowinfo, rowoff, ldb(jv.pred + me.pb + kb + lane), xs);
             if (has_ps) px_ps = ldb(jv.predscore + me.pb + kb + lane);
         }
     };
@@ -239,7 +241,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
             pc.row = -1; pc.beg = 0; pc.end = -1; pc_ps = 0;
             if (lane < np) {
                 const int prow = lane == 0 ? me.p0 : (lane == 1 ? me.p1 : ldb(jv.pred + me.pb + lane));
-                bt_load_row<ST>(pc, jv, planes, rowinfo, rowoff, prow);
+                bt_load_row<ST>(pc, jv, planes, rowinfo, rowoff, prow, xs);
                 if (has_ps) pc_ps = ldb(jv.predscore + me.pb + lane);
             }
             cand_loaded = true;
@@ -257,7 +259,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
             s_p0 = snx > sm.x ? ldb(jv.pred + sm.x) : 0;
             const int jp = j - s_ahead - 1;
             if (si.end >= si.beg) {
-                const ST *sp = planes + ((ptrdiff_t)so - (si.beg >> 3)) * POA_GROUP;
+                const ST *sp = planes + ((ptrdiff_t)so - (((si.beg >> xs) << xs) >> 3)) * POA_GROUP;
                 const int ja = min(max(jp - 16, si.beg), si.end), jb = min(max(jp + 8, si.beg), si.end);
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + ja));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + jb));
@@ -412,6 +414,18 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
     const int pnv = jv.pn;
     const int zr = prm->zero;            /* run-time 0: keeps ptxas from fusing the LOCAL floors into VIMNMX.RELU */
+    /* "lgx": banded linear gaps outside local mode.  There the specification is the reference's VECTOR procedure
+     * (simd_abpoa_lg_dp, src/abpoa_align_simd.c:727-815), whose band edges depend on the vector width
+     * pn (16 lanes for int16 scores, 8 for int32):
+     *   - a row is stored in whole vectors around its band, xbeg = beg/pn*pn .. xend = (end/pn+1)*pn-1;
+     *   - the cells end+1 .. xend are not re-masked after the scan, they hold H[end] - k*E1 and successors see them;
+     *   - predecessor p contributes to the cells of vectors <= (p.end+1)/pn only;
+     *   - vectors beyond V1 = max_p(p.end/pn) + 1 are scanned incompletely (SIMD_SET_F with set_num 0): in vector
+     *     V1 + 1 only the even lanes receive the running value, later vectors nothing.
+     * The scalar oracle (oracle/poa_oracle.c: lg_vector_row, lg_set_f) restates that procedure lane by lane; the closed
+     * form used here is pinned against it and against the live reference by the banded linear-gap sweeps in tests/. */
+    const bool lgx = GAP == LG && MODE != LOCAL && banded;
+    const int xs = lgx ? (pnv == 16 ? 4 : 3) : 3;         /* log2 of a row's storage granule */
 
     PoaResultDev res;
     res.status = POA_ST_OK; res.best_score = NEG; res.best_i = 0; res.best_j = 0; res.n_ops = 0;
@@ -427,7 +441,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     {
         int end0 = qlen;
         if (banded) end0 = min(qlen, max(0, qlen - jv.remain(0)) + w);
-        const int g1 = end0 >> 3, ngrp = g1 + 1;
+        const int g1 = ((((end0 >> xs) + 1) << xs) - 1) >> 3, ngrp = g1 + 1;
         if ((uint64_t)ngrp * PL::N > jd.plane_cap_units) { if (lane == 0) { res.status = POA_ST_PLANE_OVF; *jd.result = res; signal_done(jd); } return; }
         for (int gp = 0; gp <= g1; gp += 32) {
             const int g = gp + lane;
@@ -486,15 +500,15 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
 
         /* lane k holds predecessor k (chunk 0); band hints are reductions over all of them */
         int pk_row = -1, pk_beg = 0, pk_end = -1, pk_ps = 0; uint32_t pk_off = 0;
-        int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
+        int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX, max_pre_end = -1;
         for (int kb = 0; kb < np; kb += 32) {
             const int k = kb + lane;
-            int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX;
+            int l1 = INT32_MAX, r1 = INT32_MIN, b1 = INT32_MAX, e1x = -1;
             if (k < np) {
                 const int prow = kb == 0 ? mypred : ldb(jv.pred + pb + k);
                 const bool near = (i - prow) <= rmask;
                 const PoaRowInfo pi = near ? ring_info[prow & rmask] : rowinfo[prow];
-                l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg;
+                l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg; e1x = pi.end;
                 if (kb == 0) {
                     pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_ps = myps;
                     pk_off = near ? ring_off[prow & rmask] : rowoff[prow];
@@ -504,6 +518,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 ml = min(ml, __reduce_min_sync(FULL, l1));
                 mr = max(mr, __reduce_max_sync(FULL, r1));
                 min_pre_beg = min(min_pre_beg, __reduce_min_sync(FULL, b1));
+                if (lgx) max_pre_end = max(max_pre_end, __reduce_max_sync(FULL, e1x));
             }
         }
         int beg = 0, end = qlen;
@@ -513,7 +528,8 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             end = min(qlen, max(mr, r) + w);
             if (np > 0 && beg / pnv < min_pre_beg / pnv) beg = min_pre_beg;      /* reference's vector-granular clamp */
         }
-        const int g0 = beg >> 3, g1 = end >> 3, ngrp = g1 - g0 + 1;
+        const int g0 = ((beg >> xs) << xs) >> 3, g1 = ((((end >> xs) + 1) << xs) - 1) >> 3, ngrp = g1 - g0 + 1;
+        const int lgx_v1 = lgx ? (max_pre_end >> xs) + 1 : 0;                 /* last vector with a complete scan */
         if (cursor + (uint64_t)ngrp * PL::N > jd.plane_cap_units || cursor + (uint64_t)ngrp * PL::N > 0xffffffffull) {
             if (lane == 0) { res.status = POA_ST_PLANE_OVF; res.plane_units_used = cursor; *jd.result = res; signal_done(jd); }
             return;
@@ -553,7 +569,8 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                     const int p_beg = __shfl_sync(FULL, c_beg, k), p_end = __shfl_sync(FULL, c_end, k);
                     const uint32_t p_off = __shfl_sync(FULL, c_off, k);
                     const int ps = jv.predscore ? __shfl_sync(FULL, c_ps, k) : 0;
-                    const int pg0 = p_beg >> 3, pg1 = p_end >> 3, png = pg1 - pg0 + 1;
+                    const int pg0 = ((p_beg >> xs) << xs) >> 3, pg1 = ((((p_end >> xs) + 1) << xs) - 1) >> 3, png = pg1 - pg0 + 1;
+                    const int p_vlim = lgx ? ((((p_end + 1) >> xs) + 1) << xs) : INT32_MAX;      /* lgx: p feeds cells j < p_vlim only */
                     const bool near = (i - p_row) <= rmask;
                     const ST *ph = planes + (size_t)p_off * POA_GROUP;                       /* HBM copy   */
                     const ST *rh = ring_data + (size_t)(p_row & rmask) * RN * ring_cells;    /* smem copy  */
@@ -578,12 +595,21 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                         if (relm >= 0 && relm < png) hm1 = (near && relm < ring_groups) ? (int)rh[(size_t)relm * POA_GROUP + 7] : (int)ph[(size_t)relm * POA_GROUP + 7];
                         if (MODE == LOCAL && g == 0) hm1 = 0;
                     }
+                    if (GAP == LG && lgx) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (g * 8 + c < p_vlim) { M[c] = max(M[c], (c == 0 ? hm1 : hp[c - 1]) + ps); X1[c] = max(X1[c], hp[c] - e1 + ps); }
+                        }
+                    } else {
                     M[0] = max(M[0], hm1 + ps);
 #pragma unroll
                     for (int c = 1; c < 8; ++c) M[c] = max(M[c], hp[c - 1] + ps);
+                    }
                     if (GAP == LG) {
+                        if (!lgx) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) X1[c] = max(X1[c], hp[c] - e1 + ps);
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) X1[c] = max(X1[c], ep1[c] + ps);
@@ -638,6 +664,13 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                     x1 = max(x1, a1[c]);                    /* inclusive: H[j] = max(H0[j], H[j-1]-e) */
                     int h = max(x1 - e1 * jr, NEG);
                     if (MODE == LOCAL) h = max(h, zr);
+                    if (lgx) {                              /* stored cell of the row's vectors: the running value survives to the right of
+                                                               `end`; beyond the last completely scanned vector only even lanes of the next one */
+                        const int v = j >> xs;
+                        const bool keep = active && j >= beg && j <= ((((end >> xs) + 1) << xs) - 1) &&
+                                          (v <= lgx_v1 || (v == lgx_v1 + 1 && !(j & 1)));
+                        H[c] = keep ? h : NEG;
+                    } else
                     H[c] = inb[c] ? h : NEG;
                 } else {
                     const int f1 = max(x1 - e1 * (jr - 1), NEG);
@@ -724,7 +757,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             const int prow = jv.pred[sb + k];
             const PoaRowInfo pi = rowinfo[prow];
             const int endc = qlen > pi.end ? pi.end : qlen;
-            const int pg0 = pi.beg >> 3;
+            const int pg0 = ((pi.beg >> xs) << xs) >> 3;
             const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow] * POA_GROUP + (endc - pg0 * 8)] : NEG;
             if (v > best_score) { best_score = v; best_i = prow; best_j = endc; }
         }
@@ -736,7 +769,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     if (lane == 0) *jd.result = res;
     __syncwarp();
     if (prm->ret_cigar) {
-        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result, xs);
         if (lane == 0) jd.result->bt_clk = clock64() - clk1;
     }
     if (lane == 0) signal_done(jd);

@@ -276,3 +276,30 @@ def test_subgraph_alignment(product_lib, reference_lib, path_score):
         assert x[5] == y[5], f"read {i}: ends"
     assert all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))
     assert len(a[2]) == len(b[2]) and all(np.array_equal(x, y) for x, y in zip(a[2], b[2]))
+
+
+# ------------------------------------------------------------------------------------------- a7: banded linear gaps, lane-exact
+@pytest.mark.parametrize("mode", [0, 2])
+def test_linear_banded_lane_exact_sweep(product_lib, reference_lib, mode):
+    """Banded linear-gap alignment (global and extend): the specification is the reference's vector procedure (SURVEY 8a a7:
+    leaked cells right of `end`, vector-granular predecessor reads, incomplete scans beyond the predecessors' last vector).
+    Sweep of group shapes, error rates (3-25 %) and band widths: every score, graph-CIGAR word, end point AND the DP-cell
+    count (= the band of every row) must equal the live reference."""
+    from cases import LINEAR
+    n_aln = 0
+    for seed in range(60):
+        reads = synth.make_group(5000 + seed, 4 + seed % 5, 150 + 37 * (seed % 9), [0.03, 0.08, 0.15, 0.25][seed % 4])
+        cfg = PoaConfig(align_mode=mode, **LINEAR) if seed % 2 == 0 else PoaConfig(align_mode=mode, wb=6 + seed % 7, wf=0.01, **LINEAR)
+        a = run_group(product_lib, cfg, reads)
+        b = run_group(reference_lib, cfg, reads)
+        assert_group_equal(a, b, f"linear banded mode {mode} seed {seed}")
+        n_aln += sum(1 for x in a["alns"] if x.aligned)
+    assert n_aln >= 250
+
+
+def test_linear_banded_int32_width(product_lib, reference_lib):
+    """The same with scores that make the reference pick int32 (vectors of 8 lanes instead of 16)."""
+    cfg = PoaConfig(match=20, mismatch=40, gap_open1=0, gap_ext1=20, gap_open2=0, gap_ext2=0, wb=8)
+    for seed in range(6):
+        reads = synth.make_group(5100 + seed, 6, 1800, 0.10)
+        assert_group_equal(run_group(product_lib, cfg, reads), run_group(reference_lib, cfg, reads), f"linear banded int32 seed {seed}")

@@ -37,13 +37,10 @@ def check(reference_lib, cfg, groups, expect_chain=None, expect_fallback=None, *
     return st
 
 
-@pytest.mark.parametrize("gap", ["convex", "affine", "linear"])
+@pytest.mark.parametrize("gap", ["convex", "affine"])
 def test_chain_many_groups(reference_lib, gap):
-    kw = {} if gap == "convex" else (AFFINE if gap == "affine" else dict(gap_open1=0, gap_ext1=2, gap_open2=0, gap_ext2=0))
+    kw = {} if gap == "convex" else AFFINE
     groups = [synth.make_group(5000 + g, 6 + g % 5, 300 + 40 * (g % 7), 0.04 + 0.01 * (g % 6)) for g in range(40)]
-    if gap == "linear":
-        # banded global linear-gap: the DP-cell count is the documented a7 deviation, compared elsewhere
-        pytest.skip("banded global linear-gap cell counts: see test_linear_banded_*")
     check(reference_lib, PoaConfig(**kw), groups, expect_chain=40, expect_fallback=0)
 
 
