@@ -342,6 +342,21 @@ def main():
     # mode) keep the replay of all captured alignment jobs.
     value = chain_cells / (chain_ms / 1e3) / 1e9 if used_chain else kernel_only_gcups
 
+    # N > 1: exercise the scatter -> compute -> gather path itself (abpoa_b200.parallel.distributed_msa: packed reads scattered
+    # from rank 0 and packed consensus gathered back as uint8 tensors over NCCL) on a small set, outside the timed region
+    dist_check = None
+    if world > 1:
+        from abpoa_b200.parallel import distributed_msa
+        small = w.groups(8 * world, base_seed=900000)
+        small = [[r[: min(len(r), 1500)] for r in g[: min(len(g), 10)]] for g in small]
+        run_here = lambda c_, gs: [list(r.cons) + list(r.cov) for r in eng.run(c_, gs)]
+        got = distributed_msa(small if rank == 0 else None, w.cfg, runner=run_here)
+        if rank == 0:
+            import numpy as np
+            local = run_here(w.cfg, small)
+            same = sum(1 for a, b in zip(got, local) if len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)))
+            dist_check = {"groups": len(small), "identical_to_single_rank": same, "backend": dist.get_backend(), "ranks": world}
+
     # parity sample: consensus of the first groups of rank 0 against the reference's (computed in the cpu_baseline leg)
     sample_cons = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -417,7 +432,7 @@ def main():
                 "engine": "device-resident chain (align + fuse kernels per round, host only for upload / final consensus)" if used_chain
                           else "launch engine: pipelined launches, one per half-chunk round, host graph fusion"},
         "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "chain": chain,
+        "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "chain": chain, "distributed_check": dist_check,
         "kernel_only": {"ms_per_pass": rp["kernel_ms"], "ms_min": rp["kernel_ms_min"], "jobs": rp["n_jobs"], "cells": rp["cells"], "hbm_resident_input_bytes": rp["input_bytes"],
                         "gcups": kernel_only_gcups},
     }))
