@@ -1,12 +1,10 @@
 """ctypes view of the abpoa.h C ABI (include/abpoa.h; reference include/abpoa.h:58-230).
 
-The same Structure definitions bind BOTH shared objects that export this ABI:
-
-* ``abpoa_b200/lib/libabpoa_b200.so`` -- the product: host C + sm_100a CUDA kernels;
-* ``oracle/_ref/libabpoa_ref.so``     -- the unmodified reference built by ``oracle/Makefile``
-  (test infrastructure only).
-
-so a parity test is literally "run the same calls through two libraries and compare".
+The Structure definitions bind ANY shared object that exports this ABI: the product
+(``abpoa_b200/lib/libabpoa_b200.so``: host C + sm_100a CUDA kernels) through ``product()``, and -- from the
+test suite and the benchmark's reference arm only, which locate it themselves -- the unmodified reference
+built by ``oracle/Makefile``, through ``load_library(path)``; a parity test is literally "run the same calls
+through two libraries and compare".  Nothing in this package knows where the reference lives.
 Nothing in this module computes alignments; it only marshals arguments.
 """
 from __future__ import annotations
@@ -17,7 +15,6 @@ from pathlib import Path
 
 REPO_ROOT = Path(__file__).resolve().parent.parent
 PRODUCT_LIB = REPO_ROOT / "abpoa_b200" / "lib" / "libabpoa_b200.so"
-REFERENCE_LIB = REPO_ROOT / "oracle" / "_ref" / "libabpoa_ref.so"
 
 # constants of include/abpoa.h
 ABPOA_GLOBAL_MODE, ABPOA_LOCAL_MODE, ABPOA_EXTEND_MODE = 0, 1, 2
@@ -218,7 +215,3 @@ def product() -> PoaLibrary:
     override = os.environ.get("ABPOA_B200_LIB")          # experiments: another build of the same library
     return load_library(Path(override) if override else PRODUCT_LIB)
 
-
-def reference() -> PoaLibrary:
-    """The unmodified reference (oracle/_ref).  TEST INFRASTRUCTURE ONLY."""
-    return load_library(REFERENCE_LIB)

@@ -106,7 +106,7 @@ def _ref_worker(args):
     from abpoa_b200 import capi, synth
     from abpoa_b200.aligner import PoaSession
     w = synth.WORKLOADS[wname]
-    lib = capi.reference()
+    lib = capi.load_library(ROOT / "oracle" / "_ref" / "libabpoa_ref.so")     # the unmodified reference (oracle/Makefile)
     cells = 0
     reads_done = 0
     groups = [synth.make_group(seed, n_reads, length, w.err, w.cfg.m) for seed in seeds]     # outside the timed window

@@ -22,9 +22,12 @@ def product_lib():
     return capi.product()
 
 
+REFERENCE_LIB = ROOT / "oracle" / "_ref" / "libabpoa_ref.so"      # the unmodified reference, built by oracle/Makefile
+
+
 @pytest.fixture(scope="session")
 def reference_lib():
     from abpoa_b200 import capi
-    if not capi.REFERENCE_LIB.exists():
+    if not REFERENCE_LIB.exists():
         pytest.skip("oracle/_ref/libabpoa_ref.so not built (reference tree absent and no prebuilt copy)")
-    return capi.reference()
+    return capi.load_library(REFERENCE_LIB)

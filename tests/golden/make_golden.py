@@ -29,7 +29,7 @@ def sha(a) -> str:
 
 
 def main():
-    ref = capi.reference()
+    ref = capi.load_library(Path(__file__).resolve().parents[2] / "oracle" / "_ref" / "libabpoa_ref.so")
     out = {"reference": "abPOA v1.5.6 (make avx2=1 flags), built by oracle/Makefile", "cases": {}, "cli_md5": {}}
     for name, case in CASES.items():
         cfg = PoaConfig(**case["cfg"])

@@ -8,6 +8,7 @@ import numpy as np
 from abpoa_b200.aligner import PoaConfig, PoaSession, encode
 
 INPUTS = Path(__file__).resolve().parent / "golden" / "inputs"
+REFERENCE_LIB = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libabpoa_ref.so"
 
 
 def read_fasta(path: Path, m: int = 5) -> list[np.ndarray]:
@@ -121,7 +122,7 @@ def _ref_records_worker(args):
     cfg_kw, reads, want_msa = args
     from abpoa_b200 import capi
     from abpoa_b200.batch import fnv1a_words
-    r = run_group(capi.load_library(capi.REFERENCE_LIB), PoaConfig(**cfg_kw), reads, want_msa=want_msa)
+    r = run_group(capi.load_library(REFERENCE_LIB), PoaConfig(**cfg_kw), reads, want_msa=want_msa)
     return {
         "score": [a.best_score if a.aligned else 0 for a in r["alns"]],
         "n_cigar": [len(a.cigar) for a in r["alns"]],

@@ -27,7 +27,7 @@ def _record(args):
     name, gi = args
     w = synth.WORKLOADS[name]
     reads = w.groups(gi + 1)[gi]
-    with PoaSession(w.cfg, capi.reference()) as s:
+    with PoaSession(w.cfg, capi.load_library(Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "libabpoa_ref.so")) as s:
         alns = s.run_reads(reads, count_cells=False)
     return [a.cigar for a in alns]
 
