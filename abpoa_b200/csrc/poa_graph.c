@@ -640,6 +640,27 @@ static int splice_order(abpoa_graph_t *abg) {
     return 1;
 }
 
+/* ABPOA_GPU_CHECK_ORDER=1 (tests): after a splice, verify what the splice relies on -- every edge points forward in the
+ * order and the members of every aligned group occupy consecutive rows -- instead of letting a violation show up as parity drift. */
+static void check_spliced_order(const abpoa_graph_t *abg) {
+    const poa_graph_x *x = cgx(abg);
+    const int n = abg->node_n;
+    for (int v = 0; v < n; ++v) {
+        const int ne = x->cout[v]; const int *oid = out_ids_of(x, v);
+        for (int e = 0; e < ne; ++e)
+            if (abg->node_id_to_index[v] >= abg->node_id_to_index[oid[e]])
+                poa_die(__func__, "spliced order: edge %d -> %d points backwards (rows %d -> %d)", v, oid[e], abg->node_id_to_index[v], abg->node_id_to_index[oid[e]]);
+        const int na = x->caln[v];
+        if (na) {
+            const int *al = na <= POA_INL ? x->aln4 + (size_t)v * POA_INL : abg->node[v].aligned_node_id;
+            int lo = abg->node_id_to_index[v], hi = lo;
+            for (int a = 0; a < na; ++a) { const int r = abg->node_id_to_index[al[a]]; if (r < lo) lo = r; if (r > hi) hi = r; }
+            if (hi - lo != na) poa_die(__func__, "spliced order: aligned group of node %d spans rows %d..%d for %d members", v, lo, hi, na + 1);
+        }
+    }
+    for (int i = 0; i < n; ++i) if (abg->node_id_to_index[abg->index_to_node_id[i]] != i) poa_die(__func__, "spliced order: index arrays are not inverse at row %d", i);
+}
+
 void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
     if (abg->node_n <= 0) { fprintf(stderr, "[%s] Empty graph.\n", __func__); return; }
     const int n = abg->node_n;
@@ -651,6 +672,7 @@ void abpoa_topological_sort(abpoa_graph_t *abg, abpoa_para_t *abpt) {
         if (x->tracking) {
             spliced = splice_order(abg);
             if (spliced) x->n_spliced += 1; else x->n_splice_fallback += 1;
+            if (spliced) { static int check = -1; if (check < 0) { const char *e = getenv("ABPOA_GPU_CHECK_ORDER"); check = e && *e == '1'; } if (check) check_spliced_order(abg); }
             x->tracking = 0;
         }
         if (!spliced) abpoa_BFS_set_node_index(abg, ABPOA_SRC_NODE_ID, ABPOA_SINK_NODE_ID);

@@ -8,8 +8,11 @@ from pathlib import Path
 
 import pytest
 
+import os
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+os.environ.setdefault("ABPOA_GPU_CHECK_ORDER", "1")     # the whole suite runs with the spliced-order invariants asserted (poa_graph.c)
 
 
 def pytest_configure(config):
