@@ -114,7 +114,7 @@ int main(int argc, char **argv) {
         abpoa_free(ab);
     } else {
         extern int poa_read_fastx(const char *fn, abpoa_seq_t *abs);
-        extern char ab_char26_table[256];
+        extern void poa_encode_residues(const char *s, int l, uint8_t *out);
         FILE *lf = fopen(argv[optind], "r");
         if (!lf) { fprintf(stderr, "Failed to open the list file %s\n", argv[optind]); return 1; }
         int n_groups = 0, cap = 0; cli_group *gr = NULL;
@@ -138,7 +138,7 @@ int main(int argc, char **argv) {
                 g->names[i] = strdup(abs->name[i].l > 0 ? abs->name[i].s : "");
                 g->lens[i] = sl;
                 g->seqs[i] = (uint8_t *)malloc((size_t)(sl > 0 ? sl : 1));
-                for (int j = 0; j < sl; ++j) g->seqs[i][j] = (uint8_t)ab_char26_table[(int)(unsigned char)abs->seq[i].s[j]];
+                poa_encode_residues(abs->seq[i].s, sl, g->seqs[i]);
                 if (abpt->use_qv && abs->qual[i].l > 0) {
                     g->weights[i] = (int *)malloc((size_t)(sl > 0 ? sl : 1) * sizeof(int));
                     for (int j = 0; j < sl; ++j) g->weights[i][j] = (int)abs->qual[i].s[j] - 32;

@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_seed_kernel(PoaChainSlo
     chain_seed(&slots[blockIdx.x], cp);
 }
 
-__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_kernel(PoaChainSlot *slots, const int32_t *idx, const PoaChainParams *cp, int n) {
+__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_kernel(PoaChainSlot *slots, const int32_t *idx, const PoaChainParams *cp, int n, int round) {
     if ((int)blockIdx.x >= n) return;
-    chain_fuse(&slots[idx[blockIdx.x]], cp);
+    chain_fuse(&slots[idx[blockIdx.x]], cp, round);
 }
 
 /* Compact export of the final graphs (layout: poa_graph_import in poa_graph.c).  ex_off[g] = first int32 word of
@@ -135,6 +135,27 @@ struct Cohort {
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+/* Pinned staging buffers are kept for the life of the process (grow-only, one per purpose): cudaHostAlloc / cudaFreeHost of
+ * half a gigabyte per batch call cost ~0.2 s, more than the copies they serve. */
+struct PinnedSlot { void *p = NULL; size_t cap = 0; bool busy = false; };
+std::mutex g_pin_mu; PinnedSlot g_pin[4];
+void *pinned_get(int which, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    PinnedSlot &ps = g_pin[which];
+    if (ps.busy) { void *q = NULL; CK(cudaHostAlloc(&q, bytes ? bytes : 1, cudaHostAllocPortable)); return q; }      /* concurrent caller: private buffer */
+    if (bytes > ps.cap) {
+        if (ps.p) CK(cudaFreeHost(ps.p));
+        ps.cap = bytes + bytes / 4 + 4096;
+        CK(cudaHostAlloc(&ps.p, ps.cap, cudaHostAllocPortable));
+    }
+    ps.busy = true;
+    return ps.p;
+}
+void pinned_put(int which, void *q) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (q == g_pin[which].p) g_pin[which].busy = false; else CK(cudaFreeHost(q));
+}
+
 }  // namespace
 
 /* Run the groups listed in `todo` (eligible ones) through the device chain.  Groups that could not be
@@ -151,6 +172,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
     const int P = abpt->gap_mode == ABPOA_LINEAR_GAP ? 1 : (abpt->gap_mode == ABPOA_AFFINE_GAP ? 3 : 5);
     int n_cohorts = [&] { const char *e = getenv("ABPOA_GPU_CHAIN_COHORTS"); return e && *e ? atoi(e) : 4; }();
     if (n_cohorts < 1) n_cohorts = 1;
+    if (n_cohorts > 16) n_cohorts = 16;
 
     /* ---- per-group sizes ---- */
     std::vector<GroupPlan> plans;
@@ -217,13 +239,13 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         PoaChainSlot *d_slots = (PoaChainSlot *)dtake((size_t)nw * sizeof(PoaChainSlot));
         PoaChainParams *d_cp = (PoaChainParams *)dtake(sizeof(PoaChainParams));
         PoaParamsDev *d_prm = (PoaParamsDev *)dtake(sizeof(PoaParamsDev));
-        unsigned long long *d_cursors = (unsigned long long *)dtake((size_t)n_cohorts * 2 * sizeof(unsigned long long));
+        unsigned long long *d_cursors = (unsigned long long *)dtake((size_t)32 * sizeof(unsigned long long));       /* 2 per cohort, <= 16 cohorts */
 
         /* pinned staging: slots | params | reads + offsets + w of every group | round index lists */
         std::vector<PoaChainSlot> hs((size_t)nw);
         size_t reads_bytes = 0;
         for (int t = 0; t < nw; ++t) reads_bytes += al256((size_t)plans[pos + t].bases) + al256(((size_t)plans[pos + t].n_reads + 1) * 4) + al256((size_t)plans[pos + t].n_reads * 4);
-        uint8_t *h_reads = NULL; CK(cudaHostAlloc((void **)&h_reads, reads_bytes + 256, cudaHostAllocDefault));
+        uint8_t *h_reads = (uint8_t *)pinned_get(0, reads_bytes + 256);
         uint8_t *d_reads = dtake(reads_bytes);
         size_t roff = 0;
         int max_reads = 0, band_cells = 64;
@@ -265,13 +287,22 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             if (p.n_reads > max_reads) max_reads = p.n_reads;
         }
         /* round index lists per cohort: wave-local slot indices of the groups that still have a read r */
-        std::vector<Cohort> coh((size_t)std::min(n_cohorts, nw));
+        /* cohorts: each cohort's alignment kernel is one CTA (warp) per group; with at most one CTA per SM per cohort the
+         * concurrently running kernels of all cohorts load every SM alike (a 250-CTA grid next to three more would put
+         * twice as many warps on the first 102 SMs as on the rest, and a round ends when its slowest warp does) */
+        int sm_count = 148; { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) sm_count = pr.multiProcessorCount; }
+        const int auto_cohorts = std::max(1, std::min(16, (nw + sm_count - 1) / sm_count));
+        const int use_cohorts = getenv("ABPOA_GPU_CHAIN_COHORTS") ? n_cohorts : auto_cohorts;
+        std::vector<Cohort> coh((size_t)std::min(use_cohorts, nw));
         for (int t = 0; t < nw; ++t) coh[(size_t)t % coh.size()].members.push_back(t);
         std::vector<int32_t> h_idx; std::vector<std::vector<std::pair<size_t, int>>> round_of(coh.size());   /* (offset into h_idx, count) per round */
+        /* a group that has to re-run an alignment (band wider than its plane slab) falls one round behind the schedule:
+         * every group stays listed EXTRA rounds beyond its last read (slots with nothing to do return at once) */
+        const int EXTRA = 2, n_rounds = max_reads - 1 + EXTRA;
         for (size_t c = 0; c < coh.size(); ++c)
-            for (int r = 1; r < max_reads; ++r) {
+            for (int r = 1; r <= n_rounds; ++r) {
                 const size_t o = h_idx.size(); int cnt = 0;
-                for (int t : coh[c].members) if (plans[pos + t].n_reads > r) { h_idx.push_back(t); ++cnt; }
+                for (int t : coh[c].members) if (plans[pos + t].n_reads + EXTRA > r) { h_idx.push_back(t); ++cnt; }
                 round_of[c].push_back({o, cnt});
             }
         int32_t *d_idx = (int32_t *)dtake(std::max<size_t>(h_idx.size(), 1) * 4);
@@ -287,7 +318,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         doff = al256(doff);
         if (doff > total) poa_die("libabpoa_b200/chain", "wave layout (%zu bytes) exceeds the arena (%zu bytes)", doff, total);
         if (doff + (size_t)ex_words * 4 + (32 << 20) > total) {       /* cannot happen with the wave sizing above; be safe */
-            poa_arena_return(arena, d_base, total); CK(cudaFreeHost(h_reads));
+            poa_arena_return(arena, d_base, total); pinned_put(0, h_reads);
             for (int t = 0; t < nw; ++t) fallback.push_back(plans[pos + t].g);
             pos = end; continue;
         }
@@ -320,7 +351,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         CK(cudaMemcpyAsync(d_idx, h_idx.data(), h_idx.size() * 4, cudaMemcpyHostToDevice, s0));
         CK(cudaMemcpyAsync(d_exoff, h_exoff.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, s0));
         CK(cudaMemcpyAsync(d_excap, h_excap.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, s0));
-        CK(cudaMemsetAsync(d_cursors, 0, (size_t)n_cohorts * 2 * sizeof(unsigned long long), s0));
+        CK(cudaMemsetAsync(d_cursors, 0, (size_t)32 * sizeof(unsigned long long), s0));
         const uint64_t h2d = reads_bytes + (uint64_t)nw * sizeof(PoaChainSlot) + sizeof hcp + sizeof hprm + h_idx.size() * 4 + (uint64_t)nw * 12;
         /* timed region of the device work: inputs are resident when ev_t0 fires */
         CK(cudaEventRecord(ev_t0, s0));
@@ -335,7 +366,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         for (size_t c = 0; c < coh.size(); ++c) {
             cudaStream_t st = coh[c].st;
             if (c > 0) CK(cudaStreamWaitEvent(st, ev_up, 0));
-            for (int r = 1; r < max_reads; ++r) {
+            for (int r = 1; r <= n_rounds; ++r) {
                 const std::pair<size_t, int> &ro = round_of[c][(size_t)r - 1];
                 if (ro.second == 0) break;
                 cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
@@ -343,7 +374,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                 CK(cudaEventRecord(e0, st));
                 CK(poa_launch_chain_align_p16(abpt->gap_mode, gaps, d_slots, d_idx + ro.first, ro.second, r, d_prm, ring_rows, ring_cells, st));
                 CK(cudaEventRecord(e1, st));
-                poa_chain_fuse_kernel<<<ro.second, POA_CHAIN_T, 0, st>>>(d_slots, d_idx + ro.first, d_cp, ro.second);
+                poa_chain_fuse_kernel<<<ro.second, POA_CHAIN_T, 0, st>>>(d_slots, d_idx + ro.first, d_cp, ro.second, r);
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(e2, st));
                 launches += 2;
@@ -366,7 +397,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         CK(cudaGetLastError());
         ++launches;
         std::vector<PoaChainSlot> fin((size_t)nw);
-        PoaChainSlot *h_fin = NULL; CK(cudaHostAlloc((void **)&h_fin, (size_t)nw * sizeof(PoaChainSlot), cudaHostAllocDefault));
+        PoaChainSlot *h_fin = (PoaChainSlot *)pinned_get(1, (size_t)nw * sizeof(PoaChainSlot));
         CK(cudaMemcpyAsync(h_fin, d_slots, (size_t)nw * sizeof(PoaChainSlot), cudaMemcpyDeviceToHost, s0));
         CK(cudaStreamSynchronize(s0));
         float dev_ms = 0.f; CK(cudaEventElapsedTime(&dev_ms, ev_t0, ev_t1));
@@ -381,7 +412,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             c.marks.clear();
         }
         memcpy(fin.data(), h_fin, (size_t)nw * sizeof(PoaChainSlot));
-        CK(cudaFreeHost(h_fin));
+        pinned_put(1, h_fin);
         const double t_dev_done = now_ms();
         /* ---- device consensus: record offsets, then one copy of all records ---- */
         std::vector<int64_t> recoff((size_t)nw, -1); int32_t *h_cons = NULL; unsigned long long cons_words = 0;
@@ -393,7 +424,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             memcpy(recoff.data(), h_ro, (size_t)nw * 8); cons_words = (unsigned long long)h_ro[nw];
             CK(cudaFreeHost(h_ro));
             if (cons_words > pool_bytes / 4) cons_words = pool_bytes / 4;
-            CK(cudaHostAlloc((void **)&h_cons, (size_t)std::max<unsigned long long>(cons_words, 1) * 4, cudaHostAllocDefault));
+            h_cons = (int32_t *)pinned_get(2, (size_t)std::max<unsigned long long>(cons_words, 1) * 4);
             if (cons_words) CK(cudaMemcpyAsync(h_cons, d_ex, (size_t)cons_words * 4, cudaMemcpyDeviceToHost, s0));
         }
         /* word counts: header words 0..3 of every record */
@@ -412,7 +443,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             words[t] = 4 + 5ll * hdr4[4 * t] + 4ll * hdr4[4 * t + 1] + hdr4[4 * t + 2];
             hoff2[t] = tot_words; tot_words += words[t];
         }
-        int32_t *h_ex = NULL; CK(cudaHostAlloc((void **)&h_ex, (size_t)std::max<int64_t>(tot_words, 1) * 4, cudaHostAllocDefault));
+        int32_t *h_ex = (int32_t *)pinned_get(3, (size_t)std::max<int64_t>(tot_words, 1) * 4);
         if (export_graph) for (int t = 0; t < nw; ++t) if (words[t]) CK(cudaMemcpyAsync(h_ex + hoff2[t], d_ex + h_exoff[t], (size_t)words[t] * 4, cudaMemcpyDeviceToHost, s0));
         /* per-read records */
         std::vector<std::vector<int32_t>> rs((size_t)nw), rn((size_t)nw); std::vector<std::vector<uint64_t>> rh((size_t)nw);
@@ -432,7 +463,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         std::atomic<int> next(0); std::atomic<int> n_failed(0);
         std::vector<int> failed_groups; std::mutex fmu;
         int64_t cells = 0, alns = 0, fwd_clk = 0, bt_clk = 0;
-        for (int t = 0; t < nw; ++t) if (!fin[t].failed && words[t]) { cells += fin[t].cells; alns += plans[pos + t].n_reads - 1; fwd_clk += fin[t].fwd_clk; bt_clk += fin[t].bt_clk; }
+        for (int t = 0; t < nw; ++t) if (!fin[t].failed && words[t] && fin[t].fused == plans[pos + t].n_reads) { cells += fin[t].cells; alns += plans[pos + t].n_reads - 1; fwd_clk += fin[t].fwd_clk; bt_clk += fin[t].bt_clk; }
         const int nth = std::max(1, std::min(n_workers, nw));
         std::vector<std::thread> th;
         for (int w = 0; w < nth; ++w)
@@ -443,7 +474,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                     const int t = next.fetch_add(1);
                     if (t >= nw) break;
                     const GroupPlan &p = plans[pos + t];
-                    if (fin[t].failed || !words[t]) {
+                    if (fin[t].failed || !words[t] || fin[t].fused != p.n_reads) {
                         if (verbose) fprintf(stderr, "[chain] group %d left the device chain after %d reads (flags 0x%x)\n", p.g, fin[t].fused, fin[t].failed);
                         std::lock_guard<std::mutex> lk(fmu); failed_groups.push_back(p.g); n_failed += 1; continue;
                     }
@@ -476,7 +507,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             });
         for (auto &x : th) x.join();
         for (int g : failed_groups) fallback.push_back(g);
-        CK(cudaFreeHost(h_ex)); CK(cudaFreeHost(h_reads)); if (h_cons) CK(cudaFreeHost(h_cons));
+        pinned_put(3, h_ex); pinned_put(0, h_reads); if (h_cons) pinned_put(2, h_cons);
         for (Cohort &c : coh) { cudaEventDestroy(c.ev_begin); cudaEventDestroy(c.ev_end); cudaStreamDestroy(c.st); }
         cudaEventDestroy(ev_up); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
         if (stats) {

@@ -68,6 +68,7 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
     int32_t n_nodes, n_cap, pred_cap, blob_cap;
     int32_t failed;                     /* POA_CF_* bits; non-zero: the slot is inert       */
     int32_t n_reads, fused;             /* reads of the group / reads already in the graph  */
+    int32_t retry;                      /* the pending job is the generous re-run of an alignment whose band outgrew its plane slab */
     int32_t cur;                        /* which of order[2] is current                     */
     int64_t cells;                      /* DP cells of all alignments so far                */
     int64_t fwd_clk, bt_clk;            /* SM cycles of the forward DP / the backtrace, summed over the alignments */
@@ -236,7 +237,7 @@ POA_DEV void chain_set_remain(PoaChainSlot *s, int K, const int32_t *order, int 
 /* Flatten the graph + read `r` into the slot's job blob (layout: PoaJobHeader; the host twin is
  * poa_blob_fill in poa_flat.c).  Also the last line of defence for the order: every predecessor row
  * must be smaller than its row. */
-POA_DEV void chain_flatten(PoaChainSlot *s, const PoaChainParams *cp, const int32_t *order, int n, int r) {
+POA_DEV void chain_flatten(PoaChainSlot *s, const PoaChainParams *cp, const int32_t *order, int n, int r, int pool_parity, int generous) {
     const int K = cp->K;
     int32_t *cnt = s->scr[0];
     POA_PAR_FOR(i, n) cnt[i] = i == 0 ? 0 : s->in_cnt[order[i]];
@@ -282,11 +283,17 @@ POA_DEV void chain_flatten(PoaChainSlot *s, const PoaChainParams *cp, const int3
         h->off_qs = (int32_t)off_qs; h->rsv[0] = h->rsv[1] = h->rsv[2] = h->rsv[3] = 0;
         h->blob_bytes = (int32_t)off; h->pn = chain_ref_pn(cp, qlen, n); h->pad[0] = h->pad[1] = 0;
 #ifndef POA_CHAIN_EMUL
-        if (s->pool_base) {                                  /* planes of the job: same estimate as the launch path (plane_units_for) */
+        if (s->pool_base) {
+            /* planes of the job.  Band of a row = [min(ml, c) - w, max(mr, c) + w] with c the remain-centre: when read and graph
+             * differ in length the arg-max drifts away from c by up to that difference, so the estimate carries it; a band
+             * that still outgrows the slab comes back as PLANE_OVF and is re-run once with the full rectangle (generous). */
             const int w = s->read_w[r];
-            const unsigned long long per_row = (unsigned long long)((2 * w + 1 + 32 + 7) / 8 + 2);
+            const int drift = qlen > s->rem_row[0] ? qlen - s->rem_row[0] : s->rem_row[0] - qlen;
+            unsigned long long per_row = (unsigned long long)((2 * w + 1 + drift + 64 + 7) / 8 + 2);
+            const unsigned long long full = (unsigned long long)((qlen + 1 + 7) / 8 + 1);
+            if (generous || per_row > full) per_row = full;
             const unsigned long long units = per_row * (unsigned long long)cp->P * (unsigned long long)n;
-            const unsigned long long at = atomicAdd(&s->pool_cursor[r & 1], units);
+            const unsigned long long at = atomicAdd(&s->pool_cursor[pool_parity & 1], units);
             if (at + units > s->pool_units) POA_ATOMIC_OR(&s->failed, POA_CF_POOL);
             else { s->jd.planes = s->pool_base + (size_t)at * (POA_GROUP * 2); s->jd.plane_cap_units = units; }
         }
@@ -326,10 +333,10 @@ POA_DEV void chain_seed(PoaChainSlot *s, const PoaChainParams *cp) {
             order[i + 1] = v; s->node_row[v] = i + 1;
         }
     }
-    if (POA_TID0) { s->n_nodes = n; s->cur = 0; s->fused = 1; }
+    if (POA_TID0) { s->n_nodes = n; s->cur = 0; s->fused = 1; s->retry = 0; }
     POA_CTA_SYNC();
     chain_set_remain(s, K, order, n);
-    if (s->n_reads > 1) chain_flatten(s, cp, order, n, 1);
+    if (s->n_reads > 1) chain_flatten(s, cp, order, n, 1, /*pool_parity=*/1, 0);
 }
 
 /* ------------------------------------------------------------------ fuse read r, prepare read r + 1 */
@@ -338,12 +345,21 @@ POA_DEV void chain_seed(PoaChainSlot *s, const PoaChainParams *cp) {
 #define CK_NEWM 1       /* mismatch: new node aligned with the matched column                                 */
 #define CK_NEWI 2       /* inserted base: new unaligned node                                                  */
 
-POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp) {
+/* `round`: the round of the cohort's schedule that just ran (the next alignment kernel is round + 1; its plane pool is
+ * the one with that parity).  A group normally fuses read `round`, but one that had to re-run an alignment lags behind. */
+POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp, int round) {
     const int K = cp->K, A = cp->A;
     const int r = s->fused;                                /* the read whose alignment just finished */
     PoaJobHeader *hdr = reinterpret_cast<PoaJobHeader *>(const_cast<uint8_t *>(s->jd.blob));
     if (s->failed || r >= s->n_reads) return;
     const PoaResultDev *res = s->jd.result;
+    if (res->status == POA_ST_SKIP) return;               /* nothing ran for this slot in this round */
+    if (res->status == POA_ST_PLANE_OVF && !s->retry) {   /* band wider than the slab: same read again, full-rectangle slab */
+        POA_CTA_SYNC();
+        if (POA_TID0) s->retry = 1;
+        chain_flatten(s, cp, s->order[s->cur], s->n_nodes, r, round + 1, 1);
+        return;
+    }
     if (res->status != POA_ST_OK) {
         if (POA_TID0) { POA_ATOMIC_OR(&s->failed, POA_CF_DP_STATUS); hdr->n_rows = 0; }
         POA_CTA_SYNC();
@@ -529,12 +545,12 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp) {
         order_new[nr] = v; s->node_row[v] = nr;
     }
     POA_CTA_SYNC();
-    if (POA_TID0) { s->n_nodes = n; s->cur ^= 1; s->fused = r + 1; }
+    if (POA_TID0) { s->n_nodes = n; s->cur ^= 1; s->fused = r + 1; s->retry = 0; }
     POA_CTA_SYNC();
 
     /* ---- 9. band centres and the next job ---- */
     chain_set_remain(s, K, order_new, n);
-    if (r + 1 < s->n_reads) chain_flatten(s, cp, order_new, n, r + 1);
+    if (r + 1 < s->n_reads) chain_flatten(s, cp, order_new, n, r + 1, round + 1, 0);
     else if (POA_TID0) hdr->n_rows = 0;
     POA_CTA_SYNC();
 }

@@ -42,6 +42,7 @@ abpoa_seq_t *poa_seq_new(void);
 void poa_seq_free(abpoa_seq_t *abs);
 void poa_seq_reserve(abpoa_seq_t *abs);            /* grow arrays so that n_seq entries exist */
 void poa_str_assign(abpoa_str_t *dst, const char *s, int l);
+void poa_encode_residues(const char *s, int l, uint8_t *out);     /* letters -> codes (alphabet of the last abpoa_post_set_para) */
 int poa_read_fastx(const char *fn, abpoa_seq_t *abs);   /* append every FASTA/FASTQ record of a (gz) file; returns the count, -1: cannot open */
 
 /* ---- graph (poa_graph.c) ---- */

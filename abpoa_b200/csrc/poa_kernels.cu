@@ -980,26 +980,31 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     uint32_t cur32 = (uint32_t)cursor;
     const bool has_ps = LEAN ? false : (jv.predscore != nullptr);
 
-    int pb = 0, pe = 0, rbase = 0, rem = 0, mypred = -1, myps = 0;
+    /* Graph metadata runs one full row ahead of its use: what iteration i loads (row i+1's list end, residue / band centre
+     * and -- unconditionally, clamped to the list -- its per-lane predecessor entries) is first touched at the top of
+     * iteration i+1.  (ncu: with the loads consumed in the same iteration -- the list length as the predicate of the
+     * predecessor load, the loaded predecessors by the LEAN broadcast -- 10 % of all stall samples sat on these two.) */
+    const int npred_tot = ldb(&jv.rowmeta[n_rows].x);
+    int pb = 0, pe = 0, rbase = 0, rem = 0, raw_pred = -1, raw_ps = 0;
     if (n_rows > 2) {
         { const int2 m1 = ldb(jv.rowmeta + 1); pb = m1.x; pe = jv.predoff(2); rbase = m1.y & 0xff; rem = m1.y >> 8; }
-        if (lane < pe - pb) { mypred = ldb(jv.pred + pb + lane); if (has_ps) myps = ldb(jv.predscore + pb + lane); }
+        { const int k = max(min(pb + lane, npred_tot - 1), 0); raw_pred = ldb(jv.pred + k); if (has_ps) raw_ps = ldb(jv.predscore + k); }
     }
-    int p0 = -1, p1 = -1;                                 /* LEAN: the row's first two predecessors, known to every lane */
-    if (LEAN) { p0 = __shfl_sync(FULL, mypred, 0); p1 = __shfl_sync(FULL, mypred, 1); }
     int nx_y = n_rows > 3 ? ldb(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
     KP_DECL
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         KP(5)
-        int n_pe = pe, n_rbase = 0, n_rem = 0, n_mypred = -1, n_myps = 0;
-        if (i + 1 < n_rows - 1) {
-            const int2 m2 = ldb(jv.rowmeta + i + 2);
-            n_pe = m2.x; n_rbase = nx_y & 0xff; n_rem = nx_y >> 8; nx_y = m2.y;
-            if (lane < n_pe - pe) { n_mypred = ldb(jv.pred + pe + lane); if (has_ps) n_myps = ldb(jv.predscore + pe + lane); }
-        }
-        int n_p0 = -1, n_p1 = -1;
-        if (LEAN) { n_p0 = __shfl_sync(FULL, n_mypred, 0); n_p1 = __shfl_sync(FULL, n_mypred, 1); }   /* consumed one row later: off the chain */
         const int np = pe - pb;
+        const int mypred = lane < np ? raw_pred : -1, myps = lane < np ? raw_ps : 0;
+        int p0 = -1, p1 = -1;                                 /* LEAN: the row's first two predecessors, known to every lane */
+        if (LEAN) { p0 = __shfl_sync(FULL, mypred, 0); p1 = __shfl_sync(FULL, mypred, 1); }
+        int2 m2 = make_int2(pe, 0); int n_raw_pred = -1, n_raw_ps = 0;
+        const int n_rbase = nx_y & 0xff, n_rem = nx_y >> 8;
+        if (i + 1 < n_rows - 1) {
+            m2 = ldb(jv.rowmeta + i + 2);
+            const int k = max(min(pe + lane, npred_tot - 1), 0);
+            n_raw_pred = ldb(jv.pred + k); if (has_ps) n_raw_ps = ldb(jv.predscore + k);
+        }
         if (LEAN || !(jv.live && !ldb(jv.live + i))) {
 
         /* ---- LEAN fast row: <= 2 predecessors, all in the ring, their whole bands cached there ---- */
@@ -1369,8 +1374,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         }
         __syncwarp();
         }   /* live row */
-        pb = pe; pe = n_pe; rbase = n_rbase; rem = n_rem; mypred = n_mypred; myps = n_myps;
-        if (LEAN) { p0 = n_p0; p1 = n_p1; }
+        pb = pe; pe = m2.x; rbase = n_rbase; rem = n_rem; nx_y = m2.y; raw_pred = n_raw_pred; raw_ps = n_raw_ps;
     }
     cursor = cur32;
     KP_OUT(res)
@@ -1451,7 +1455,7 @@ __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__
     if (job == 0 && lane == 0 && sl->pool_cursor) sl->pool_cursor[(round + 1) & 1] = 0ull;
     const PoaJobDesc jd = sl->jd;
     const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
-    if (sl->failed || sl->fused != round || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
+    if (sl->failed || sl->fused >= sl->n_reads || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
     p16_run_job<GAP, GLOBAL, true, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
 }

@@ -132,3 +132,11 @@ int poa_read_fastx(const char *fn, abpoa_seq_t *abs) {
     free(buf);
     return n;
 }
+
+/* residue letters -> codes with the alphabet table abpoa_post_set_para selected (reference: ab_char26_table lookups in
+ * abpoa_msa1, src/abpoa_align.c:499).  A function rather than the table itself: the library is linked -Bsymbolic, so an
+ * executable that referenced the table would get its own, never initialised copy (copy relocation). */
+extern char ab_char26_table[256];
+void poa_encode_residues(const char *s, int l, uint8_t *out) {
+    for (int j = 0; j < l; ++j) out[j] = (uint8_t)ab_char26_table[(int)(unsigned char)s[j]];
+}

@@ -53,7 +53,7 @@ extern "C" void chain_emul_seed(Emul *e) { chain_seed(&e->s, &e->cp); }
 extern "C" int chain_emul_fuse(Emul *e, const uint64_t *ops, int n_ops, int best_score, int64_t cells) {
     memcpy(e->cigar.data(), ops, (size_t)n_ops * 8);
     e->res.status = POA_ST_OK; e->res.n_ops = n_ops; e->res.best_score = best_score; e->res.cells = cells;
-    chain_fuse(&e->s, &e->cp);
+    chain_fuse(&e->s, &e->cp, e->s.fused);
     return e->s.failed;
 }
 extern "C" const PoaChainSlot *chain_emul_slot(Emul *e) { return &e->s; }
