@@ -201,7 +201,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         b += al256((size_t)p.bases) + al256(((size_t)p.n_reads + 1) * 4) + al256((size_t)p.n_reads * 4);   /* reads, offsets, w */
         const size_t pred_cap = nc * 3;
         b += al256(256 + (nc + 1) * 8 + pred_cap * 4 + 4 + (size_t)p.qmax + 64);    /* job blob        */
-        b += al256(nc * sizeof(PoaRowInfo)) + al256(nc * 4);       /* rowinfo, rowoff */
+        b += al256(nc * sizeof(PoaRowInfo)) + al256(nc * sizeof(PoaRowOff));       /* rowinfo, rowoff */
         b += al256(((size_t)p.qmax + nc + 8) * 8);                 /* graph-CIGAR     */
         b += al256((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);  /* query profile   */
         b += al256(sizeof(PoaResultDev));
@@ -278,7 +278,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             /* job */
             s.blob_cap = (int32_t)(256 + (nc + 1) * 8 + (size_t)s.pred_cap * 4 + 4 + (size_t)p.qmax + 64);
             s.jd.blob = dtake((size_t)s.blob_cap);
-            s.jd.rowinfo = (PoaRowInfo *)dtake(nc * sizeof(PoaRowInfo)); s.jd.rowoff = (uint32_t *)dtake(nc * 4);
+            s.jd.rowinfo = (PoaRowInfo *)dtake(nc * sizeof(PoaRowInfo)); s.jd.rowoff = (PoaRowOff *)dtake(nc * sizeof(PoaRowOff));
             s.jd.cigar_cap = (int32_t)(p.qmax + p.n_cap + 8);
             s.jd.cigar = (uint64_t *)dtake((size_t)s.jd.cigar_cap * 8);
             s.jd.qprof = (int16_t *)dtake((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);

@@ -217,7 +217,7 @@ static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint) {
     CK(cudaSetDevice(c->dev));
     const size_t r = (size_t)rows_hint, q = (size_t)qlen_hint, j = (size_t)jobs;
-    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 20 + (q + r + 8) * 8 + 1024 + (q + 32) * 2 * 32), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
+    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 24 + (q + r + 8) * 8 + 1024 + (q + 32) * 2 * 32), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
     if (in_b > c->h_in_cap) grow_host(&c->h_in, &c->h_in_cap, in_b / 2 + 1);
     if (in_b > c->d_in_cap) grow_dev(&c->d_in, &c->d_in_cap, in_b / 2 + 1, 1);
     if (work_b > c->d_work_cap) grow_dev(&c->d_work, &c->d_work_cap, work_b / 2 + 1, 1);
@@ -300,7 +300,7 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     for (int t = 0; t < n; ++t) {
         const poa_job &j = jobs[idx[t]];
         work_off[t] = work_bytes;
-        work_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)) + al256((size_t)j.plan.n_rows * 4);
+        work_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)) + al256((size_t)j.plan.n_rows * sizeof(PoaRowOff));
         cig_off[t] = work_bytes;
         work_bytes += al256((size_t)(j.plan.qlen + j.plan.n_rows + 8) * 8);
         qp_off[t] = work_bytes;
@@ -333,7 +333,7 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
         desc[t].planes = planes_base + (size_t)plane_off[t] * POA_GROUP * S;
         desc[t].plane_cap_units = units[t];
         desc[t].rowinfo = (PoaRowInfo *)(c->d_work + work_off[t]);
-        desc[t].rowoff = (uint32_t *)(c->d_work + work_off[t] + al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)));
+        desc[t].rowoff = (PoaRowOff *)(c->d_work + work_off[t] + al256((size_t)j.plan.n_rows * sizeof(PoaRowInfo)));
         desc[t].cigar = (uint64_t *)(c->d_work + cig_off[t]);
         desc[t].cigar_cap = j.plan.qlen + j.plan.n_rows + 8;
         desc[t].pad = 0;
@@ -629,9 +629,10 @@ extern "C" int poa_debug_fetch_row(abpoa_t *ab, int row, int32_t *out, int cap, 
     poa_dev_ctx *c = (poa_dev_ctx *)ab->abm->s_mem;
     if (!c || c->arena || row < 0 || row >= c->last_rows) return -1;
     CK(cudaSetDevice(c->dev));
-    PoaRowInfo ri; uint32_t off;
+    PoaRowInfo ri; PoaRowOff ro; uint32_t off;
     CK(cudaMemcpy(&ri, c->last_desc.rowinfo + row, sizeof ri, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&off, c->last_desc.rowoff + row, sizeof off, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ro, c->last_desc.rowoff + row, sizeof ro, cudaMemcpyDeviceToHost));
+    off = ro.off;
     info4[0] = ri.beg; info4[1] = ri.end; info4[2] = ri.left; info4[3] = ri.right;
     const int P = planes_of(c->last_gap), S = c->last_bits == 32 ? 4 : 2;
     const int g0 = ri.beg >> 3, ng = (ri.end >> 3) - g0 + 1, wd = ri.end - ri.beg + 1;
@@ -666,7 +667,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
     uint64_t tot_units = 0; int band_cells = 0;
     for (int t = 0; t < n; ++t) {
         work_off[t] = work_bytes;
-        work_bytes += al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)) + al256((size_t)rj[t].n_rows * 4);
+        work_bytes += al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)) + al256((size_t)rj[t].n_rows * sizeof(PoaRowOff));
         cig_off[t] = work_bytes;
         work_bytes += al256((size_t)(rj[t].qlen + rj[t].n_rows + 8) * 8);
         qp_off[t] = work_bytes;
@@ -692,7 +693,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         desc[t].planes = planes_base + (size_t)plane_off[t] * POA_GROUP * S;
         desc[t].plane_cap_units = units[t];
         desc[t].rowinfo = (PoaRowInfo *)(c->d_work + work_off[t]);
-        desc[t].rowoff = (uint32_t *)(c->d_work + work_off[t] + al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)));
+        desc[t].rowoff = (PoaRowOff *)(c->d_work + work_off[t] + al256((size_t)rj[t].n_rows * sizeof(PoaRowInfo)));
         desc[t].cigar = (uint64_t *)(c->d_work + cig_off[t]);
         desc[t].cigar_cap = rj[t].qlen + rj[t].n_rows + 8;
         desc[t].pad = 0;

@@ -38,6 +38,9 @@ typedef struct PoaJobHeader {
 /* one DP row's band and arg-max, 16 B: the adaptive band of a successor row is derived
  * from (left, right) of its predecessors */
 typedef struct PoaRowInfo { int32_t beg, end, left, right; } PoaRowInfo;
+/* where a row's planes start (in units of POA_GROUP cells) and the row's first predecessor (-1: none): one 8-byte
+ * record, so that the backtrace and its prefetching scout learn "where next" with a single load */
+typedef struct __attribute__((aligned(8))) PoaRowOff { uint32_t off; int32_t p0; } PoaRowOff;
 
 typedef struct PoaResultDev {
     int32_t status;
@@ -59,7 +62,7 @@ typedef struct PoaJobDesc {
     void *planes;                       /* score planes slab of this job                    */
     uint64_t plane_cap_units;           /* capacity in units of POA_GROUP cells             */
     PoaRowInfo *rowinfo;                /* [n_rows]                                         */
-    uint32_t *rowoff;                   /* [n_rows] start of the row's planes, in units     */
+    PoaRowOff *rowoff;                  /* [n_rows] start of the row's planes (units) + first predecessor row */
     uint64_t *cigar;                    /* [cigar_cap]                                      */
     int32_t cigar_cap;
     int32_t pad;

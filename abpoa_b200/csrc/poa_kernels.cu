@@ -144,15 +144,15 @@ template <typename ST> struct BtRow {
     }
 };
 template <typename ST>
-__device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, const ST *planes, const PoaRowInfo *rowinfo, const uint32_t *rowoff, int row, int xs = 3) {
+__device__ __forceinline__ void bt_load_row(BtRow<ST> &r, const JobView &jv, const ST *planes, const PoaRowInfo *rowinfo, const PoaRowOff *rowoff, int row, int xs = 3) {
     r.row = row;
     const PoaRowInfo pi = rowinfo[row];
-    const uint32_t off = rowoff[row];
+    const uint2 ro = *reinterpret_cast<const uint2 *>(rowoff + row);       /* { plane offset, first predecessor } */
     const int2 m0 = ldb(jv.rowmeta + row);
     const int nx = ldb(&jv.rowmeta[row + 1].x);
-    r.beg = pi.beg; r.end = pi.end; r.off = off;
+    r.beg = pi.beg; r.end = pi.end; r.off = ro.x;
     r.pb = m0.x; r.np = nx - m0.x; r.base = m0.y & 0xff;
-    r.p0 = r.np > 0 ? ldb(jv.pred + r.pb) : -1;
+    r.p0 = r.np > 0 ? (int)ro.y : -1;
     r.p1 = r.np > 1 ? ldb(jv.pred + r.pb + 1) : -1;
     r.locate(planes, xs);
 }
@@ -177,7 +177,7 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                               int lane, int best_i, int best_j, PoaResultDev &res, int xs = 3) {
     typedef Planes<GAP> PL;
     const ST *planes = reinterpret_cast<const ST *>(jd.planes);
-    const PoaRowInfo *rowinfo = jd.rowinfo; const uint32_t *rowoff = jd.rowoff;
+    const PoaRowInfo *rowinfo = jd.rowinfo; const PoaRowOff *rowoff = jd.rowoff;
     const int m = prm->m, e1 = prm->e1, oe1 = prm->oe1, e2 = prm->e2, oe2 = prm->oe2;
     const int qlen = jv.qlen;
     const bool has_ps = jv.predscore != nullptr;
@@ -204,10 +204,12 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
      * simply carries on, otherwise (the walk overtook it) it restarts at the walk's row. */
     constexpr int BT_LEAD = 6;
     int s_row = i, s_p0 = me.p0, s_ahead = 0, s_hist = (lane == 0) ? i : -1;
+    PoaRowInfo s_info; s_info.beg = 0; s_info.end = -1; s_info.left = s_info.right = 0;
+    uint2 s_ro = make_uint2(0u, 0u); bool s_pend = false;      /* metadata of row s_row is in flight (loaded one step ago) */
     auto scout_sync = [&](int new_row) {               /* the walk moved to new_row */
         const unsigned on_chain = __ballot_sync(FULL, s_hist == new_row);
         if (on_chain) s_ahead = __ffs(on_chain) - 1;
-        else if (new_row <= s_row) { s_row = new_row; s_p0 = me.p0; s_ahead = 0; s_hist = (lane == 0) ? new_row : -1; }
+        else if (new_row <= s_row) { s_row = new_row; s_p0 = me.p0; s_pend = false; s_ahead = 0; s_hist = (lane == 0) ? new_row : -1; }
         else if (s_ahead > 1) --s_ahead;
     };
 
@@ -249,21 +251,27 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         const bool c_in_m = pc.has(j - 1);
         const int c_hm1 = c_in_m ? (int)pc.ptr[j - 1] : NEG;
         int hit = 0;
-        if (s_ahead < BT_LEAD && s_p0 > 0) {   /* one scout row per step (loads issued here are consumed after the walk's own cell load) */
-            s_row = s_p0; ++s_ahead;
-            const int up = __shfl_up_sync(FULL, s_hist, 1); s_hist = lane == 0 ? s_row : up;
-            const int2 sm = ldb(jv.rowmeta + s_row);
-            const int snx = ldb(&jv.rowmeta[s_row + 1].x);
-            const PoaRowInfo si = rowinfo[s_row];
-            const uint32_t so = rowoff[s_row];
-            s_p0 = snx > sm.x ? ldb(jv.pred + sm.x) : 0;
+        /* One scout row per step, software-pipelined: the row record requested in the previous step (band + plane offset +
+         * ITS first predecessor, 24 bytes in two loads) is consumed now -- prefetch the cells the walk will look at there,
+         * learn the next row of the chain -- and the next row's record is requested.  Nothing the scout loads is needed
+         * in the step that loads it (ncu, round-2 pass B: the unpipelined scout cost 8.6 % of all stall samples). */
+        if (s_pend) {
+            s_pend = false;
+            s_p0 = (int)s_ro.y;
             const int jp = j - s_ahead - 1;
-            if (si.end >= si.beg) {
-                const ST *sp = planes + ((ptrdiff_t)so - (((si.beg >> xs) << xs) >> 3)) * POA_GROUP;
-                const int ja = min(max(jp - 16, si.beg), si.end), jb = min(max(jp + 8, si.beg), si.end);
+            if (s_info.end >= s_info.beg) {
+                const ST *sp = planes + ((ptrdiff_t)s_ro.x - (((s_info.beg >> xs) << xs) >> 3)) * POA_GROUP;
+                const int ja = min(max(jp - 16, s_info.beg), s_info.end), jb = min(max(jp + 8, s_info.beg), s_info.end);
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + ja));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sp + jb));
             }
+        }
+        if (s_ahead < BT_LEAD && s_p0 > 0) {
+            s_row = s_p0; ++s_ahead; s_p0 = -1;
+            const int up = __shfl_up_sync(FULL, s_hist, 1); s_hist = lane == 0 ? s_row : up;
+            s_info = rowinfo[s_row];
+            s_ro = *reinterpret_cast<const uint2 *>(rowoff + s_row);
+            s_pend = true;
         }
 
         /* first predecessor (reference order) whose diagonal cell explains H[i][j] */
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
     const PoaJobDesc jd = jobs[job];
     const JobView jv = open_job(jd.blob);
     ST *planes = reinterpret_cast<ST *>(jd.planes);
-    PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
+    PoaRowInfo *rowinfo = jd.rowinfo; PoaRowOff *rowoff = jd.rowoff;
     const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
     const bool banded = w >= 0;
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
@@ -473,7 +481,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         }
         if (lane == 0) {
             PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0;
-            rowinfo[0] = r0; rowoff[0] = 0; ring_info[0] = r0; ring_off[0] = 0;
+            rowinfo[0] = r0; { PoaRowOff z; z.off = 0; z.p0 = -1; rowoff[0] = z; } ring_info[0] = r0; ring_off[0] = 0;
         }
         cursor = (uint64_t)ngrp * PL::N;
         cells += end0 + 1; max_band = end0 + 1;
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                 l1 = pi.left + 1; r1 = pi.right + 1; b1 = pi.beg; e1x = pi.end;
                 if (kb == 0) {
                     pk_row = prow; pk_beg = pi.beg; pk_end = pi.end; pk_ps = myps;
-                    pk_off = near ? ring_off[prow & rmask] : rowoff[prow];
+                    pk_off = near ? ring_off[prow & rmask] : rowoff[prow].off;
                 }
             }
             if (banded) {
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
                     const int k = kb + lane; c_row = -1;
                     if (k < np) {
                         c_row = ldb(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[c_row];
-                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row]; c_ps = jv.predscore ? ldb(jv.predscore + pb + k) : 0;
+                        c_beg = pi.beg; c_end = pi.end; c_off = rowoff[c_row].off; c_ps = jv.predscore ? ldb(jv.predscore + pb + k) : 0;
                     }
                 }
                 const int nk = min(32, np - kb);
@@ -734,7 +742,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
         if (lane == 0) {
             PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
             ring_info[i & rmask] = ri; ring_off[i & rmask] = my_off;
-            rowinfo[i] = ri; rowoff[i] = my_off;
+            rowinfo[i] = ri; { PoaRowOff z; z.off = my_off; z.p0 = mypred; *reinterpret_cast<uint2 *>(rowoff + i) = make_uint2(z.off, (unsigned)z.p0); }
         }
         if (MODE == LOCAL) {
             if (row_max > best_score) { best_score = row_max; best_i = i; best_j = row_left; }
@@ -758,7 +766,7 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
             const PoaRowInfo pi = rowinfo[prow];
             const int endc = qlen > pi.end ? pi.end : qlen;
             const int pg0 = ((pi.beg >> xs) << xs) >> 3;
-            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow] * POA_GROUP + (endc - pg0 * 8)] : NEG;
+            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow].off * POA_GROUP + (endc - pg0 * 8)] : NEG;
             if (v > best_score) { best_score = v; best_i = prow; best_j = endc; }
         }
     }
@@ -899,7 +907,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     const int m = prm->m;
     const JobView jv = open_job(jd.blob);
     ST *planes = reinterpret_cast<ST *>(jd.planes);
-    PoaRowInfo *rowinfo = jd.rowinfo; uint32_t *rowoff = jd.rowoff;
+    PoaRowInfo *rowinfo = jd.rowinfo; PoaRowOff *rowoff = jd.rowoff;
     const int qlen = jv.qlen, n_rows = jv.n_rows, w = jv.w;
     const bool banded = w >= 0;
     const int e1 = prm->e1, o1 = prm->o1, oe1 = prm->oe1, e2 = prm->e2, o2 = prm->o2, oe2 = prm->oe2;
@@ -961,7 +969,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         }
         if (lane == 0) {
             PoaRowInfo r0; r0.beg = 0; r0.end = end0; r0.left = 0; r0.right = 0;
-            rowinfo[0] = r0; rowoff[0] = 0; ring_meta[0] = make_uint4(0u, (unsigned)end0, 1u | (1u << 16), 0u);
+            rowinfo[0] = r0; { PoaRowOff z; z.off = 0; z.p0 = -1; rowoff[0] = z; } ring_meta[0] = make_uint4(0u, (unsigned)end0, 1u | (1u << 16), 0u);
         }
         cursor = (uint64_t)ngrp * PL::N;
         cells += end0 + 1; max_band = end0 + 1;
@@ -1027,7 +1035,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             const bool near = (i - prow) <= rmask;
             uint4 mi;
             if (near) mi = ring_meta[prow & rmask];
-            else { const PoaRowInfo pi = rowinfo[prow]; mi = make_uint4((unsigned)pi.beg, (unsigned)pi.end, (unsigned)(pi.left + 1) | ((unsigned)(pi.right + 1) << 16), rowoff[prow]); }
+            else { const PoaRowInfo pi = rowinfo[prow]; mi = make_uint4((unsigned)pi.beg, (unsigned)pi.end, (unsigned)(pi.left + 1) | ((unsigned)(pi.right + 1) << 16), rowoff[prow].off); }
             l1 = (int)(mi.z & 0xffffu); r1 = (int)(mi.z >> 16); b1 = (int)mi.x;
             const unsigned pg0 = mi.x >> 3, png = (mi.y >> 3) - pg0 + 1;
             wA = pg0 | (png << 12) | ((unsigned)near << 25) | ((unsigned)(prow & rmask) << 26);
@@ -1148,7 +1156,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                     if (k < np) {
                         const int prow = ldb(jv.pred + pb + k); const PoaRowInfo pi = rowinfo[prow];
                         const unsigned pg0 = (unsigned)pi.beg >> 3, png = ((unsigned)pi.end >> 3) - pg0 + 1;
-                        cA = pg0 | (png << 12); cB = rowoff[prow]; if (has_ps) c_ps = ldb(jv.predscore + pb + k);
+                        cA = pg0 | (png << 12); cB = rowoff[prow].off; if (has_ps) c_ps = ldb(jv.predscore + pb + k);
                     }
                 }
                 const int nk = min(32, np - kb);
@@ -1360,7 +1368,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         if (lane == 0) {
             ring_meta[i & rmask] = make_uint4((unsigned)beg, (unsigned)end, (unsigned)(row_left + 1) | ((unsigned)(row_right + 1) << 16), my_off);
             PoaRowInfo ri; ri.beg = beg; ri.end = end; ri.left = row_left; ri.right = row_right;
-            rowinfo[i] = ri; rowoff[i] = my_off;
+            rowinfo[i] = ri; { PoaRowOff z; z.off = my_off; z.p0 = mypred; *reinterpret_cast<uint2 *>(rowoff + i) = make_uint2(z.off, (unsigned)z.p0); }
         }
         guard_lo |= (row_max < -14000); guard_hi |= (row_max > 29000);
         if (MODE == LOCAL) {
@@ -1390,7 +1398,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             const PoaRowInfo pi = rowinfo[prow];
             const int endc = qlen > pi.end ? pi.end : qlen;
             const int pg0 = pi.beg >> 3;
-            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow] * POA_GROUP + (endc - pg0 * 8)] : NEG;
+            const int v = (endc >= pi.beg) ? (int)planes[(size_t)rowoff[prow].off * POA_GROUP + (endc - pg0 * 8)] : NEG;
             if (v > best_score) { best_score = v; best_i = prow; best_j = endc; }
         }
     }
