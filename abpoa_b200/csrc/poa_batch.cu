@@ -666,12 +666,15 @@ void worker_pipelined(Worker wk) {
     for (int k = 0; k < K; ++k) poa_dev_ctx_set_pressure_cb(half[k].ctx, NULL, NULL);
     for (int k = 0; k < K; ++k) for (abpoa_t *ab : half[k].handles) abpoa_free(ab);
     if (prof) {
-        double wait = 0, fill = 0, copy = 0, kern = 0; double ph[6] = {0, 0, 0, 0, 0, 0}; int64_t alns = 0, fwd = 0, bt = 0;
+        double wait = 0, fill = 0, copy = 0, kern = 0; double ph[6] = {0, 0, 0, 0, 0, 0}; int64_t alns = 0, fwd = 0, bt = 0, dg[4] = {0, 0, 0, 0};
         for (int k = 0; k < K; ++k) {
             const poa_engine_stats *st = poa_dev_ctx_stats(wk.ctxs[k]); wait += st->wait_ms; fill += st->fill_ms; copy += st->copy_ms; kern += st->kernel_ms;
             for (int z = 0; z < 6; ++z) ph[z] += (double)st->prof[z];
+            for (int z = 0; z < 4; ++z) dg[z] += st->diag[z];
             alns += st->alignments; fwd += st->fwd_clk; bt += st->bt_clk;
         }
+        if (dg[0] + dg[1] + dg[2] + dg[3] > 0) fprintf(stderr, "[kernel rows] straight-line %lld | generic: predecessors>2 %lld, predecessor outside the ring %lld, predecessor band wider than its ring slot %lld\n",
+                                                      (long long)dg[0], (long long)dg[1], (long long)dg[2], (long long)dg[3]);
         if (alns > 0) fprintf(stderr, "[kernel, k-cycles/alignment] forward %.0f backtrace %.0f | -DPOA_KPROF phases: setup %.0f pred %.0f compute %.0f store %.0f rowmax %.0f tail+prefetch %.0f\n",
                               fwd / 1e3 / alns, bt / 1e3 / alns, ph[0] / 1e3 / alns, ph[1] / 1e3 / alns, ph[2] / 1e3 / alns, ph[3] / 1e3 / alns, ph[4] / 1e3 / alns, ph[5] / 1e3 / alns);
         fprintf(stderr, "[worker-host] bfs %.0f sort_edges %.0f remain %.0f thread_cigar %.0f ms\n", poa_prof_ms[0], poa_prof_ms[1], poa_prof_ms[2], poa_prof_ms[3]);

@@ -269,7 +269,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                 memcpy(hr + acc, in.seqs[i], (size_t)in.seq_lens[i]);
                 hoff[i] = acc; acc += in.seq_lens[i];
                 hw[i] = poa_band_halfwidth(abpt, in.seq_lens[i]);
-                const int bc = (2 * hw[i] + 1 + 40 + 7) / 8 * 8;
+                const int bc = (2 * hw[i] + 1 + 104 + 7) / 8 * 8;
                 if (bc > band_cells) band_cells = bc;
             }
             hoff[p.n_reads] = acc;

@@ -350,7 +350,7 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     int band_cells = 0;
     for (int t = 0; t < n; ++t) {
         const poa_blob_plan &pl = jobs[idx[t]].plan;
-        const int bc = pl.w >= 0 ? (2 * pl.w + 1 + 40 + 7) / 8 * 8 : (pl.qlen + 1 + 7) / 8 * 8 + 8;
+        const int bc = pl.w >= 0 ? (2 * pl.w + 1 + 104 + 7) / 8 * 8 : (pl.qlen + 1 + 7) / 8 * 8 + 8;
         if (bc > band_cells) band_cells = bc;
     }
     static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
@@ -443,7 +443,7 @@ static void run_finish(poa_dev_ctx *c) {
             cj.bits = bits; cj.best_score = resv[t].best_score; cj.n_ops = resv[t].n_ops; cj.cells = resv[t].cells; cj.plane_units = resv[t].plane_units_used;
             c->capture(c->capture_user, &cj);
         }
-        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; for (int z = 0; z < 6; ++z) c->stats.prof[z] += resv[t].prof[z]; }
+        if (resv[t].status == POA_ST_OK) { c->stats.cells += resv[t].cells; c->stats.alignments += 1; c->stats.fwd_clk += resv[t].fwd_clk; c->stats.bt_clk += resv[t].bt_clk; for (int z = 0; z < 6; ++z) c->stats.prof[z] += resv[t].prof[z]; for (int z = 0; z < 4; ++z) c->stats.diag[z] += resv[t].diag[z]; }
     }
 }
 
@@ -676,7 +676,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         units[t] = plane_units_for(&tmp, abpt->gap_mode, 0);
         if (rj[t].plane_units > units[t]) units[t] = rj[t].plane_units;          /* a job that needed the generous slab */
         plane_off[t] = tot_units; tot_units += units[t];
-        const int bc = rj[t].w >= 0 ? (2 * rj[t].w + 1 + 40 + 7) / 8 * 8 : (rj[t].qlen + 1 + 7) / 8 * 8 + 8;
+        const int bc = rj[t].w >= 0 ? (2 * rj[t].w + 1 + 104 + 7) / 8 * 8 : (rj[t].qlen + 1 + 7) / 8 * 8 + 8;
         if (bc > band_cells) band_cells = bc;
     }
     const size_t plane_bytes = (size_t)tot_units * POA_GROUP * S;

@@ -54,6 +54,8 @@ typedef struct PoaResultDev {
     int64_t fwd_clk, bt_clk;            /* SM clock cycles spent in the forward DP / the backtrace */
     uint64_t t_start_ns, t_end_ns;      /* %globaltimer at entry / exit of the job's warp          */
     int64_t prof[6];                    /* optional per-phase SM cycles (ABPOA kernel built with -DPOA_KPROF) */
+    int32_t diag[4];                    /* -DPOA_KPROF: rows on the straight-line path / rows sent to the generic path because of
+                                           > 2 predecessors / a predecessor outside the ring / a predecessor band wider than its ring slot */
 } PoaResultDev;
 
 /* device pointers of one job */

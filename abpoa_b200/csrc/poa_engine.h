@@ -41,6 +41,7 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     int64_t fwd_clk, bt_clk;            /* SM cycles in the forward DP / backtrace, summed over alignments */
     int64_t prof[6];                    /* -DPOA_KPROF builds: per-phase cycles */
+    int64_t diag[4];                    /* -DPOA_KPROF builds: rows on the straight-line path / generic because of np, ring distance, band width */
     double fill_ms, wait_ms, copy_ms;   /* host-side phases of a launch: blob fill, kernel wait, result copies */
 } poa_engine_stats;
 

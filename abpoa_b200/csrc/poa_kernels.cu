@@ -799,9 +799,9 @@ __global__ void __launch_bounds__(32) poa_align_kernel(const PoaJobDesc *__restr
  * The launcher uses this kernel whenever scores provably fit (see poa_p16_ok); a run-time guard
  * (row maxima drifting towards the rails) makes the job fall back to the 32-bit kernel. */
 #ifdef POA_KPROF
-#define KP_DECL long long kp[6] = {0,0,0,0,0,0}; long long kp_t = clock64();
+#define KP_DECL long long kp[6] = {0,0,0,0,0,0}; long long kp_t = clock64(); int kdiag[4] = {0,0,0,0};
 #define KP(n) { const long long t_ = clock64(); kp[n] += t_ - kp_t; kp_t = t_; }
-#define KP_OUT(res) { for (int z_ = 0; z_ < 6; ++z_) (res).prof[z_] = kp[z_]; }
+#define KP_OUT(res) { for (int z_ = 0; z_ < 6; ++z_) (res).prof[z_] = kp[z_]; for (int z_ = 0; z_ < 4; ++z_) (res).diag[z_] = kdiag[z_]; }
 #else
 #define KP_DECL
 #define KP(n)
@@ -1020,11 +1020,17 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         uint4 lm0 = make_uint4(0u, 0u, 0u, 0u), lm1 = lm0;
         if (LEAN) {
             lean_row = np >= 1 && np <= 2 && (i - p0) <= rmask && (np < 2 || (i - p1) <= rmask);
+#ifdef POA_KPROF
+            if (!lean_row) { if (np > 2 || np < 1) ++kdiag[1]; else ++kdiag[2]; }
+#endif
             if (lean_row) {
                 lm0 = ring_meta[p0 & rmask];
                 lm1 = np == 2 ? ring_meta[p1 & rmask] : lm0;
                 const int png0 = (int)(lm0.y >> 3) - (int)(lm0.x >> 3) + 1, png1 = (int)(lm1.y >> 3) - (int)(lm1.x >> 3) + 1;
                 if (png0 > ring_groups || png1 > ring_groups) lean_row = false;      /* a row wider than its ring slot: only a prefix is cached */
+#ifdef POA_KPROF
+                if (lean_row) ++kdiag[0]; else ++kdiag[3];
+#endif
             }
         }
         /* ---- predecessor k on lane k: band hints + the two broadcast words ---- */
