@@ -16,6 +16,8 @@ grep "chain\]" $O/r02c_bench_convex_10k.err | tail -3
 timeout 600 python tools/exp_batch.py convex_10k 1000 32 0 3 > $O/r02c_e2e_default.log 2>&1; tail -2 $O/r02c_e2e_default.log
 ABPOA_GPU_TMA=1 timeout 600 python tools/exp_batch.py convex_10k 1000 32 0 3 > $O/r02c_e2e_tma.log 2>&1; tail -2 $O/r02c_e2e_tma.log
 ABPOA_GPU_TMA=1 timeout 900 python -m pytest tests/test_gpu_chain.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider > $O/r02c_pytest_tma.log 2>&1; tail -3 $O/r02c_pytest_tma.log
+# where rows go and where the cycles of a row go (-DPOA_KPROF build, launch engine so that the worker prints the per-kernel phases)
+ABPOA_GPU_NO_CHAIN=1 ABPOA_B200_LIB=$PWD/abpoa_b200/lib/libabpoa_b200_kprof.so ABPOA_GPU_PROFILE=1 timeout 600 python tools/exp_batch.py convex_10k 256 32 0 1 > $O/r02c_kprof.log 2>&1; grep "kernel rows\|kernel, k-cycles" $O/r02c_kprof.log | head -4
 for wl in "affine_1k 0" "aa_blosum62_2k 0" "affine_10k 1000" "local_linear_5k 100"; do
   set -- $wl
   ABPOA_GPU_PROFILE=1 timeout 900 python bench.py --workload $1 --groups $2 --steps 2 --warmup 3 > $O/r02c_bench_$1.json 2> $O/r02c_bench_$1.err; echo "bench $1 rc=$?"
