@@ -108,6 +108,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 int poa_chain_eligible(const abpoa_para_t *abpt) {
     const char *off = getenv("ABPOA_GPU_NO_CHAIN");
     if (off && *off == '1') return 0;
+    { const char *np = getenv("ABPOA_GPU_NO_P16"); if (np && *np == '1') return 0; }      /* the chain only has the packed int16 kernel */
     if (abpt->align_mode != ABPOA_GLOBAL_MODE || abpt->wb < 0) return 0;
     if (abpt->gap_mode == ABPOA_LINEAR_GAP) return 0;                      /* banded linear gaps: generic kernel only (lane-exact band edges) */
     if (abpt->use_read_ids || abpt->out_msa || abpt->out_gfa || abpt->max_n_cons > 1 || abpt->cons_algrm != ABPOA_HB) return 0;
@@ -204,7 +205,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         b += al256(nc * sizeof(PoaRowInfo)) + al256(nc * sizeof(PoaRowOff));       /* rowinfo, rowoff */
         b += al256(((size_t)p.qmax + nc + 8) * 8);                 /* graph-CIGAR     */
         b += al256((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);  /* query profile   */
-        b += al256(sizeof(PoaResultDev));
+        b += al256(sizeof(PoaResultDev)) + al256(nc * sizeof(PoaBtRec));
         if (record) b += 2 * al256((size_t)p.n_reads * 4) + al256((size_t)p.n_reads * 8);
         p.static_bytes = b;
         const int wmax = poa_band_halfwidth(abpt, p.qmax);
@@ -283,6 +284,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             s.jd.cigar = (uint64_t *)dtake((size_t)s.jd.cigar_cap * 8);
             s.jd.qprof = (int16_t *)dtake((size_t)m * ((((size_t)p.qmax + 1 + 7) & ~(size_t)7) + 8) * 2);
             s.jd.result = (PoaResultDev *)dtake(sizeof(PoaResultDev));
+            s.jd.btrec = (PoaBtRec *)dtake(nc * sizeof(PoaBtRec));
             if (record) { s.rec_score = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_nops = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_hash = (uint64_t *)dtake((size_t)p.n_reads * 8); }
             if (p.n_reads > max_reads) max_reads = p.n_reads;
         }

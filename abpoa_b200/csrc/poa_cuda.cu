@@ -217,7 +217,7 @@ static void grow_dev(uint8_t **p, size_t *cap, size_t need, int slack) {
 void poa_dev_ctx_reserve(poa_dev_ctx *c, int jobs, int rows_hint, int qlen_hint) {
     CK(cudaSetDevice(c->dev));
     const size_t r = (size_t)rows_hint, q = (size_t)qlen_hint, j = (size_t)jobs;
-    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * 24 + (q + r + 8) * 8 + 1024 + (q + 32) * 2 * 32), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
+    const size_t in_b = 4096 + j * (r * 28 + q + 1024), work_b = 4096 + j * (r * (24 + 64) + (q + r + 8) * 8 + 1024 + (q + 32) * 2 * 32), out_b = 4096 + j * ((q + r + 8) * 8 + 512);
     if (in_b > c->h_in_cap) grow_host(&c->h_in, &c->h_in_cap, in_b / 2 + 1);
     if (in_b > c->d_in_cap) grow_dev(&c->d_in, &c->d_in_cap, in_b / 2 + 1, 1);
     if (work_b > c->d_work_cap) grow_dev(&c->d_work, &c->d_work_cap, work_b / 2 + 1, 1);
@@ -291,7 +291,7 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
     /* ---- layout of the input arena: params | descs | blobs ---- */
     size_t in_bytes = al256(sizeof(PoaParamsDev)) + al256((size_t)n * sizeof(PoaJobDesc));
     const size_t off_desc = al256(sizeof(PoaParamsDev));
-    std::vector<size_t> &blob_off = L.blob_off, &work_off = L.work_off, &cig_off = L.cig_off; std::vector<size_t> qp_off(n);
+    std::vector<size_t> &blob_off = L.blob_off, &work_off = L.work_off, &cig_off = L.cig_off; std::vector<size_t> qp_off(n), bt_off(n);
     blob_off.assign(n, 0); work_off.assign(n, 0); cig_off.assign(n, 0);
     std::vector<uint64_t> units(n), plane_off(n);
     for (int t = 0; t < n; ++t) { blob_off[t] = in_bytes; in_bytes += al256(jobs[idx[t]].plan.bytes); }
@@ -305,6 +305,8 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
         work_bytes += al256((size_t)(j.plan.qlen + j.plan.n_rows + 8) * 8);
         qp_off[t] = work_bytes;
         if (bits == 15) work_bytes += al256((size_t)abpt->m * ((((size_t)j.plan.qlen + 1 + 7) & ~(size_t)7) + 8) * 2);
+        bt_off[t] = work_bytes;
+        if (bits == 15) work_bytes += al256((size_t)j.plan.n_rows * sizeof(PoaBtRec));
     }
     uint64_t tot_units = 0;
     for (int t = 0; t < n; ++t) {
@@ -340,6 +342,7 @@ static bool run_begin(poa_dev_ctx *c, const abpoa_para_t *abpt, poa_job *jobs, c
         desc[t].result = (PoaResultDev *)(c->h_res + 256) + t;      /* mapped pinned host memory */
         desc[t].done = NULL;
         desc[t].qprof = (int16_t *)(c->d_work + qp_off[t]);
+        desc[t].btrec = bits == 15 ? (PoaBtRec *)(c->d_work + bt_off[t]) : NULL;
         ((volatile PoaResultDev *)(c->h_res + 256))[t].t_end_ns = 0;
     }
     __sync_synchronize();
@@ -663,7 +666,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
     const size_t off_desc = al256(sizeof(PoaParamsDev));
     const size_t in_bytes = off_desc + al256((size_t)n * sizeof(PoaJobDesc));
     size_t work_bytes = al256((size_t)n * sizeof(PoaResultDev));
-    std::vector<size_t> work_off(n), cig_off(n), qp_off(n); std::vector<uint64_t> units(n), plane_off(n);
+    std::vector<size_t> work_off(n), cig_off(n), qp_off(n), bt_off(n); std::vector<uint64_t> units(n), plane_off(n);
     uint64_t tot_units = 0; int band_cells = 0;
     for (int t = 0; t < n; ++t) {
         work_off[t] = work_bytes;
@@ -672,6 +675,8 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         work_bytes += al256((size_t)(rj[t].qlen + rj[t].n_rows + 8) * 8);
         qp_off[t] = work_bytes;
         if (bits == 15) work_bytes += al256((size_t)abpt->m * ((((size_t)rj[t].qlen + 1 + 7) & ~(size_t)7) + 8) * 2);
+        bt_off[t] = work_bytes;
+        if (bits == 15) work_bytes += al256((size_t)rj[t].n_rows * sizeof(PoaBtRec));
         poa_job tmp; memset(&tmp, 0, sizeof tmp); tmp.plan.n_rows = rj[t].n_rows; tmp.plan.qlen = rj[t].qlen; tmp.plan.w = rj[t].w;
         units[t] = plane_units_for(&tmp, abpt->gap_mode, 0);
         if (rj[t].plane_units > units[t]) units[t] = rj[t].plane_units;          /* a job that needed the generous slab */
@@ -700,6 +705,7 @@ double poa_dev_ctx_replay_launch(poa_dev_ctx *c, const abpoa_para_t *abpt, const
         desc[t].result = (PoaResultDev *)c->d_work + t;
         desc[t].done = NULL;
         desc[t].qprof = (int16_t *)(c->d_work + qp_off[t]);
+        desc[t].btrec = bits == 15 ? (PoaBtRec *)(c->d_work + bt_off[t]) : NULL;
     }
     static const size_t smem_budget = [] { const char *e = getenv("ABPOA_GPU_SMEM_KB"); return (size_t)(e && *e ? atoi(e) : 28) * 1024; }();
     int ring_rows = 2, ring_cells = 64;

@@ -58,6 +58,20 @@ typedef struct PoaResultDev {
                                            > 2 predecessors / a predecessor outside the ring / a predecessor band wider than its ring slot */
 } PoaResultDev;
 
+/* Backtrace shortcut record of one DP row, written by the packed forward kernel (64 B, one cache-line half):
+ * bit k says "cell c0 + k of this row is explained by the diagonal of the row's FIRST predecessor"
+ * (H[i][j] == H[p0][j-1] + s(i,j) (+ path score) with j-1 inside p0's band) -- the test the reference's backtrace makes
+ * first whenever a match is allowed (src/abpoa_align_simd.c:211-227), true on ~90 % of its steps.  With the first
+ * predecessor and the residue in the same record, such a step needs one small load instead of the generic machinery. */
+#define POA_BTREC_BYTES 64
+#define POA_BTREC_BITS  (52 * 8)
+typedef struct __attribute__((aligned(16))) PoaBtRec {
+    int32_t c0;                         /* column of bit 0 (first cell of the row's first stored group)   */
+    int32_t p0;                         /* first predecessor row, -1: none                                 */
+    uint8_t base, valid, pad[2];        /* residue of the node; valid = 0: the row has no bitmap (too wide) */
+    uint8_t bits[52];
+} PoaBtRec;
+
 /* device pointers of one job */
 typedef struct PoaJobDesc {
     const uint8_t *blob;
@@ -71,6 +85,7 @@ typedef struct PoaJobDesc {
     PoaResultDev *result;               /* may live in mapped pinned host memory            */
     int32_t *done;                      /* unused (kept for layout)                                        */
     int16_t *qprof;                     /* packed kernel: query profile scratch [m][qstride] in HBM         */
+    PoaBtRec *btrec;                    /* packed kernel: [n_rows] backtrace shortcut records, or NULL               */
 } PoaJobDesc;
 
 /* alignment parameters, identical for all jobs of a launch */

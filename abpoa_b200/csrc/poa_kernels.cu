@@ -174,7 +174,7 @@ struct CigarSink {
 
 template <int GAP, typename ST, int MODE>
 __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const PoaParamsDev *prm, const int *mat_s,
-                              int lane, int best_i, int best_j, PoaResultDev &res, int xs = 3) {
+                              int lane, int best_i, int best_j, PoaResultDev &res, int xs = 3, const PoaBtRec *btrec = nullptr) {
     typedef Planes<GAP> PL;
     const ST *planes = reinterpret_cast<const ST *>(jd.planes);
     const PoaRowInfo *rowinfo = jd.rowinfo; const PoaRowOff *rowoff = jd.rowoff;
@@ -233,6 +233,34 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     };
 
     while (i > 0 && j > 0) {
+        /* ---- shortcut: while a match is the first thing the reference would test and the row's bitmap says the first
+         *      predecessor's diagonal explains the cell, the step is MATCH -> (p0, j-1) (src/abpoa_align_simd.c:211-227) and
+         *      everything it needs sits in one 64-byte record per row (PoaBtRec).  Records of the rows just below are
+         *      prefetched: the first predecessor is almost always within a few rows. ---- */
+        if (btrec != nullptr && MODE != LOCAL && !gap_on_right) {
+            bool moved = false;
+            while (i > 0 && j > 0 && (GAP == LG || (cur & OP_M)) && !gap_at_end) {
+                const uint8_t *rec = reinterpret_cast<const uint8_t *>(btrec + i);
+                const uint4 hd = *reinterpret_cast<const uint4 *>(rec);            /* c0, p0, base | valid << 8, bits[0..3] */
+                const int kbit = j - (int)hd.x;
+                if (!((hd.z >> 8) & 0xffu) || (unsigned)kbit >= (unsigned)POA_BTREC_BITS) break;
+                const unsigned byte = rec[12 + (kbit >> 3)];
+                if (!((byte >> (kbit & 7)) & 1u)) break;
+                start_i = i; start_j = j;
+                cg.match(i, j - 1);
+                ++n_aln; n_match += ((int)(hd.z & 0xffu) == (int)jv.qs[j]);
+                i = (int)hd.y; --j; cur = OP_ALL; moved = true;
+                if (i >= 6) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 6)));
+            }
+            if (moved) {                               /* back to the general step: rebuild its view of (i, j) */
+                if (!(i > 0 && j > 0)) break;
+                bt_load_row<ST>(me, jv, planes, rowinfo, rowoff, i, xs);
+                h_ij = me.has(j) ? (int)me.ptr[j] : NEG;
+                qc = (int)jv.qs[j];
+                cand_loaded = false;
+                s_row = i; s_p0 = me.p0; s_pend = false; s_ahead = 0; s_hist = (lane == 0) ? i : -1;
+            }
+        }
         if (MODE == LOCAL && h_ij == 0) break;
         start_i = i; start_j = j;
         const int id = i;                       /* the host maps DP rows back to node ids */
@@ -1107,8 +1135,9 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             uint4 sv = make_uint4(0u, 0u, 0u, 0u);
             if (active) sv = *reinterpret_cast<const uint4 *>(qrow + (size_t)g * 8);
             unsigned M[4], X1[4], X2[4];
+            unsigned D0[4];                                   /* diagonal term of the FIRST predecessor alone (backtrace shortcut bits) */
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { M[k] = NEGP2; X1[k] = NEGP2; X2[k] = NEGP2; }
+            for (int k = 0; k < 4; ++k) { M[k] = NEGP2; X1[k] = NEGP2; X2[k] = NEGP2; D0[k] = NEGP2; }
             /* lane 0's left neighbour (cell 8g-1) lives in the previous group: only needed when that
              * cell is inside the band, i.e. on later passes or when the band starts on a group boundary */
             const bool fix_left = (gp > g0) || ((beg & 7) == 0);
@@ -1145,6 +1174,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                     }
                     const uint4 x1 = GAP == LG ? hp : ep1;
                     if (k == 0) {
+                        D0[0] = d0; D0[1] = d1; D0[2] = d2; D0[3] = d3;
                         M[0] = d0; M[1] = d1; M[2] = d2; M[3] = d3;
                         X1[0] = x1.x; X1[1] = x1.y; X1[2] = x1.z; X1[3] = x1.w;
                         if (GAP == CG) { X2[0] = ep2.x; X2[1] = ep2.y; X2[2] = ep2.z; X2[3] = ep2.w; }
@@ -1220,6 +1250,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                             }
                         }
                     }
+                    if (kb == 0 && k == 0) { D0[0] = d0; D0[1] = d1; D0[2] = d2; D0[3] = d3; }
                     M[0] = __vmaxs2(M[0], d0); M[1] = __vmaxs2(M[1], d1); M[2] = __vmaxs2(M[2], d2); M[3] = __vmaxs2(M[3], d3);
                     if (GAP == LG) {        /* vertical term H[p][j] - e1 */
                         X1[0] = __vmaxs2(X1[0], __viaddmax_s16x2(hp.x, kc.NE1, NEGP2)); X1[1] = __vmaxs2(X1[1], __viaddmax_s16x2(hp.y, kc.NE1, NEGP2));
@@ -1297,6 +1328,21 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                 }
             }
 
+            /* backtrace shortcut record (PoaBtRec): one bit per cell -- is H explained by the first predecessor's diagonal? */
+            if (jd.btrec != nullptr) {
+                unsigned t = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    t |= __vcmpeq2(__viaddmax_s16x2(D0[k], S[k], NEGP2), H[k]) & (0x00020001u << (2 * k));
+                const unsigned byte = (t | (t >> 16)) & 0xffu;
+                uint8_t *rec = reinterpret_cast<uint8_t *>(jd.btrec + i);
+                const int rel = g - g0;
+                if (active && rel < 52) rec[12 + rel] = (uint8_t)byte;
+                if (lane == 0 && gp == g0) {
+                    *reinterpret_cast<int2 *>(rec) = make_int2(g0 * 8, mypred);
+                    *reinterpret_cast<unsigned *>(rec + 8) = (unsigned)rbase | (ngrp <= 52 ? 0x100u : 0u);
+                }
+            }
             KP(2)
             if (TMA && tma_row) {
                 if (gp == g0) {                              /* the slot's previous tenant (ring_rows rows ago) must have been read out */
@@ -1424,7 +1470,7 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
     if (lane == 0) *jd.result = res;
     __syncwarp();
     if (prm->ret_cigar && res.status == POA_ST_OK) {
-        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result);
+        poa_backtrack<GAP, ST, MODE>(jv, jd, prm, mat_s, lane, best_i, best_j, *jd.result, 3, jd.btrec);
         if (lane == 0) jd.result->bt_clk = clock64() - clk1;
     }
 }
@@ -1432,11 +1478,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 
 /* POA_P16_MINB (build-time, experiments): minimum resident CTAs per SM the compiler must allow for, i.e. a
  * register cap of 65536 / (32 * POA_P16_MINB) per thread */
-#ifdef POA_P16_MINB
-#define POA_P16_BOUNDS __launch_bounds__(32, POA_P16_MINB)
-#else
-#define POA_P16_BOUNDS __launch_bounds__(32)
+#ifndef POA_P16_MINB
+#define POA_P16_MINB 10      /* register budget 65536 / (32 * 10) = 204 per thread: without a budget ptxas settles on 128 and spills */
 #endif
+#define POA_P16_BOUNDS __launch_bounds__(32, POA_P16_MINB)
 template <int GAP, int MODE, bool LEAN, bool TMA>
 __global__ void POA_P16_BOUNDS poa_align_kernel_p16(const PoaJobDesc *__restrict__ jobs, const PoaParamsDev *__restrict__ prm,
                                                            int n_jobs, int ring_rows, int ring_cells, const __grid_constant__ P16Consts kc) {

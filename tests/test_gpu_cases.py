@@ -147,7 +147,8 @@ def test_batch_arena_contention(reference_lib, monkeypatch):
 
 
 def test_batch_no_p16_and_slab_redo(reference_lib, monkeypatch):
-    """Redo paths inside the pipelined engine (poa_engine_collect): slab overflow on the generic kernel."""
+    """Redo paths inside the pipelined engine (poa_engine_collect): slab overflow on the generic kernel (with the packed
+    kernel switched off the chain engine, which only has that kernel, steps aside)."""
     monkeypatch.setenv("ABPOA_GPU_NO_P16", "1")
     monkeypatch.setenv("ABPOA_GPU_SLAB_PCT", "30")
     groups = [synth.make_group(1700 + g, 6, 400, 0.06) for g in range(10)]
