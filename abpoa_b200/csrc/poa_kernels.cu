@@ -1034,13 +1034,14 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         const int mypred = lane < np ? raw_pred : -1, myps = lane < np ? raw_ps : 0;
         int p0 = -1, p1 = -1;                                 /* LEAN: the row's first two predecessors, known to every lane */
         if (LEAN) { p0 = __shfl_sync(FULL, mypred, 0); p1 = __shfl_sync(FULL, mypred, 1); }
-        int2 m2 = make_int2(pe, 0); int n_raw_pred = -1, n_raw_ps = 0;
+        /* unconditional: rowmeta has n_rows + 1 entries and i + 2 <= n_rows; the predecessor index is clamped (a predicated
+         * load would need a select on its result, which the compiler schedules right behind the load) */
+        int2 m2;                                              /* two 32-bit loads: a 64-bit one ties up an aligned register pair that ptxas frees by
+                                                                 copying the result out right behind the load, i.e. by waiting for it */
+        m2.x = ldb(&jv.rowmeta[i + 2].x); m2.y = ldb(&jv.rowmeta[i + 2].y);
         const int n_rbase = nx_y & 0xff, n_rem = nx_y >> 8;
-        if (i + 1 < n_rows - 1) {
-            m2 = ldb(jv.rowmeta + i + 2);
-            const int k = max(min(pe + lane, npred_tot - 1), 0);
-            n_raw_pred = ldb(jv.pred + k); if (has_ps) n_raw_ps = ldb(jv.predscore + k);
-        }
+        int n_raw_pred, n_raw_ps = 0;
+        { const int k = max(min(pe + lane, npred_tot - 1), 0); n_raw_pred = ldb(jv.pred + k); if (has_ps) n_raw_ps = ldb(jv.predscore + k); }
         if (LEAN || !(jv.live && !ldb(jv.live + i))) {
 
         /* ---- LEAN fast row: <= 2 predecessors, all in the ring, their whole bands cached there ---- */
@@ -1434,6 +1435,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         }
         __syncwarp();
         }   /* live row */
+        /* The compiler must not pull this rotation up to the loads at the top of the iteration (it did: the copy of m2.x then
+         * waited for the load in the very iteration that issued it).  An empty volatile asm pins "first use" here, after the
+         * row's volatile shared-memory stores, a whole row later. */
+        asm volatile("" : "+r"(m2.x), "+r"(m2.y), "+r"(n_raw_pred), "+r"(n_raw_ps));
         pb = pe; pe = m2.x; rbase = n_rbase; rem = n_rem; nx_y = m2.y; raw_pred = n_raw_pred; raw_ps = n_raw_ps;
     }
     cursor = cur32;
