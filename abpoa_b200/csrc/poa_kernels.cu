@@ -1032,8 +1032,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         KP(5)
         const int np = pe - pb;
         const int mypred = lane < np ? raw_pred : -1, myps = lane < np ? raw_ps : 0;
-        int p0 = -1, p1 = -1;                                 /* LEAN: the row's first two predecessors, known to every lane */
-        if (LEAN) { p0 = __shfl_sync(FULL, mypred, 0); p1 = __shfl_sync(FULL, mypred, 1); }
+        constexpr int LP = 4;                                 /* LEAN: up to LP predecessors per row on the straight-line path (> 2: 14 % of the rows at 10 kbp x 50) */
+        int lp[LP];                                           /* the row's first LP predecessors, known to every lane */
+#pragma unroll
+        for (int k = 0; k < LP; ++k) lp[k] = LEAN ? __shfl_sync(FULL, mypred, k) : -1;
         /* unconditional: rowmeta has n_rows + 1 entries and i + 2 <= n_rows; the predecessor index is clamped (a predicated
          * load would need a select on its result, which the compiler schedules right behind the load) */
         int2 m2;                                              /* two 32-bit loads: a 64-bit one ties up an aligned register pair that ptxas frees by
@@ -1046,17 +1048,25 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 
         /* ---- LEAN fast row: <= 2 predecessors, all in the ring, their whole bands cached there ---- */
         bool lean_row = false;
-        uint4 lm0 = make_uint4(0u, 0u, 0u, 0u), lm1 = lm0;
+        uint4 lm[LP];
+#pragma unroll
+        for (int k = 0; k < LP; ++k) lm[k] = make_uint4(0u, 0u, 0u, 0u);
         if (LEAN) {
-            lean_row = np >= 1 && np <= 2 && (i - p0) <= rmask && (np < 2 || (i - p1) <= rmask);
+            lean_row = np >= 1 && np <= LP;
+#pragma unroll
+            for (int k = 0; k < LP; ++k) if (k < np && (i - lp[k]) > rmask) lean_row = false;       /* every predecessor still in the ring */
 #ifdef POA_KPROF
-            if (!lean_row) { if (np > 2 || np < 1) ++kdiag[1]; else ++kdiag[2]; }
+            if (!lean_row) { if (np > LP || np < 1) ++kdiag[1]; else ++kdiag[2]; }
 #endif
             if (lean_row) {
-                lm0 = ring_meta[p0 & rmask];
-                lm1 = np == 2 ? ring_meta[p1 & rmask] : lm0;
-                const int png0 = (int)(lm0.y >> 3) - (int)(lm0.x >> 3) + 1, png1 = (int)(lm1.y >> 3) - (int)(lm1.x >> 3) + 1;
-                if (png0 > ring_groups || png1 > ring_groups) lean_row = false;      /* a row wider than its ring slot: only a prefix is cached */
+                lm[0] = ring_meta[lp[0] & rmask];
+                int wide = (int)(lm[0].y >> 3) - (int)(lm[0].x >> 3) + 1;
+#pragma unroll
+                for (int k = 1; k < LP; ++k) {
+                    lm[k] = k < np ? ring_meta[lp[k] & rmask] : lm[0];
+                    wide = max(wide, (int)(lm[k].y >> 3) - (int)(lm[k].x >> 3) + 1);
+                }
+                if (wide > ring_groups) lean_row = false;            /* a row wider than its ring slot: only a prefix is cached */
 #ifdef POA_KPROF
                 if (lean_row) ++kdiag[0]; else ++kdiag[3];
 #endif
@@ -1078,9 +1088,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         }
         int ml = jv.node_n, mr = 0, min_pre_beg = INT32_MAX;
         if (lean_row) {
-            ml = min(ml, (int)min(lm0.z & 0xffffu, lm1.z & 0xffffu));
-            mr = max(mr, (int)max(lm0.z >> 16, lm1.z >> 16));
-            min_pre_beg = (int)min(lm0.x, lm1.x);
+#pragma unroll
+            for (int k = 0; k < LP; ++k) {                   /* lm[k >= np] repeats lm[0]: harmless for min / max */
+                ml = min(ml, (int)(lm[k].z & 0xffffu)); mr = max(mr, (int)(lm[k].z >> 16)); min_pre_beg = min(min_pre_beg, (int)lm[k].x);
+            }
         } else if (banded) {
             ml = min(ml, __reduce_min_sync(FULL, l1));
             mr = max(mr, __reduce_max_sync(FULL, r1));
@@ -1145,13 +1156,13 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
 
             if (lean_row) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (k == 1 && np < 2) break;
-                    const uint4 mi = k == 0 ? lm0 : lm1;
+                for (int k = 0; k < LP; ++k) {
+                    if (k >= np) break;
+                    const uint4 mi = lm[k];
                     const int pg0 = (int)(mi.x >> 3), png = (int)(mi.y >> 3) - pg0 + 1;
                     const int rel = g - pg0;
                     const bool inr = active && (unsigned)rel < (unsigned)png;
-                    const uint32_t prs = ring_s + (uint32_t)((k == 0 ? p0 : p1) & rmask) * ring_row_bytes;
+                    const uint32_t prs = ring_s + (uint32_t)(lp[k] & rmask) * ring_row_bytes;
                     uint4 hp = make_uint4(NEGP2, NEGP2, NEGP2, NEGP2), ep1 = hp, ep2 = hp;
                     if (inr) {
                         const uint32_t a = prs + (uint32_t)rel * 16u;
