@@ -40,7 +40,8 @@ class abpoa_gpu_stats_t(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_workers", C.c_int), ("device", C.c_int),
                 ("fwd_clk", C.c_int64), ("bt_clk", C.c_int64),
                 ("chain_device_ms", C.c_double), ("chain_cells", C.c_int64), ("chain_groups", C.c_int), ("chain_fallback_groups", C.c_int),
-                ("chain_dp_ms", C.c_double), ("chain_fuse_ms", C.c_double), ("chain_dp_launches", C.c_int64)]
+                ("chain_dp_ms", C.c_double), ("chain_fuse_ms", C.c_double), ("chain_dp_launches", C.c_int64),
+                ("chain_wait_ms", C.c_double), ("chain_free_running", C.c_int)]
 
 
 class abpoa_gpu_replay_t(C.Structure):

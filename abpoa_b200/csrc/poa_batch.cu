@@ -195,6 +195,7 @@ extern "C" void abpoa_gpu_batch_get_stats(abpoa_gpu_batch_t *e, abpoa_gpu_stats_
     out->fwd_clk += e->chain.fwd_clk; out->bt_clk += e->chain.bt_clk;
     out->chain_device_ms = e->chain.device_ms; out->chain_cells = e->chain.cells; out->chain_groups = e->chain.groups_done; out->chain_fallback_groups = e->chain.groups_failed;
     out->chain_dp_ms = e->chain.dp_ms; out->chain_fuse_ms = e->chain.fuse_ms; out->chain_dp_launches = e->chain.dp_launches;
+    out->chain_wait_ms = e->chain.wait_ms; out->chain_free_running = e->chain.free_running;
 }
 
 extern "C" void abpoa_gpu_batch_reset_stats(abpoa_gpu_batch_t *e) {

@@ -37,6 +37,8 @@
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     poa_die("libabpoa_b200/chain", "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 
+extern "C" cudaError_t poa_launch_chain_dp_worker(int gap_mode, const int *gaps, PoaChainSlot *slots, PoaChainSync *sync, int n_groups,
+                                                  const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st);
 extern "C" cudaError_t poa_launch_chain_align_p16(int gap_mode, const int *gaps, const PoaChainSlot *slots, const int32_t *idx, int n_jobs, int round,
                                                   const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st);
 extern "C" void poa_pick_ring(int gap_mode, int bits, int band_cells, size_t smem_budget, int *ring_rows, int *ring_cells);
@@ -50,6 +52,45 @@ __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_seed_kernel(PoaChainSlo
 __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_kernel(PoaChainSlot *slots, const int32_t *idx, const PoaChainParams *cp, int n, int round) {
     if ((int)blockIdx.x >= n) return;
     chain_fuse(&slots[idx[blockIdx.x]], cp, round);
+}
+
+/* Free-running chain, fuse side: persistent CTAs draw tickets from PoaChainSync; ticket t is served when tasks[t] holds a group.
+ * (The alignment side is poa_chain_dp_worker_kernel in poa_kernels.cu.) */
+__device__ __forceinline__ int sync_ld(const int32_t *p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void sync_st(int32_t *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long sync_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_worker_kernel(PoaChainSlot *slots, PoaChainSync *sync, const PoaChainParams *cp) {
+    __shared__ int task_s;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(&sync->q_head, 1u);
+            int g = -2; unsigned ns = 64;
+            const unsigned long long t0 = sync_now_ns(), limit = sync->watchdog_ns;
+            for (;;) {
+                if ((long long)ticket >= (long long)sync_ld(&sync->total) || sync_ld(&sync->abort)) { g = -2; break; }
+                g = sync_ld(&sync->tasks[ticket]);
+                if (g >= 0) break;
+                __nanosleep(ns); if (ns < 1024) ns <<= 1;
+                /* nobody appended a task for this long: the alignment kernel is not running next to this one (a tool that
+                 * serialises kernels, a device shared with a long-running grid): give up, the launch engine finishes the groups */
+                if (sync_now_ns() - t0 > limit) { sync_st(&sync->abort, 1); g = -2; break; }
+            }
+            task_s = g;
+        }
+        __syncthreads();
+        const int g = task_s;
+        __syncthreads();
+        if (g < 0) return;
+        __threadfence();                                       /* acquire: graph arrays / CIGAR of this group may have been written from another SM */
+        PoaChainSlot *s = &slots[g];
+        const unsigned long long t0 = sync_now_ns();
+        chain_fuse(s, cp, 0);
+        __syncthreads();
+        __threadfence();                                       /* release */
+        __syncthreads();
+        if (threadIdx.x == 0) { s->fuse_ns += sync_now_ns() - t0; __threadfence(); sync_st(&s->turn, 0); }
+    }
 }
 
 /* Compact export of the final graphs (layout: poa_graph_import in poa_graph.c).  ex_off[g] = first int32 word of
@@ -174,6 +215,20 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
     int n_cohorts = [&] { const char *e = getenv("ABPOA_GPU_CHAIN_COHORTS"); return e && *e ? atoi(e) : 4; }();
     if (n_cohorts < 1) n_cohorts = 1;
     if (n_cohorts > 16) n_cohorts = 16;
+    /* free-running (default): every group advances at its own pace (PoaChainSync); ABPOA_GPU_CHAIN_ROUNDS=1: lock-step rounds,
+     * two kernels per round and cohort */
+    const bool free_run = [] {
+        const char *e = getenv("ABPOA_GPU_CHAIN_ROUNDS");
+        if (e && *e) return *e != '1';
+        /* two kernels that wait for each other need to run CONCURRENTLY: under a tool that injects into the CUDA driver and
+         * serialises kernel launches (ncu, compute-sanitizer) use the round schedule */
+        extern char **environ;
+        for (char **v = environ; v && *v; ++v)
+            if (!strncmp(*v, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*v, "NV_NSIGHT_INJECTION", 19) || !strncmp(*v, "NV_COMPUTE_PROFILER", 19) ||
+                !strncmp(*v, "NV_SANITIZER_INJECTION", 22)) return false;
+        return true;
+    }();
+    const double pool_margin = free_run ? 1.6 : 1.15;          /* private slabs cannot borrow from a neighbour that needs less */
 
     /* ---- per-group sizes ---- */
     std::vector<GroupPlan> plans;
@@ -223,7 +278,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         size_t end = pos, need_static = 0; double need_pool = 0;
         while (end < plans.size()) {
             const size_t s2 = need_static + plans[end].static_bytes + sizeof(PoaChainSlot) + 4096;
-            const double p2 = need_pool + plans[end].pool_units_est * 16.0 * 1.15;
+            const double p2 = need_pool + plans[end].pool_units_est * 16.0 * pool_margin;
             if (end > pos && (double)s2 + p2 + (64 << 20) > (double)arena_cap) break;
             need_static = s2; need_pool = p2; ++end;
         }
@@ -241,6 +296,10 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         PoaChainParams *d_cp = (PoaChainParams *)dtake(sizeof(PoaChainParams));
         PoaParamsDev *d_prm = (PoaParamsDev *)dtake(sizeof(PoaParamsDev));
         unsigned long long *d_cursors = (unsigned long long *)dtake((size_t)32 * sizeof(unsigned long long));       /* 2 per cohort, <= 16 cohorts */
+        PoaChainSync *d_sync = (PoaChainSync *)dtake(sizeof(PoaChainSync));
+        int64_t n_tasks = 0;
+        for (int t = 0; t < nw; ++t) n_tasks += plans[pos + t].n_reads - 1;
+        int32_t *d_tasks = (int32_t *)dtake((size_t)std::max<int64_t>(n_tasks, 1) * 4);
 
         /* pinned staging: slots | params | reads + offsets + w of every group | round index lists */
         std::vector<PoaChainSlot> hs((size_t)nw);
@@ -250,6 +309,8 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         uint8_t *d_reads = dtake(reads_bytes);
         size_t roff = 0;
         int max_reads = 0, band_cells = 64;
+        struct ReadCopy { uint8_t *dst; int g; };
+        std::vector<ReadCopy> read_copies((size_t)nw);
         for (int t = 0; t < nw; ++t) {
             const GroupPlan &p = plans[pos + t];
             const abpoa_gpu_group_t &in = groups[p.g];
@@ -266,8 +327,8 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             uint8_t *hr = h_reads + roff; const size_t rb = al256((size_t)p.bases), ob = al256(((size_t)p.n_reads + 1) * 4);
             int32_t *hoff = (int32_t *)(hr + rb), *hw = (int32_t *)(hr + rb + ob);
             int acc = 0;
+            read_copies[t] = { hr, p.g };
             for (int i = 0; i < p.n_reads; ++i) {
-                memcpy(hr + acc, in.seqs[i], (size_t)in.seq_lens[i]);
                 hoff[i] = acc; acc += in.seq_lens[i];
                 hw[i] = poa_band_halfwidth(abpt, in.seq_lens[i]);
                 const int bc = (2 * hw[i] + 1 + 104 + 7) / 8 * 8;
@@ -288,13 +349,30 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             if (record) { s.rec_score = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_nops = (int32_t *)dtake((size_t)p.n_reads * 4); s.rec_hash = (uint64_t *)dtake((size_t)p.n_reads * 8); }
             if (p.n_reads > max_reads) max_reads = p.n_reads;
         }
+        /* the read bytes themselves: half a gigabyte at BASELINE size, copied into the pinned buffer by all workers */
+        {
+            std::atomic<int> nx(0);
+            auto copy_reads = [&]() {
+                for (int t; (t = nx.fetch_add(1)) < nw;) {
+                    const abpoa_gpu_group_t &in = groups[read_copies[t].g];
+                    uint8_t *q = read_copies[t].dst;
+                    for (int i = 0; i < in.n_seq; ++i) { memcpy(q, in.seqs[i], (size_t)in.seq_lens[i]); q += in.seq_lens[i]; }
+                }
+            };
+            const int nth = reads_bytes < (8u << 20) ? 1 : std::max(1, std::min(n_workers, 16));
+            std::vector<std::thread> th;
+            for (int w = 1; w < nth; ++w) th.emplace_back(copy_reads);
+            copy_reads();
+            for (auto &x : th) x.join();
+        }
+        const double t_staged = now_ms();
         /* round index lists per cohort: wave-local slot indices of the groups that still have a read r */
         /* cohorts: each cohort's alignment kernel is one CTA (warp) per group; with at most one CTA per SM per cohort the
          * concurrently running kernels of all cohorts load every SM alike (a 250-CTA grid next to three more would put
          * twice as many warps on the first 102 SMs as on the rest, and a round ends when its slowest warp does) */
-        int sm_count = 148; { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) sm_count = pr.multiProcessorCount; }
+        int sm_count = 148; if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count < 1) sm_count = 148;
         const int auto_cohorts = std::max(1, std::min(16, (nw + sm_count - 1) / sm_count));
-        const int use_cohorts = getenv("ABPOA_GPU_CHAIN_COHORTS") ? n_cohorts : auto_cohorts;
+        const int use_cohorts = free_run ? 1 : (getenv("ABPOA_GPU_CHAIN_COHORTS") ? n_cohorts : auto_cohorts);
         std::vector<Cohort> coh((size_t)std::min(use_cohorts, nw));
         for (int t = 0; t < nw; ++t) coh[(size_t)t % coh.size()].members.push_back(t);
         std::vector<int32_t> h_idx; std::vector<std::vector<std::pair<size_t, int>>> round_of(coh.size());   /* (offset into h_idx, count) per round */
@@ -329,7 +407,14 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         /* pool shares per cohort, proportional to the estimates */
         std::vector<double> est(coh.size(), 0.0); double est_tot = 0;
         for (size_t c = 0; c < coh.size(); ++c) { for (int t : coh[c].members) est[c] += plans[pos + t].pool_units_est; est_tot += est[c]; }
-        {
+        if (free_run) {
+            size_t o = 0;
+            for (int t = 0; t < nw; ++t) {
+                const size_t share = (size_t)((double)pool_bytes * plans[pos + t].pool_units_est / est_tot) & ~(size_t)255;
+                hs[t].pool_base = d_pool + o; hs[t].pool_units = share / 16; hs[t].pool_cursor = NULL;
+                o += share;
+            }
+        } else {
             size_t o = 0;
             for (size_t c = 0; c < coh.size(); ++c) {
                 const size_t share = c + 1 == coh.size() ? pool_bytes - o : (size_t)((double)pool_bytes * est[c] / est_tot) & ~(size_t)255;
@@ -365,12 +450,39 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         poa_pick_ring(abpt->gap_mode, 16, band_cells, smem_budget, &ring_rows, &ring_cells);
         int64_t launches = 1;
         const int gaps[4] = { abpt->gap_ext1, abpt->gap_open1 + abpt->gap_ext1, abpt->gap_ext2, abpt->gap_open2 + abpt->gap_ext2 };
-        for (size_t c = 0; c < coh.size(); ++c) {
-            cudaStream_t st = coh[c].st;
-            if (c > 0) CK(cudaStreamWaitEvent(st, ev_up, 0));
-            for (int r = 1; r <= n_rounds; ++r) {
+        const double t_uploaded = now_ms();
+        for (size_t c = 1; c < coh.size(); ++c) CK(cudaStreamWaitEvent(coh[c].st, ev_up, 0));
+        cudaStream_t st_dp = NULL;
+        if (free_run) {
+            /* two persistent kernels: the fuse workers first (one CTA per SM; they must be resident while alignment warps
+             * wait for them -- 10 alignment CTAs, the most one SM takes, leave registers and shared memory for one), then one
+             * alignment warp per group */
+            static const double watchdog_s = [] { const char *e = getenv("ABPOA_GPU_CHAIN_WATCHDOG_S"); return e && *e ? atof(e) : 30.0; }();
+            static const int fuse_per_sm = [] { const char *e = getenv("ABPOA_GPU_CHAIN_FUSE_PER_SM"); return e && *e ? std::max(1, atoi(e)) : 1; }();
+            PoaChainSync hsync; memset(&hsync, 0, sizeof hsync);
+            hsync.total = (int32_t)n_tasks; hsync.watchdog_ns = (unsigned long long)(watchdog_s * 1e9); hsync.tasks = d_tasks;
+            CK(cudaMemcpyAsync(d_sync, &hsync, sizeof hsync, cudaMemcpyHostToDevice, s0));
+            CK(cudaMemsetAsync(d_tasks, 0xff, (size_t)std::max<int64_t>(n_tasks, 1) * 4, s0));
+            CK(cudaStreamCreateWithFlags(&st_dp, cudaStreamNonBlocking));
+            cudaEvent_t ev_sync; CK(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
+            CK(cudaEventRecord(ev_sync, s0));
+            const int n_fuse = std::max(1, std::min(nw, sm_count * fuse_per_sm));
+            poa_chain_fuse_worker_kernel<<<n_fuse, POA_CHAIN_T, 0, s0>>>(d_slots, d_sync, d_cp);
+            CK(cudaGetLastError());
+            CK(cudaStreamWaitEvent(st_dp, ev_sync, 0));
+            CK(poa_launch_chain_dp_worker(abpt->gap_mode, gaps, d_slots, d_sync, nw, d_prm, ring_rows, ring_cells, st_dp));
+            cudaEvent_t ev_dp; CK(cudaEventCreateWithFlags(&ev_dp, cudaEventDisableTiming));
+            CK(cudaEventRecord(ev_dp, st_dp));
+            CK(cudaStreamWaitEvent(s0, ev_dp, 0));
+            CK(cudaEventDestroy(ev_sync)); CK(cudaEventDestroy(ev_dp));
+            launches += 2;
+        }
+        /* round-major enqueue: every cohort's stream gets its first kernels at once */
+        for (int r = 1; r <= (free_run ? 0 : n_rounds); ++r)
+            for (size_t c = 0; c < coh.size(); ++c) {
+                cudaStream_t st = coh[c].st;
                 const std::pair<size_t, int> &ro = round_of[c][(size_t)r - 1];
-                if (ro.second == 0) break;
+                if (ro.second == 0) continue;
                 cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
                 coh[c].marks.push_back(e0); coh[c].marks.push_back(e1); coh[c].marks.push_back(e2);
                 CK(cudaEventRecord(e0, st));
@@ -381,8 +493,8 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                 CK(cudaEventRecord(e2, st));
                 launches += 2;
             }
-            CK(cudaEventRecord(coh[c].ev_end, st));
-        }
+        for (size_t c = 0; c < coh.size(); ++c) CK(cudaEventRecord(coh[c].ev_end, coh[c].st));
+        const double t_enqueued = now_ms();
         for (size_t c = 1; c < coh.size(); ++c) CK(cudaStreamWaitEvent(s0, coh[c].ev_end, 0));
         CK(cudaEventRecord(ev_t1, s0));
         /* ---- results.  Default: heaviest-bundling consensus on the device, only consensus bytes come back.
@@ -415,6 +527,18 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         }
         memcpy(fin.data(), h_fin, (size_t)nw * sizeof(PoaChainSlot));
         pinned_put(1, h_fin);
+        double wait_ms = 0;
+        if (free_run) {                   /* no per-launch marks: time inside the alignments (SM cycles) and inside chain_fuse, summed over groups */
+            int khz = 0; if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+            for (int t = 0; t < nw; ++t) {
+                dp_ms += (double)(fin[t].fwd_clk + fin[t].bt_clk) / (double)khz; fuse_ms += (double)fin[t].fuse_ns * 1e-6; wait_ms += (double)fin[t].wait_ns * 1e-6;
+                n_marks += fin[t].fused > 0 ? fin[t].fused - 1 : 0;
+            }
+            CK(cudaStreamDestroy(st_dp));
+            PoaChainSync hs2; CK(cudaMemcpy(&hs2, d_sync, sizeof hs2, cudaMemcpyDeviceToHost));
+            if (hs2.abort) fprintf(stderr, "[libabpoa_b200/chain] watchdog: the alignment and the fuse kernel did not make progress together within ABPOA_GPU_CHAIN_WATCHDOG_S; "
+                                           "unfinished groups go to the launch engine (ABPOA_GPU_CHAIN_ROUNDS=1 selects the round schedule)\n");
+        }
         const double t_dev_done = now_ms();
         /* ---- device consensus: record offsets, then one copy of all records ---- */
         std::vector<int64_t> recoff((size_t)nw, -1); int32_t *h_cons = NULL; unsigned long long cons_words = 0;
@@ -517,12 +641,15 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; stats->groups_done += nw - n_failed.load(); stats->groups_failed += n_failed.load();
             stats->fwd_clk += fwd_clk; stats->bt_clk += bt_clk;
             stats->dp_ms += dp_ms; stats->fuse_ms += fuse_ms; stats->dp_launches += n_marks; stats->fuse_launches += n_marks;
+            stats->wait_ms += wait_ms; stats->free_running = free_run ? 1 : 0;
         }
         if (verbose)
-            fprintf(stderr, "[chain] DP kernels %.1f ms + fuse kernels %.1f ms summed over %zu concurrent cohort streams (%lld rounds)\n", dp_ms, fuse_ms, coh.size(), (long long)n_marks),
-            fprintf(stderr, "[chain] wave of %d groups (%zu cohorts, K=%d): stage+launch+device %.0f ms (device %.1f ms), export copy %.0f ms, import+consensus %.0f ms; "
+            free_run ? fprintf(stderr, "[chain] free-running: per group on average %.1f ms inside alignments + %.1f ms inside fuse (waited %.1f ms for fuse workers incl. the fuse itself), %lld alignments\n",
+                               dp_ms / nw, fuse_ms / nw, wait_ms / nw, (long long)n_marks)
+                     : fprintf(stderr, "[chain] DP kernels %.1f ms + fuse kernels %.1f ms summed over %zu concurrent cohort streams (%lld rounds)\n", dp_ms, fuse_ms, coh.size(), (long long)n_marks),
+            fprintf(stderr, "[chain] wave of %d groups (%zu cohorts, K=%d): stage %.0f + upload-enqueue %.0f + launch-enqueue %.0f ms, stage+launch+device %.0f ms (device %.1f ms), export copy %.0f ms, import+consensus %.0f ms; "
                             "static %.2f GB, pool %.2f GB, export %.1f MB; %d groups handed to the launch engine\n",
-                    nw, coh.size(), K, t_dev_done - t_wave0, dev_ms, t_copied - t_dev_done, now_ms() - t_copied,
+                    nw, coh.size(), K, t_staged - t_wave0, t_uploaded - t_staged, t_enqueued - t_uploaded, t_dev_done - t_wave0, dev_ms, t_copied - t_dev_done, now_ms() - t_copied,
                     (double)doff / 1e9, (double)pool_bytes / 1e9, (double)tot_words * 4 / 1e6, n_failed.load());
         pos = end;
     }

@@ -89,9 +89,26 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
      * pool (exact size: rows x band estimate x planes).  Two cursors alternate by round parity -- the DP kernel of
      * round r zeroes the one the fuse kernel of round r fills for round r + 1 -- over the SAME memory. */
     uint8_t *pool_base; unsigned long long *pool_cursor; uint64_t pool_units;
+    /* free-running mode (no rounds): pool_cursor == NULL, [pool_base, pool_units) is the group's PRIVATE plane slab, and the
+     * alignment warp and the fuse workers hand the slot back and forth through `turn` (PoaChainSync below) */
+    int32_t turn;                       /* 0: the alignment warp's move, 1: a fuse worker's move */
+    int32_t rsv0;
+    unsigned long long wait_ns, fuse_ns;        /* time the alignment warp waited for its fuse tasks / time inside chain_fuse */
     /* per-read records (record mode) */
     int32_t *rec_score, *rec_nops; uint64_t *rec_hash;
 } PoaChainSlot;
+
+/* Free-running chain: every group advances at its own pace.  One resident warp per group runs its alignments back to back;
+ * after each one it appends the group to `tasks` and waits; persistent fuse CTAs draw tickets, fuse + flatten the group and
+ * hand it back.  `total` = fuse tasks that will ever be appended (lowered when a group leaves the chain early): a worker
+ * whose ticket is >= total exits. */
+typedef struct PoaChainSync {
+    unsigned int q_head, q_tail;        /* next ticket / next free task slot */
+    int32_t total;
+    int32_t abort;                      /* set by a waiter whose partner did not answer within the watchdog time */
+    unsigned long long watchdog_ns;
+    int32_t *tasks;                     /* [sum over groups of (n_reads - 1)], initialised to -1 */
+} PoaChainSync;
 
 /* ------------------------------------------------------------------ block-wide helpers */
 #ifdef POA_CHAIN_EMUL
@@ -293,9 +310,13 @@ POA_DEV void chain_flatten(PoaChainSlot *s, const PoaChainParams *cp, const int3
             const unsigned long long full = (unsigned long long)((qlen + 1 + 7) / 8 + 1);
             if (generous || per_row > full) per_row = full;
             const unsigned long long units = per_row * (unsigned long long)cp->P * (unsigned long long)n;
-            const unsigned long long at = atomicAdd(&s->pool_cursor[pool_parity & 1], units);
-            if (at + units > s->pool_units) POA_ATOMIC_OR(&s->failed, POA_CF_POOL);
-            else { s->jd.planes = s->pool_base + (size_t)at * (POA_GROUP * 2); s->jd.plane_cap_units = units; }
+            if (!s->pool_cursor) {                                     /* private slab: the job may use all of it */
+                s->jd.planes = s->pool_base; s->jd.plane_cap_units = s->pool_units;
+            } else {
+                const unsigned long long at = atomicAdd(&s->pool_cursor[pool_parity & 1], units);
+                if (at + units > s->pool_units) POA_ATOMIC_OR(&s->failed, POA_CF_POOL);
+                else { s->jd.planes = s->pool_base + (size_t)at * (POA_GROUP * 2); s->jd.plane_cap_units = units; }
+            }
         }
 #endif
     }
@@ -354,7 +375,7 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp, int round) {
     if (s->failed || r >= s->n_reads) return;
     const PoaResultDev *res = s->jd.result;
     if (res->status == POA_ST_SKIP) return;               /* nothing ran for this slot in this round */
-    if (res->status == POA_ST_PLANE_OVF && !s->retry) {   /* band wider than the slab: same read again, full-rectangle slab */
+    if (res->status == POA_ST_PLANE_OVF && !s->retry && s->pool_cursor) {   /* band wider than the slab: same read again, full-rectangle slab */
         POA_CTA_SYNC();
         if (POA_TID0) s->retry = 1;
         chain_flatten(s, cp, s->order[s->cur], s->n_nodes, r, round + 1, 1);

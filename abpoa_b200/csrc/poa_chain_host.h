@@ -14,6 +14,9 @@ typedef struct {
                                            (cohorts run concurrently: dp_ms + fuse_ms ~ n_cohorts x device_ms) */
     int64_t dp_launches, fuse_launches;
     int64_t fwd_clk, bt_clk;            /* SM cycles inside the forward DP / the backtrace, summed over alignments */
+    double wait_ms;                     /* free-running mode: time the alignment warps waited for their fuse tasks, summed over groups
+                                           (then dp_ms / fuse_ms are per-group sums of time inside the alignments / inside chain_fuse) */
+    int free_running;
 } PoaChainStats;
 
 /* may this parameter set run on the device chain at all? */

@@ -29,6 +29,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "poa_device.cuh"
 #include "poa_chain.cuh"
 
@@ -1533,6 +1534,85 @@ __global__ void POA_P16_BOUNDS poa_chain_align_kernel_p16(const PoaChainSlot *__
     if (sl->failed || sl->fused >= sl->n_reads || n_rows < 3) { if (lane == 0) jd.result->status = POA_ST_SKIP; return; }
     const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
     p16_run_job<GAP, GLOBAL, true, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
+}
+
+/* Free-running chain (PoaChainSync in poa_chain.cuh): one resident warp per group runs the group's alignments back to
+ * back.  Between two alignments the slot belongs to a fuse worker (poa_chain_fuse_worker_kernel); the hand-over is a
+ * release store / relaxed poll + acquire fence pair on slot->turn, so nothing read here is stale in this SM's L1. */
+__device__ __forceinline__ int chain_ld_relaxed(const int32_t *p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void chain_st_relaxed(int32_t *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long chain_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+template <int GAP, bool TMA>
+__global__ void POA_P16_BOUNDS poa_chain_dp_worker_kernel(PoaChainSlot *slots, PoaChainSync *sync, const PoaParamsDev *__restrict__ prm, int n_groups,
+                                                          int ring_rows, int ring_cells, const __grid_constant__ P16Consts kc) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const int lane = threadIdx.x;
+    const int g = blockIdx.x;
+    if (g >= n_groups) return;
+    PoaChainSlot *sl = &slots[g];
+    const P16Smem sm = p16_smem_init(dyn_smem, prm, ring_rows, lane);
+    const unsigned long long limit = sync->watchdog_ns;
+    int pushed = 0;
+    unsigned long long waited = 0;
+    for (;;) {
+        /* ---- wait for the slot ---- */
+        int state = 0;                                         /* 0 go, 2 stop */
+        if (lane == 0) {
+            const unsigned long long t0 = chain_now_ns();
+            unsigned ns = 64;
+            while (chain_ld_relaxed(&sl->turn) != 0) {
+                if (chain_ld_relaxed(&sync->abort)) { state = 2; break; }
+                __nanosleep(ns); if (ns < 2048) ns <<= 1;
+                if (chain_now_ns() - t0 > limit) { chain_st_relaxed(&sync->abort, 1); state = 2; break; }
+            }
+            waited += chain_now_ns() - t0;
+        }
+        state = __shfl_sync(0xffffffffu, state, 0);
+        if (state) break;
+        __threadfence();                                       /* acquire side: also drops this SM's L1 lines of the slot / job blob */
+        const PoaJobDesc jd = sl->jd;
+        const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
+        if (sl->failed || sl->fused >= sl->n_reads || n_rows < 3) break;
+        p16_run_job<GAP, GLOBAL, true, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
+        __syncwarp();
+        __threadfence();                                       /* release side: CIGAR + result are out before the task is */
+        if (lane == 0) {
+            chain_st_relaxed(&sl->turn, 1);
+            const unsigned slot = atomicAdd(&sync->q_tail, 1u);
+            chain_st_relaxed(&sync->tasks[slot], g);
+        }
+        ++pushed;
+        __syncwarp();
+    }
+    /* the group is finished, failed or the run was aborted: fuse tasks it will never append leave the count */
+    if (lane == 0) {
+        const int never = sl->n_reads - 1 - pushed;
+        if (never > 0) atomicSub(&sync->total, never);
+        sl->wait_ns = waited;
+    }
+}
+
+template <int GAP, bool TMA>
+static cudaError_t launch_chain_worker_one(PoaChainSlot *slots, PoaChainSync *sync, int n_groups, const PoaParamsDev *prm, int ring_rows, int ring_cells,
+                                           const P16Consts &kc, cudaStream_t st) {
+    /* at least 23 KB: at most 9 of these CTAs fit one SM, which leaves registers (9 x 160 x 32 of 64 K) and shared memory for a
+     * 256-thread fuse worker next to them even if the alignment warps were dispatched first -- they wait for fuse workers */
+    const size_t smem = std::max<size_t>(ring_smem_bytes(GAP, 16, ring_rows, ring_cells, TMA) + 18 * sizeof(uint4), (size_t)23 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    poa_chain_dp_worker_kernel<GAP, TMA><<<n_groups, 32, smem, st>>>(slots, sync, prm, n_groups, ring_rows, ring_cells, kc);
+    return cudaGetLastError();
+}
+extern "C" int poa_tma_enabled(void);
+extern "C" cudaError_t poa_launch_chain_dp_worker(int gap_mode, const int *gaps, PoaChainSlot *slots, PoaChainSync *sync, int n_groups,
+                                                  const PoaParamsDev *prm, int ring_rows, int ring_cells, cudaStream_t st) {
+    if (n_groups <= 0) return cudaSuccess;
+    const P16Consts kc = make_p16_consts(gaps[0], gaps[1], gaps[2], gaps[3]);
+    const bool tma = poa_tma_enabled() && ring_rows >= 2;
+    if (gap_mode == LG) return tma ? launch_chain_worker_one<LG, true>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st) : launch_chain_worker_one<LG, false>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st);
+    if (gap_mode == AG) return tma ? launch_chain_worker_one<AG, true>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st) : launch_chain_worker_one<AG, false>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st);
+    return tma ? launch_chain_worker_one<CG, true>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st) : launch_chain_worker_one<CG, false>(slots, sync, n_groups, prm, ring_rows, ring_cells, kc, st);
 }
 
 template <int GAP, bool TMA>

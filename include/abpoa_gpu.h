@@ -64,6 +64,10 @@ typedef struct {
     double chain_device_ms; int64_t chain_cells; int chain_groups, chain_fallback_groups;
     /* per-launch CUDA-event times of its two kernels summed over rounds and over the concurrent cohort streams */
     double chain_dp_ms, chain_fuse_ms; int64_t chain_dp_launches;
+    /* free-running chain (the default; ABPOA_GPU_CHAIN_ROUNDS=1 selects lock-step rounds): chain_dp_ms / chain_fuse_ms are then
+     * sums over GROUPS of the time spent inside alignments / inside the fuse step, chain_wait_ms of the time alignment warps
+     * waited for a fuse worker (queueing + the fuse itself), chain_dp_launches the number of alignments */
+    double chain_wait_ms; int chain_free_running;
 } abpoa_gpu_stats_t;
 
 #define ABPOA_GPU_RECORD_READS 0x1

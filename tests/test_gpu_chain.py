@@ -14,6 +14,17 @@ from helpers import run_group
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["free-running", "rounds"])
+def chain_mode(request, monkeypatch):
+    """Every test runs on both schedules of the chain engine: free-running groups (two persistent kernels, the default) and
+    lock-step rounds (two kernels per round and cohort)."""
+    if request.param == "rounds":
+        monkeypatch.setenv("ABPOA_GPU_CHAIN_ROUNDS", "1")
+    else:
+        monkeypatch.delenv("ABPOA_GPU_CHAIN_ROUNDS", raising=False)
+    return request.param
+
+
 def check(reference_lib, cfg, groups, expect_chain=None, expect_fallback=None, **engine_kw):
     with BatchEngine(**engine_kw) as eng:
         got = eng.run(cfg, groups, record_reads=True)
@@ -111,3 +122,11 @@ def test_chain_graph_export_cross_check(reference_lib, monkeypatch):
     check(reference_lib, PoaConfig(), groups, expect_chain=6, expect_fallback=0)
     monkeypatch.setenv("ABPOA_GPU_CHAIN_EXPORT_GRAPH", "1")
     check(reference_lib, PoaConfig(), groups, expect_chain=6, expect_fallback=0)
+
+
+def test_chain_more_groups_than_resident_warps(reference_lib, chain_mode):
+    """1600 tiny groups: more than the alignment warps one B200 keeps resident (9 per SM), so late groups start when early ones
+    have left; the fuse queue sees every group several times."""
+    groups = [synth.make_group(6000 + g, 3 + g % 3, 60 + g % 50, 0.06) for g in range(1600)]
+    st = check(reference_lib, PoaConfig(**AFFINE), groups, expect_chain=1600, expect_fallback=0)
+    assert st["chain_free_running"] == (1 if chain_mode == "free-running" else 0)
