@@ -236,22 +236,37 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     while (i > 0 && j > 0) {
         /* ---- shortcut: while a match is the first thing the reference would test and the row's bitmap says the first
          *      predecessor's diagonal explains the cell, the step is MATCH -> (p0, j-1) (src/abpoa_align_simd.c:211-227) and
-         *      everything it needs sits in one 64-byte record per row (PoaBtRec).  Records of the rows just below are
-         *      prefetched: the first predecessor is almost always within a few rows. ---- */
+         *      everything it needs sits in one 64-byte record per row (PoaBtRec).  The records were written long ago (HBM
+         *      latency), so the walk SPECULATES: lane L assumes the L steps before it were such matches along rows i, i-1, ...
+         *      (the first predecessor is the previous row on the path most reads take) and tests row i-L, column j-L.  One
+         *      round of 32 independent record loads then advances the walk by the length of the confirmed prefix, its
+         *      graph-CIGAR words go out as one coalesced store, and the records of the next 32 rows are prefetched. ---- */
         if (btrec != nullptr && MODE != LOCAL && !gap_on_right) {
             bool moved = false;
             while (i > 0 && j > 0 && (GAP == LG || (cur & OP_M)) && !gap_at_end) {
-                const uint8_t *rec = reinterpret_cast<const uint8_t *>(btrec + i);
-                const uint4 hd = *reinterpret_cast<const uint4 *>(rec);            /* c0, p0, base | valid << 8, bits[0..3] */
-                const int kbit = j - (int)hd.x;
-                if (!((hd.z >> 8) & 0xffu) || (unsigned)kbit >= (unsigned)POA_BTREC_BITS) break;
-                const unsigned byte = rec[12 + (kbit >> 3)];
-                if (!((byte >> (kbit & 7)) & 1u)) break;
-                start_i = i; start_j = j;
-                cg.match(i, j - 1);
-                ++n_aln; n_match += ((int)(hd.z & 0xffu) == (int)jv.qs[j]);
-                i = (int)hd.y; --j; cur = OP_ALL; moved = true;
-                if (i >= 6) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 6)));
+                const int ri = i - lane, cj = j - lane;
+                bool step_ok = false, cont = false; int rp0 = 0, same = 0;
+                if (ri > 0 && cj > 0) {
+                    const uint8_t *rec = reinterpret_cast<const uint8_t *>(btrec + ri);
+                    const uint4 hd = *reinterpret_cast<const uint4 *>(rec);        /* c0, p0, base | valid << 8, bits[0..3] */
+                    const int kbit = cj - (int)hd.x;
+                    if (((hd.z >> 8) & 0xffu) && (unsigned)kbit < (unsigned)POA_BTREC_BITS)
+                        step_ok = (rec[12 + (kbit >> 3)] >> (kbit & 7)) & 1u;
+                    rp0 = (int)hd.y; cont = rp0 == ri - 1;
+                    same = (int)(hd.z & 0xffu) == (int)jv.qs[cj];
+                }
+                const unsigned b_step = __ballot_sync(FULL, step_ok), b_cont = __ballot_sync(FULL, cont);
+                const unsigned run = b_step & ((b_cont << 1) | 1u);               /* step L happens iff steps 0..L-1 did and led to row i-L */
+                const int r = run == FULL ? 32 : __ffs(~run) - 1;
+                if (r == 0) break;
+                cg.flush();
+                if (lane < r) { if (cg.n + lane < cg.cap) cg.out[cg.n + lane] = ((uint64_t)ri << 34) | ((uint64_t)(cj - 1) << 4); }
+                if (cg.n + r > cg.cap) cg.ovf = 1;
+                cg.n += r;
+                n_aln += r; n_match += __popc(__ballot_sync(FULL, lane < r && same));
+                start_i = i - (r - 1); start_j = j - (r - 1);
+                i = __shfl_sync(FULL, rp0, r - 1); j -= r; cur = OP_ALL; moved = true;
+                if (i - 32 - lane > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 32 - lane)));
             }
             if (moved) {                               /* back to the general step: rebuild its view of (i, j) */
                 if (!(i > 0 && j > 0)) break;
