@@ -65,16 +65,20 @@ __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_worker_kernel(PoaC
     for (;;) {
         if (threadIdx.x == 0) {
             const unsigned ticket = atomicAdd(&sync->q_head, 1u);
-            int g = -2; unsigned ns = 64;
+            int g = -2; unsigned ns = 250, polls = 0;
             const unsigned long long t0 = sync_now_ns(), limit = sync->watchdog_ns;
+            const int32_t *tasks = sync->tasks;
             for (;;) {
-                if ((long long)ticket >= (long long)sync_ld(&sync->total) || sync_ld(&sync->abort)) { g = -2; break; }
-                g = sync_ld(&sync->tasks[ticket]);
+                /* the ticket's own task word is what is polled; the shared words (total, abort) and the clock only every 32nd time */
+                if ((polls++ & 31u) == 0) {
+                    if ((long long)ticket >= (long long)sync_ld(&sync->total) || sync_ld(&sync->abort)) { g = -2; break; }
+                    /* nobody appended a task for this long: the alignment kernel is not running next to this one (a tool that
+                     * serialises kernels, a device shared with a long-running grid): give up, the launch engine finishes the groups */
+                    if (polls > 1 && sync_now_ns() - t0 > limit) { sync_st(&sync->abort, 1); g = -2; break; }
+                }
+                g = sync_ld(&tasks[ticket]);
                 if (g >= 0) break;
-                __nanosleep(ns); if (ns < 1024) ns <<= 1;
-                /* nobody appended a task for this long: the alignment kernel is not running next to this one (a tool that
-                 * serialises kernels, a device shared with a long-running grid): give up, the launch engine finishes the groups */
-                if (sync_now_ns() - t0 > limit) { sync_st(&sync->abort, 1); g = -2; break; }
+                __nanosleep(ns); if (ns < 4000) ns <<= 1;
             }
             task_s = g;
         }
@@ -228,7 +232,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
                 !strncmp(*v, "NV_SANITIZER_INJECTION", 22)) return false;
         return true;
     }();
-    const double pool_margin = free_run ? 1.6 : 1.15;          /* private slabs cannot borrow from a neighbour that needs less */
+    const double pool_margin = 1.15;
 
     /* ---- per-group sizes ---- */
     std::vector<GroupPlan> plans;
@@ -274,14 +278,26 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
     const size_t arena_cap = poa_arena_capacity(arena);
     size_t pos = 0;
     std::vector<abpoa_t *> handles;
-    while (pos < plans.size()) {
-        size_t end = pos, need_static = 0; double need_pool = 0;
-        while (end < plans.size()) {
+    /* how many groups fit one wave; when several waves are needed they get equal shares (a small tail wave would leave the
+     * device nearly empty for as long as a full one takes: a wave lasts as long as one group's chain) */
+    auto fit_from = [&](size_t from, size_t limit, size_t *need_static_out, double *need_pool_out) {
+        size_t end = from, need_static = 0; double need_pool = 0;
+        while (end < plans.size() && end - from < limit) {
             const size_t s2 = need_static + plans[end].static_bytes + sizeof(PoaChainSlot) + 4096;
             const double p2 = need_pool + plans[end].pool_units_est * 16.0 * pool_margin;
-            if (end > pos && (double)s2 + p2 + (64 << 20) > (double)arena_cap) break;
+            if (end > from && (double)s2 + p2 + (64 << 20) > (double)arena_cap) break;
             need_static = s2; need_pool = p2; ++end;
         }
+        if (need_static_out) *need_static_out = need_static;
+        if (need_pool_out) *need_pool_out = need_pool;
+        return end;
+    };
+    size_t n_waves = 0;
+    for (size_t q = 0; q < plans.size(); ++n_waves) q = fit_from(q, plans.size(), NULL, NULL);
+    const size_t per_wave = (plans.size() + n_waves - 1) / std::max<size_t>(n_waves, 1);
+    while (pos < plans.size()) {
+        size_t need_static = 0; double need_pool = 0;
+        const size_t end = fit_from(pos, per_wave, &need_static, &need_pool);
         if ((double)need_static + need_pool * 0.5 + (64 << 20) > (double)arena_cap) {       /* a single group that does not fit */
             fallback.push_back(plans[pos].g); ++pos; continue;
         }
@@ -466,7 +482,8 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             CK(cudaStreamCreateWithFlags(&st_dp, cudaStreamNonBlocking));
             cudaEvent_t ev_sync; CK(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
             CK(cudaEventRecord(ev_sync, s0));
-            const int n_fuse = std::max(1, std::min(nw, sm_count * fuse_per_sm));
+            static const int fuse_cap = [] { const char *e = getenv("ABPOA_GPU_CHAIN_FUSE_WORKERS"); return e && *e ? std::max(1, atoi(e)) : (1 << 30); }();
+            const int n_fuse = std::max(1, std::min(std::min(nw, sm_count * fuse_per_sm), fuse_cap));
             poa_chain_fuse_worker_kernel<<<n_fuse, POA_CHAIN_T, 0, s0>>>(d_slots, d_sync, d_cp);
             CK(cudaGetLastError());
             CK(cudaStreamWaitEvent(st_dp, ev_sync, 0));

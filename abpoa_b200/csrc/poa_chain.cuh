@@ -103,11 +103,14 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
  * hand it back.  `total` = fuse tasks that will ever be appended (lowered when a group leaves the chain early): a worker
  * whose ticket is >= total exits. */
 typedef struct PoaChainSync {
-    unsigned int q_head, q_tail;        /* next ticket / next free task slot */
-    int32_t total;
-    int32_t abort;                      /* set by a waiter whose partner did not answer within the watchdog time */
+    /* every word that is polled or bumped sits in its own 128-byte line: a thousand waiting warps must not queue up on the
+     * L2 line the queue counters live in (they poll their OWN slot / task word, and look at `abort` / `total` only now and then) */
+    unsigned int q_head; int32_t pad0[31];      /* next ticket */
+    unsigned int q_tail; int32_t pad1[31];      /* next free task slot */
+    int32_t total; int32_t pad2[31];
+    int32_t abort; int32_t pad3[31];            /* set by a waiter whose partner did not answer within the watchdog time */
     unsigned long long watchdog_ns;
-    int32_t *tasks;                     /* [sum over groups of (n_reads - 1)], initialised to -1 */
+    int32_t *tasks;                             /* [sum over groups of (n_reads - 1)], initialised to -1 */
 } PoaChainSync;
 
 /* ------------------------------------------------------------------ block-wide helpers */

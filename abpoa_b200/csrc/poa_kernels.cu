@@ -1574,12 +1574,16 @@ __global__ void POA_P16_BOUNDS poa_chain_dp_worker_kernel(PoaChainSlot *slots, P
         /* ---- wait for the slot ---- */
         int state = 0;                                         /* 0 go, 2 stop */
         if (lane == 0) {
+            /* poll the slot's own word, gently (a fuse takes a millisecond or more; a thousand warps wait like this at
+             * once); the shared abort flag and the clock are looked at every 64th poll */
             const unsigned long long t0 = chain_now_ns();
-            unsigned ns = 64;
+            unsigned ns = 500, polls = 0;
             while (chain_ld_relaxed(&sl->turn) != 0) {
-                if (chain_ld_relaxed(&sync->abort)) { state = 2; break; }
-                __nanosleep(ns); if (ns < 2048) ns <<= 1;
-                if (chain_now_ns() - t0 > limit) { chain_st_relaxed(&sync->abort, 1); state = 2; break; }
+                __nanosleep(ns); if (ns < 8000) ns <<= 1;
+                if ((++polls & 63u) == 0) {
+                    if (chain_ld_relaxed(&sync->abort)) { state = 2; break; }
+                    if (chain_now_ns() - t0 > limit) { chain_st_relaxed(&sync->abort, 1); state = 2; break; }
+                }
             }
             waited += chain_now_ns() - t0;
         }

@@ -390,13 +390,11 @@ def main():
     for cand in (ROOT / "profiles" / f"r02_ncu_traffic_{gapname}.json", ROOT / "profiles" / "r01_ncu_traffic.json"):
         if cand.exists():
             t_ = json.loads(cand.read_text())
-            if gapname not in t_.get("kernel", gapname) and "r01" not in cand.name:
-                continue
             if cand.name.startswith("r01") and P != 5:
                 continue
             traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
             dram_frac = traffic / (t_["duration_ms"] / 1e3) / 1e9 / peak
-            traffic_note = (f"ncu capture of one replay launch ({t_['jobs']} jobs, {t_['duration_ms']:.1f} ms): "
+            traffic_note = (f"ncu capture of one launch of {t_.get('kernel', 'the kernel').split('(')[0]} ({t_['jobs']} jobs, {t_['duration_ms']:.1f} ms): "
                             f"{t_['dram_bytes_write'] / 1e9:.1f} GB written + {t_['dram_bytes_read'] / 1e9:.1f} GB read; see {t_['source']}")
             break
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
