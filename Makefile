@@ -17,7 +17,7 @@ OBJS    := $(patsubst $(CSRC)/%.c,$(OBJ)/%.o,$(C_SRCS)) $(patsubst $(CSRC)/%.cu,
 
 BIN     := abpoa_b200/bin/abpoa
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean kprof
 all: $(LIB) $(BIN)
 
 $(OBJ)/%.o: $(CSRC)/%.c $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h)
@@ -36,6 +36,11 @@ $(LIB): $(OBJS)
 $(BIN): abpoa_b200/cli/abpoa_cli.c $(LIB) $(wildcard include/*.h)
 	@mkdir -p abpoa_b200/bin
 	$(CC) -O2 -g -Wall -Iinclude -o $@ $< -L$(LIBDIR) -labpoa_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+# profiling build of the same library (per-phase cycle counters inside the DP kernels): abpoa_b200/lib/libabpoa_b200_kprof.so,
+# selected at run time with ABPOA_B200_LIB=<path>
+kprof:
+	$(MAKE) OBJ=build/obj_kprof LIB=$(LIBDIR)/libabpoa_b200_kprof.so KPROF=-DPOA_KPROF $(LIBDIR)/libabpoa_b200_kprof.so
 
 oracle:
 	$(MAKE) -C oracle all

@@ -426,7 +426,9 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         if (free_run) {
             size_t o = 0;
             for (int t = 0; t < nw; ++t) {
-                const size_t share = (size_t)((double)pool_bytes * plans[pos + t].pool_units_est / est_tot) & ~(size_t)255;
+                size_t share = (size_t)((double)pool_bytes * plans[pos + t].pool_units_est / est_tot) & ~(size_t)255;
+                { static const double slab_x = [] { const char *e = getenv("ABPOA_GPU_CHAIN_SLAB_X"); return e && *e ? atof(e) : 0.0; }();      /* experiment: compact slabs */
+                  if (slab_x > 0) share = std::min(share, (size_t)(plans[pos + t].pool_units_est * 16.0 * slab_x) & ~(size_t)255); }
                 hs[t].pool_base = d_pool + o; hs[t].pool_units = share / 16; hs[t].pool_cursor = NULL;
                 o += share;
             }
@@ -484,10 +486,12 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             CK(cudaEventRecord(ev_sync, s0));
             static const int fuse_cap = [] { const char *e = getenv("ABPOA_GPU_CHAIN_FUSE_WORKERS"); return e && *e ? std::max(1, atoi(e)) : (1 << 30); }();
             const int n_fuse = std::max(1, std::min(std::min(nw, sm_count * fuse_per_sm), fuse_cap));
+            static const bool dp_first = [] { const char *e = getenv("ABPOA_GPU_CHAIN_DP_FIRST"); return e && *e == '1'; }();     /* experiment */
+            CK(cudaStreamWaitEvent(st_dp, ev_sync, 0));
+            if (dp_first) CK(poa_launch_chain_dp_worker(abpt->gap_mode, gaps, d_slots, d_sync, nw, d_prm, ring_rows, ring_cells, st_dp));
             poa_chain_fuse_worker_kernel<<<n_fuse, POA_CHAIN_T, 0, s0>>>(d_slots, d_sync, d_cp);
             CK(cudaGetLastError());
-            CK(cudaStreamWaitEvent(st_dp, ev_sync, 0));
-            CK(poa_launch_chain_dp_worker(abpt->gap_mode, gaps, d_slots, d_sync, nw, d_prm, ring_rows, ring_cells, st_dp));
+            if (!dp_first) CK(poa_launch_chain_dp_worker(abpt->gap_mode, gaps, d_slots, d_sync, nw, d_prm, ring_rows, ring_cells, st_dp));
             cudaEvent_t ev_dp; CK(cudaEventCreateWithFlags(&ev_dp, cudaEventDisableTiming));
             CK(cudaEventRecord(ev_dp, st_dp));
             CK(cudaStreamWaitEvent(s0, ev_dp, 0));
@@ -660,6 +664,14 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             stats->dp_ms += dp_ms; stats->fuse_ms += fuse_ms; stats->dp_launches += n_marks; stats->fuse_launches += n_marks;
             stats->wait_ms += wait_ms; stats->free_running = free_run ? 1 : 0;
         }
+#ifdef POA_KPROF
+        if (verbose) {
+            double pf[6] = {0, 0, 0, 0, 0, 0}; double na = 0;
+            for (int t = 0; t < nw; ++t) { for (int z = 0; z < 6; ++z) pf[z] += (double)fin[t].prof[z]; na += fin[t].fused > 0 ? fin[t].fused - 1 : 0; }
+            if (na > 0) fprintf(stderr, "[chain, k-cycles/alignment] -DPOA_KPROF phases: setup %.0f pred %.0f compute %.0f store %.0f rowmax %.0f tail+prefetch %.0f\n",
+                                pf[0] / na / 1e3, pf[1] / na / 1e3, pf[2] / na / 1e3, pf[3] / na / 1e3, pf[4] / na / 1e3, pf[5] / na / 1e3);
+        }
+#endif
         if (verbose)
             free_run ? fprintf(stderr, "[chain] free-running: per group on average %.1f ms inside alignments + %.1f ms inside fuse (waited %.1f ms for fuse workers incl. the fuse itself), %lld alignments\n",
                                dp_ms / nw, fuse_ms / nw, wait_ms / nw, (long long)n_marks)

@@ -94,6 +94,7 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
     int32_t turn;                       /* 0: the alignment warp's move, 1: a fuse worker's move */
     int32_t rsv0;
     unsigned long long wait_ns, fuse_ns;        /* time the alignment warp waited for its fuse tasks / time inside chain_fuse */
+    int64_t prof[6];                    /* -DPOA_KPROF builds: per-phase cycles of the forward row loop, summed over the alignments */
     /* per-read records (record mode) */
     int32_t *rec_score, *rec_nops; uint64_t *rec_hash;
 } PoaChainSlot;
@@ -402,6 +403,9 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp, int round) {
      *      (forward order, DP rows translated to node ids; poa_job_to_res in poa_cuda.cu) ---- */
     if (POA_TID0) {
         s->cells += res->cells; s->fwd_clk += res->fwd_clk; s->bt_clk += res->bt_clk;
+#ifdef POA_KPROF
+        for (int z = 0; z < 6; ++z) s->prof[z] += res->prof[z];
+#endif
         if (cp->record) {
             s->rec_score[r] = res->best_score; s->rec_nops[r] = n_ops;
             uint64_t hsh = 1469598103934665603ull;

@@ -267,6 +267,12 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 start_i = i - (r - 1); start_j = j - (r - 1);
                 i = __shfl_sync(FULL, rp0, r - 1); j -= r; cur = OP_ALL; moved = true;
                 if (i - 32 - lane > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 32 - lane)));
+                /* the run ends in a general step at one of the next rows: have their row records on the way */
+                if (i - lane > 0) {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rowinfo + (i - lane)));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rowoff + (i - lane)));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(jv.rowmeta + (i - lane)));
+                }
             }
             if (moved) {                               /* back to the general step: rebuild its view of (i, j) */
                 if (!(i > 0 && j > 0)) break;
@@ -291,6 +297,16 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 if (has_ps) pc_ps = ldb(jv.predscore + me.pb + lane);
             }
             cand_loaded = true;
+        }
+        /* every cell the tests below may look at is requested now, together: the planes were written long ago (one HBM
+         * round trip each) and the tests are sequential (match, then E planes of the candidates, then F planes of this row) */
+        {
+            if (pc.has(j - 1)) asm volatile("prefetch.global.L1 [%0];" :: "l"(pc.ptr + (j - 1)));
+            if (GAP != LG && pc.has(j)) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pc.ptr + PL::E1 * pc.pstride + j));
+                if (GAP == CG) asm volatile("prefetch.global.L1 [%0];" :: "l"(pc.ptr + PL::E2 * pc.pstride + j));
+            }
+            if (lane < PL::N && me.has(j)) asm volatile("prefetch.global.L1 [%0];" :: "l"(me.ptr + lane * me.pstride + j));
         }
         const bool c_in_m = pc.has(j - 1);
         const int c_hm1 = c_in_m ? (int)pc.ptr[j - 1] : NEG;
@@ -1560,7 +1576,7 @@ __device__ __forceinline__ unsigned long long chain_now_ns() { unsigned long lon
 
 template <int GAP, bool TMA>
 __global__ void POA_P16_BOUNDS poa_chain_dp_worker_kernel(PoaChainSlot *slots, PoaChainSync *sync, const PoaParamsDev *__restrict__ prm, int n_groups,
-                                                          int ring_rows, int ring_cells, const __grid_constant__ P16Consts kc) {
+                                                          int ring_rows, int ring_cells, int dbg, const __grid_constant__ P16Consts kc) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const int lane = threadIdx.x;
     const int g = blockIdx.x;
@@ -1589,13 +1605,13 @@ __global__ void POA_P16_BOUNDS poa_chain_dp_worker_kernel(PoaChainSlot *slots, P
         }
         state = __shfl_sync(0xffffffffu, state, 0);
         if (state) break;
-        __threadfence();                                       /* acquire side: also drops this SM's L1 lines of the slot / job blob */
+        if (!(dbg & 1)) __threadfence();                       /* acquire side: also drops this SM's L1 lines of the slot / job blob */
         const PoaJobDesc jd = sl->jd;
         const int n_rows = reinterpret_cast<const PoaJobHeader *>(jd.blob)->n_rows;
         if (sl->failed || sl->fused >= sl->n_reads || n_rows < 3) break;
         p16_run_job<GAP, GLOBAL, true, TMA>(jd, prm, kc, sm, ring_rows, ring_cells, lane);
         __syncwarp();
-        __threadfence();                                       /* release side: CIGAR + result are out before the task is */
+        if (!(dbg & 1)) __threadfence();                       /* release side: CIGAR + result are out before the task is */
         if (lane == 0) {
             chain_st_relaxed(&sl->turn, 1);
             const unsigned slot = atomicAdd(&sync->q_tail, 1u);
@@ -1617,10 +1633,14 @@ static cudaError_t launch_chain_worker_one(PoaChainSlot *slots, PoaChainSync *sy
                                            const P16Consts &kc, cudaStream_t st) {
     /* at least 23 KB: at most 9 of these CTAs fit one SM, which leaves registers (9 x 160 x 32 of 64 K) and shared memory for a
      * 256-thread fuse worker next to them even if the alignment warps were dispatched first -- they wait for fuse workers */
-    const size_t smem = std::max<size_t>(ring_smem_bytes(GAP, 16, ring_rows, ring_cells, TMA) + 18 * sizeof(uint4), (size_t)23 * 1024);
+    /* experiment hooks (timing only): ABPOA_GPU_CHAIN_DBG bit 0 = no fences (UNSAFE), bit 1 = no shared-memory padding; ABPOA_GPU_CHAIN_CARVEOUT */
+    static const int dbg = [] { const char *e = getenv("ABPOA_GPU_CHAIN_DBG"); return e && *e ? atoi(e) : 0; }();
+    const size_t smem0 = ring_smem_bytes(GAP, 16, ring_rows, ring_cells, TMA) + 18 * sizeof(uint4);
+    const size_t smem = (dbg & 2) ? smem0 : std::max<size_t>(smem0, (size_t)23 * 1024);
     cudaError_t e = cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    poa_chain_dp_worker_kernel<GAP, TMA><<<n_groups, 32, smem, st>>>(slots, sync, prm, n_groups, ring_rows, ring_cells, kc);
+    { const char *cv = getenv("ABPOA_GPU_CHAIN_CARVEOUT"); if (cv && *cv) cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)); }
+    poa_chain_dp_worker_kernel<GAP, TMA><<<n_groups, 32, smem, st>>>(slots, sync, prm, n_groups, ring_rows, ring_cells, dbg, kc);
     return cudaGetLastError();
 }
 extern "C" int poa_tma_enabled(void);
