@@ -63,24 +63,28 @@ __device__ __forceinline__ unsigned long long sync_now_ns() { unsigned long long
 __global__ void __launch_bounds__(POA_CHAIN_T) poa_chain_fuse_worker_kernel(PoaChainSlot *slots, PoaChainSync *sync, const PoaChainParams *cp) {
     __shared__ int task_s;
     for (;;) {
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(&sync->q_head, 1u);
+        if (threadIdx.x < 32) {                                /* warp 0 waits, warp-uniformly (see poa_chain_dp_worker_kernel) */
+            unsigned ticket = 0;
+            if (threadIdx.x == 0) ticket = atomicAdd(&sync->q_head, 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
             int g = -2; unsigned ns = 250, polls = 0;
             const unsigned long long t0 = sync_now_ns(), limit = sync->watchdog_ns;
             const int32_t *tasks = sync->tasks;
             for (;;) {
                 /* the ticket's own task word is what is polled; the shared words (total, abort) and the clock only every 32nd time */
                 if ((polls++ & 31u) == 0) {
-                    if ((long long)ticket >= (long long)sync_ld(&sync->total) || sync_ld(&sync->abort)) { g = -2; break; }
+                    const int tot = __shfl_sync(0xffffffffu, sync_ld(&sync->total), 0), ab = __shfl_sync(0xffffffffu, sync_ld(&sync->abort), 0);
+                    if ((long long)ticket >= (long long)tot || ab) { g = -2; break; }
                     /* nobody appended a task for this long: the alignment kernel is not running next to this one (a tool that
                      * serialises kernels, a device shared with a long-running grid): give up, the launch engine finishes the groups */
-                    if (polls > 1 && sync_now_ns() - t0 > limit) { sync_st(&sync->abort, 1); g = -2; break; }
+                    const unsigned late = __shfl_sync(0xffffffffu, (unsigned)(polls > 1 && sync_now_ns() - t0 > limit), 0);
+                    if (late) { if (threadIdx.x == 0) sync_st(&sync->abort, 1); g = -2; break; }
                 }
-                g = sync_ld(&tasks[ticket]);
+                g = __shfl_sync(0xffffffffu, sync_ld(&tasks[ticket]), 0);
                 if (g >= 0) break;
                 __nanosleep(ns); if (ns < 4000) ns <<= 1;
             }
-            task_s = g;
+            if (threadIdx.x == 0) task_s = g;
         }
         __syncthreads();
         const int g = task_s;

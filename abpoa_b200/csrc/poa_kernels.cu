@@ -1587,23 +1587,27 @@ __global__ void POA_P16_BOUNDS poa_chain_dp_worker_kernel(PoaChainSlot *slots, P
     int pushed = 0;
     unsigned long long waited = 0;
     for (;;) {
-        /* ---- wait for the slot ---- */
+        /* ---- wait for the slot.  The loop is warp-uniform on purpose (every lane polls, lane 0's view decides): a spin
+         *      loop that only lane 0 runs left the warp in a state where every later warp-collective (SHFL / VOTE / REDUX) took
+         *      its slow path -- measured 4x longer alignments.  Poll the slot's own word, gently (a fuse takes a millisecond
+         *      or more; a thousand warps wait like this at once); the shared abort flag and the clock every 64th poll. ---- */
         int state = 0;                                         /* 0 go, 2 stop */
-        if (lane == 0) {
-            /* poll the slot's own word, gently (a fuse takes a millisecond or more; a thousand warps wait like this at
-             * once); the shared abort flag and the clock are looked at every 64th poll */
+        {
             const unsigned long long t0 = chain_now_ns();
             unsigned ns = 500, polls = 0;
-            while (chain_ld_relaxed(&sl->turn) != 0) {
+            for (;;) {
+                const int v = __shfl_sync(0xffffffffu, chain_ld_relaxed(&sl->turn), 0);
+                if (v == 0) break;
                 __nanosleep(ns); if (ns < 8000) ns <<= 1;
                 if ((++polls & 63u) == 0) {
-                    if (chain_ld_relaxed(&sync->abort)) { state = 2; break; }
-                    if (chain_now_ns() - t0 > limit) { chain_st_relaxed(&sync->abort, 1); state = 2; break; }
+                    const int a = __shfl_sync(0xffffffffu, chain_ld_relaxed(&sync->abort), 0);
+                    const unsigned late = __shfl_sync(0xffffffffu, (unsigned)(chain_now_ns() - t0 > limit), 0);
+                    if (a) { state = 2; break; }
+                    if (late) { if (lane == 0) chain_st_relaxed(&sync->abort, 1); state = 2; break; }
                 }
             }
             waited += chain_now_ns() - t0;
         }
-        state = __shfl_sync(0xffffffffu, state, 0);
         if (state) break;
         if (!(dbg & 1)) __threadfence();                       /* acquire side: also drops this SM's L1 lines of the slot / job blob */
         const PoaJobDesc jd = sl->jd;
