@@ -490,6 +490,12 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
             CK(cudaEventRecord(ev_sync, s0));
             static const int fuse_cap = [] { const char *e = getenv("ABPOA_GPU_CHAIN_FUSE_WORKERS"); return e && *e ? std::max(1, atoi(e)) : (1 << 30); }();
             const int n_fuse = std::max(1, std::min(std::min(nw, sm_count * fuse_per_sm), fuse_cap));
+            /* Both persistent kernels must ask for the SAME shared-memory configuration of the SM: a resident CTA pins the
+             * SM's L1/shared split, and the other kernel's CTAs are only dispatched to SMs whose split matches its launch --
+             * with one fuse CTA on every SM (default split of a 5 KB kernel: 64 KB) the alignment grid (split: maximum) never
+             * started, and neither kernel ever ends by itself (measured: the fuse workers' watchdog fired, then the alignment
+             * grid ran). */
+            CK(cudaFuncSetAttribute(poa_chain_fuse_worker_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             static const bool dp_first = [] { const char *e = getenv("ABPOA_GPU_CHAIN_DP_FIRST"); return e && *e == '1'; }();     /* experiment */
             CK(cudaStreamWaitEvent(st_dp, ev_sync, 0));
             if (dp_first) CK(poa_launch_chain_dp_worker(abpt->gap_mode, gaps, d_slots, d_sync, nw, d_prm, ring_rows, ring_cells, st_dp));

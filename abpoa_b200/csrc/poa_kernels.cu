@@ -1643,7 +1643,10 @@ static cudaError_t launch_chain_worker_one(PoaChainSlot *slots, PoaChainSync *sy
     const size_t smem = (dbg & 2) ? smem0 : std::max<size_t>(smem0, (size_t)23 * 1024);
     cudaError_t e = cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    { const char *cv = getenv("ABPOA_GPU_CHAIN_CARVEOUT"); if (cv && *cv) cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)); }
+    /* the same L1/shared split as the fuse workers ask for (poa_chain.cu): CTAs of both kernels share SMs for the whole run */
+    { const char *cv = getenv("ABPOA_GPU_CHAIN_CARVEOUT");
+      e = cudaFuncSetAttribute(poa_chain_dp_worker_kernel<GAP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cv && *cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e; }
     poa_chain_dp_worker_kernel<GAP, TMA><<<n_groups, 32, smem, st>>>(slots, sync, prm, n_groups, ring_rows, ring_cells, dbg, kc);
     return cudaGetLastError();
 }
