@@ -678,6 +678,9 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         if (verbose) {
             double pf[6] = {0, 0, 0, 0, 0, 0}; double na = 0;
             for (int t = 0; t < nw; ++t) { for (int z = 0; z < 6; ++z) pf[z] += (double)fin[t].prof[z]; na += fin[t].fused > 0 ? fin[t].fused - 1 : 0; }
+            double bd[4] = {0, 0, 0, 0};
+            for (int t = 0; t < nw; ++t) for (int z = 0; z < 4; ++z) bd[z] += (double)fin[t].btdiag[z];
+            if (na > 0) fprintf(stderr, "[chain, backtrace per alignment] %.0f steps in %.0f speculative rounds, %.0f general steps costing %.0f k-cycles\n", bd[0] / na, bd[1] / na, bd[2] / na, bd[3] / na);
             if (na > 0) fprintf(stderr, "[chain, k-cycles/alignment] -DPOA_KPROF phases: setup %.0f pred %.0f compute %.0f store %.0f rowmax %.0f tail+prefetch %.0f\n",
                                 pf[0] / na / 1e3, pf[1] / na / 1e3, pf[2] / na / 1e3, pf[3] / na / 1e3, pf[4] / na / 1e3, pf[5] / na / 1e3);
         }

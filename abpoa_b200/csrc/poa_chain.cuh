@@ -95,6 +95,7 @@ typedef struct PoaChainSlot {           /* one per read group; every pointer aim
     int32_t rsv0;
     unsigned long long wait_ns, fuse_ns;        /* time the alignment warp waited for its fuse tasks / time inside chain_fuse */
     int64_t prof[6];                    /* -DPOA_KPROF builds: per-phase cycles of the forward row loop, summed over the alignments */
+    int64_t btdiag[4];                  /* -DPOA_KPROF builds: PoaResultDev.btdiag summed */
     /* per-read records (record mode) */
     int32_t *rec_score, *rec_nops; uint64_t *rec_hash;
 } PoaChainSlot;
@@ -405,6 +406,7 @@ POA_DEV void chain_fuse(PoaChainSlot *s, const PoaChainParams *cp, int round) {
         s->cells += res->cells; s->fwd_clk += res->fwd_clk; s->bt_clk += res->bt_clk;
 #ifdef POA_KPROF
         for (int z = 0; z < 6; ++z) s->prof[z] += res->prof[z];
+        for (int z = 0; z < 4; ++z) s->btdiag[z] += res->btdiag[z];
 #endif
         if (cp->record) {
             s->rec_score[r] = res->best_score; s->rec_nops[r] = n_ops;

@@ -56,6 +56,8 @@ typedef struct PoaResultDev {
     int64_t prof[6];                    /* optional per-phase SM cycles (ABPOA kernel built with -DPOA_KPROF) */
     int32_t diag[4];                    /* -DPOA_KPROF: rows on the straight-line path / rows sent to the generic path because of
                                            > 2 predecessors / a predecessor outside the ring / a predecessor band wider than its ring slot */
+    int32_t btdiag[4];                  /* -DPOA_KPROF: backtrace steps taken by the speculative shortcut / its rounds / general steps /
+                                           k-cycles spent in general steps */
 } PoaResultDev;
 
 /* Backtrace shortcut record of one DP row, written by the packed forward kernel (64 B, one cache-line half):
@@ -64,12 +66,15 @@ typedef struct PoaResultDev {
  * first whenever a match is allowed (src/abpoa_align_simd.c:211-227), true on ~90 % of its steps.  With the first
  * predecessor and the residue in the same record, such a step needs one small load instead of the generic machinery. */
 #define POA_BTREC_BYTES 64
-#define POA_BTREC_BITS  (52 * 8)
+#define POA_BTREC_GROUPS 48
+#define POA_BTREC_BITS  (POA_BTREC_GROUPS * 8)
 typedef struct __attribute__((aligned(16))) PoaBtRec {
     int32_t c0;                         /* column of bit 0 (first cell of the row's first stored group)   */
     int32_t p0;                         /* first predecessor row, -1: none                                 */
-    uint8_t base, valid, pad[2];        /* residue of the node; valid = 0: the row has no bitmap (too wide) */
-    uint8_t bits[52];
+    uint8_t base, valid;                /* residue of the node; valid = 0: the row has no bitmap (too wide) */
+    uint16_t ngrp;                      /* 8-cell groups the row stores per plane                           */
+    uint32_t off;                       /* start of the row's planes in the job's slab (8-cell units), as PoaRowOff.off */
+    uint8_t bits[POA_BTREC_GROUPS];
 } PoaBtRec;
 
 /* device pointers of one job */

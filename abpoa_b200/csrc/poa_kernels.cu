@@ -185,6 +185,9 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     CigarSink cg; cg.out = jd.cigar; cg.cap = jd.cigar_cap; cg.n = 0; cg.pending = 0; cg.lane = lane; cg.ovf = 0;
 
     int i = best_i, j = best_j, start_i = best_i, start_j = best_j, cur = OP_ALL;
+#ifdef POA_KPROF
+    int bd_steps = 0, bd_rounds = 0, bd_general = 0; long long bd_clk = 0;
+#endif
     int n_aln = 0, n_match = 0, err = 0;
     int gap_at_end = prm->put_gap_at_end; const int gap_on_right = prm->put_gap_on_right;
     if (best_j < qlen) cg.ins(qlen - best_j, qlen - 1);
@@ -248,16 +251,26 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 bool step_ok = false, cont = false; int rp0 = 0, same = 0;
                 if (ri > 0 && cj > 0) {
                     const uint8_t *rec = reinterpret_cast<const uint8_t *>(btrec + ri);
-                    const uint4 hd = *reinterpret_cast<const uint4 *>(rec);        /* c0, p0, base | valid << 8, bits[0..3] */
+                    const uint4 hd = *reinterpret_cast<const uint4 *>(rec);        /* c0, p0, base | valid << 8 | ngrp << 16, off */
                     const int kbit = cj - (int)hd.x;
-                    if (((hd.z >> 8) & 0xffu) && (unsigned)kbit < (unsigned)POA_BTREC_BITS)
-                        step_ok = (rec[12 + (kbit >> 3)] >> (kbit & 7)) & 1u;
+                    if (((hd.z >> 8) & 0xffu) && (unsigned)kbit < (unsigned)POA_BTREC_BITS) {
+                        step_ok = (rec[16 + (kbit >> 3)] >> (kbit & 7)) & 1u;
+                        /* wherever the run ends, the general step there looks at the cells around (row, column) of every
+                         * plane -- of the row itself and, one column over, as a candidate of the row above: request them now */
+                        const ST *cell = planes + (size_t)hd.w * POA_GROUP + kbit;
+                        const size_t gplane = (size_t)(hd.z >> 16) * POA_GROUP;
+#pragma unroll
+                        for (int pl = 0; pl < PL::N; ++pl) asm volatile("prefetch.global.L1 [%0];" :: "l"(cell + pl * gplane));
+                    }
                     rp0 = (int)hd.y; cont = rp0 == ri - 1;
                     same = (int)(hd.z & 0xffu) == (int)jv.qs[cj];
                 }
                 const unsigned b_step = __ballot_sync(FULL, step_ok), b_cont = __ballot_sync(FULL, cont);
                 const unsigned run = b_step & ((b_cont << 1) | 1u);               /* step L happens iff steps 0..L-1 did and led to row i-L */
                 const int r = run == FULL ? 32 : __ffs(~run) - 1;
+#ifdef POA_KPROF
+                ++bd_rounds; bd_steps += r;
+#endif
                 if (r == 0) break;
                 cg.flush();
                 if (lane < r) { if (cg.n + lane < cg.cap) cg.out[cg.n + lane] = ((uint64_t)ri << 34) | ((uint64_t)(cj - 1) << 4); }
@@ -268,11 +281,13 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 i = __shfl_sync(FULL, rp0, r - 1); j -= r; cur = OP_ALL; moved = true;
                 if (i - 32 - lane > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 32 - lane)));
                 /* the run ends in a general step at one of the next rows: have their row records on the way */
-                if (i - lane > 0) {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rowinfo + (i - lane)));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rowoff + (i - lane)));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(jv.rowmeta + (i - lane)));
-                }
+#pragma unroll
+                for (int wnd = 0; wnd < 64; wnd += 32)
+                    if (i - wnd - lane > 0) {
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(rowinfo + (i - wnd - lane)));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(rowoff + (i - wnd - lane)));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(jv.rowmeta + (i - wnd - lane)));
+                    }
             }
             if (moved) {                               /* back to the general step: rebuild its view of (i, j) */
                 if (!(i > 0 && j > 0)) break;
@@ -284,6 +299,9 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
             }
         }
         if (MODE == LOCAL && h_ij == 0) break;
+#ifdef POA_KPROF
+        ++bd_general; const long long bd_t0 = clock64();
+#endif
         start_i = i; start_j = j;
         const int id = i;                       /* the host maps DP rows back to node ids */
         const int rb = me.base, np = me.np;
@@ -424,6 +442,9 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         }
 
         if (!hit && (GAP == LG || (cur & OP_M))) { try_match(); if (hit) gap_at_end = 0; }
+#ifdef POA_KPROF
+        bd_clk += clock64() - bd_t0;
+#endif
         if (!hit) { err = 1; break; }
     }
     if (!err && j > 0) cg.ins(j, j - 1);
@@ -432,6 +453,9 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
         res.n_ops = cg.n; res.start_i = start_i; res.start_j = start_j;
         res.n_aln_bases = n_aln; res.n_matched_bases = n_match;
         if (err) res.status = POA_ST_BT_ERROR; else if (cg.ovf) res.status = POA_ST_CIGAR_OVF;
+#ifdef POA_KPROF
+        res.btdiag[0] = bd_steps; res.btdiag[1] = bd_rounds; res.btdiag[2] = bd_general; res.btdiag[3] = (int)(bd_clk >> 10);
+#endif
     }
 }
 
@@ -1381,11 +1405,10 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
                 const unsigned byte = (t | (t >> 16)) & 0xffu;
                 uint8_t *rec = reinterpret_cast<uint8_t *>(jd.btrec + i);
                 const int rel = g - g0;
-                if (active && rel < 52) rec[12 + rel] = (uint8_t)byte;
-                if (lane == 0 && gp == g0) {
-                    *reinterpret_cast<int2 *>(rec) = make_int2(g0 * 8, mypred);
-                    *reinterpret_cast<unsigned *>(rec + 8) = (unsigned)rbase | (ngrp <= 52 ? 0x100u : 0u);
-                }
+                if (active && rel < POA_BTREC_GROUPS) rec[16 + rel] = (uint8_t)byte;
+                if (lane == 0 && gp == g0)
+                    *reinterpret_cast<uint4 *>(rec) = make_uint4((unsigned)(g0 * 8), (unsigned)mypred,
+                                                                 (unsigned)rbase | (ngrp <= POA_BTREC_GROUPS ? 0x100u : 0u) | ((unsigned)min(ngrp, 0xffff) << 16), (unsigned)my_off);
             }
             KP(2)
             if (TMA && tma_row) {
