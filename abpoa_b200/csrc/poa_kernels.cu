@@ -239,51 +239,81 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
     while (i > 0 && j > 0) {
         /* ---- shortcut: while a match is the first thing the reference would test and the row's bitmap says the first
          *      predecessor's diagonal explains the cell, the step is MATCH -> (p0, j-1) (src/abpoa_align_simd.c:211-227) and
-         *      everything it needs sits in one 64-byte record per row (PoaBtRec).  The records were written long ago (HBM
-         *      latency), so the walk SPECULATES: lane L assumes the L steps before it were such matches along rows i, i-1, ...
-         *      (the first predecessor is the previous row on the path most reads take) and tests row i-L, column j-L.  One
-         *      round of 32 independent record loads then advances the walk by the length of the confirmed prefix, its
-         *      graph-CIGAR words go out as one coalesced store, and the records of the next 32 rows are prefetched. ---- */
+         *      everything it needs sits in one 64-byte record per row (PoaBtRec).  Followed one record at a time this is a
+         *      pointer chase through memory written long ago.  Instead every round loads the records of the 32 rows below the
+         *      walk at once (lane L: row i-L) and follows the first-predecessor chain INSIDE the warp: the rows on the chain
+         *      are found by pointer doubling over the lanes (5 x REDUX.OR + SHFL), a chain row's column is j minus its rank on
+         *      the chain, and since that rank is at most L each lane only needs the 32 bitmap bits from column j-L on.  The
+         *      walk advances to the first chain row whose bit is clear (or past the window), the confirmed steps' graph-CIGAR
+         *      words go out in one store, and the next windows' records are prefetched. ---- */
         if (btrec != nullptr && MODE != LOCAL && !gap_on_right) {
             bool moved = false;
             while (i > 0 && j > 0 && (GAP == LG || (cur & OP_M)) && !gap_at_end) {
-                const int ri = i - lane, cj = j - lane;
-                bool step_ok = false, cont = false; int rp0 = 0, same = 0;
-                if (ri > 0 && cj > 0) {
+                const int ri = i - lane;
+                unsigned W = 0;                             /* bit d: cell (ri, j - lane + d) is explained by the first predecessor's diagonal */
+                int rp0 = -1, rbase_l = 0, jmp = -1; uint32_t r_off = 0, r_ngrp = 0; int r_c0 = 0; bool has_map = false;
+                if (ri > 0) {
                     const uint8_t *rec = reinterpret_cast<const uint8_t *>(btrec + ri);
                     const uint4 hd = *reinterpret_cast<const uint4 *>(rec);        /* c0, p0, base | valid << 8 | ngrp << 16, off */
-                    const int kbit = cj - (int)hd.x;
-                    if (((hd.z >> 8) & 0xffu) && (unsigned)kbit < (unsigned)POA_BTREC_BITS) {
-                        step_ok = (rec[16 + (kbit >> 3)] >> (kbit & 7)) & 1u;
-                        /* wherever the run ends, the general step there looks at the cells around (row, column) of every
-                         * plane -- of the row itself and, one column over, as a candidate of the row above: request them now */
-                        const ST *cell = planes + (size_t)hd.w * POA_GROUP + kbit;
-                        const size_t gplane = (size_t)(hd.z >> 16) * POA_GROUP;
-#pragma unroll
-                        for (int pl = 0; pl < PL::N; ++pl) asm volatile("prefetch.global.L1 [%0];" :: "l"(cell + pl * gplane));
+                    rp0 = (int)hd.y; rbase_l = (int)(hd.z & 0xffu); r_c0 = (int)hd.x; r_off = hd.w; r_ngrp = hd.z >> 16;
+                    has_map = ((hd.z >> 8) & 0xffu) != 0;
+                    const int kb0 = (j - lane) - r_c0;
+                    if (has_map && kb0 > -32 && kb0 < POA_BTREC_BITS) {
+                        const int wi = kb0 >> 5;            /* arithmetic shift: -1 for kb0 in [-31, -1] */
+                        const uint32_t *wds = reinterpret_cast<const uint32_t *>(rec + 16);
+                        const unsigned lo = (wi >= 0) ? wds[wi] : 0u, hi = (wi + 1 < POA_BTREC_GROUPS / 4) ? wds[wi + 1] : 0u;
+                        W = __funnelshift_r(lo, hi, (unsigned)kb0 & 31u);
                     }
-                    rp0 = (int)hd.y; cont = rp0 == ri - 1;
-                    same = (int)(hd.z & 0xffu) == (int)jv.qs[cj];
+                    if (rp0 >= 0 && i - rp0 < 32) jmp = i - rp0;        /* the lane that holds the first predecessor's record */
                 }
-                const unsigned b_step = __ballot_sync(FULL, step_ok), b_cont = __ballot_sync(FULL, cont);
-                const unsigned run = b_step & ((b_cont << 1) | 1u);               /* step L happens iff steps 0..L-1 did and led to row i-L */
-                const int r = run == FULL ? 32 : __ffs(~run) - 1;
+                /* rows on the chain i -> p0(i) -> p0(p0(i)) ... inside the window (chain order = lane order) */
+                unsigned M = 1u;
+                {
+                    int jp = jmp;
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) {
+                        const unsigned add = __reduce_or_sync(FULL, (((M >> lane) & 1u) && jp >= 0) ? (1u << jp) : 0u);
+                        M |= add;
+                        const int nx = __shfl_sync(FULL, jp, jp & 31);
+                        jp = jp >= 0 ? nx : -1;
+                    }
+                }
+                const bool on_chain = (M >> lane) & 1u;
+                const int rank = __popc(M & ((1u << lane) - 1u));       /* steps before this row */
+                const int col = j - rank;
+                const bool ok = on_chain && ri > 0 && col > 0 && ((W >> (lane - rank)) & 1u);
+                const unsigned fail = __ballot_sync(FULL, on_chain && !ok);
+                const unsigned E = fail ? (M & ((fail & (0u - fail)) - 1u)) : M;     /* executed steps: chain rows before the first failure */
+                const int r = __popc(E);
 #ifdef POA_KPROF
                 ++bd_rounds; bd_steps += r;
 #endif
+                /* the general step at the row where the run stops (and its candidates, the next chain rows) reads the cells around
+                 * (row, column) of every plane: request them now */
+                if (on_chain && !((E >> lane) & 1u) && ri > 0 && has_map) {
+                    const int kb = col - r_c0;
+                    if (kb >= 0 && kb < (int)r_ngrp * POA_GROUP) {
+                        const ST *cell = planes + (size_t)r_off * POA_GROUP + kb;
+                        const size_t gplane = (size_t)r_ngrp * POA_GROUP;
+#pragma unroll
+                        for (int pl = 0; pl < PL::N; ++pl) asm volatile("prefetch.global.L1 [%0];" :: "l"(cell + pl * gplane));
+                    }
+                }
                 if (r == 0) break;
+                const bool exec = (E >> lane) & 1u;
                 cg.flush();
-                if (lane < r) { if (cg.n + lane < cg.cap) cg.out[cg.n + lane] = ((uint64_t)ri << 34) | ((uint64_t)(cj - 1) << 4); }
+                if (exec && cg.n + rank < cg.cap) cg.out[cg.n + rank] = ((uint64_t)ri << 34) | ((uint64_t)(col - 1) << 4);
                 if (cg.n + r > cg.cap) cg.ovf = 1;
                 cg.n += r;
-                n_aln += r; n_match += __popc(__ballot_sync(FULL, lane < r && same));
-                start_i = i - (r - 1); start_j = j - (r - 1);
-                i = __shfl_sync(FULL, rp0, r - 1); j -= r; cur = OP_ALL; moved = true;
-                if (i - 32 - lane > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 32 - lane)));
-                /* the run ends in a general step at one of the next rows: have their row records on the way */
+                n_aln += r; n_match += __popc(__ballot_sync(FULL, exec && rbase_l == (int)jv.qs[exec ? col : 0]));
+                const int last = 31 - __clz(E);                         /* lane of the last executed step */
+                start_i = i - last; start_j = j - (r - 1);
+                i = __shfl_sync(FULL, rp0, last); j -= r; cur = OP_ALL; moved = true;
+                /* records of the next windows, and the row records a general step needs there */
 #pragma unroll
                 for (int wnd = 0; wnd < 64; wnd += 32)
                     if (i - wnd - lane > 0) {
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(rowinfo + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(rowoff + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(jv.rowmeta + (i - wnd - lane)));
