@@ -309,11 +309,14 @@ __device__ void poa_backtrack(const JobView &jv, const PoaJobDesc &jd, const Poa
                 const int last = 31 - __clz(E);                         /* lane of the last executed step */
                 start_i = i - last; start_j = j - (r - 1);
                 i = __shfl_sync(FULL, rp0, last); j -= r; cur = OP_ALL; moved = true;
-                /* records of the next windows, and the row records a general step needs there */
+                /* records of the coming windows (a round advances 9 rows on average and lasts well under one HBM round trip:
+                 * the frontier runs three windows ahead, the far ones into L2 only), and the row records a general step needs where a run stops */
+                if (i - 32 - lane > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - 32 - lane)));
+                if (i - 64 - lane > 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(btrec + (i - 64 - lane)));       /* L1 is 28 KB for 7 warps */
+                if (i - 96 - lane > 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(btrec + (i - 96 - lane)));
 #pragma unroll
                 for (int wnd = 0; wnd < 64; wnd += 32)
                     if (i - wnd - lane > 0) {
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(btrec + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(rowinfo + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(rowoff + (i - wnd - lane)));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(jv.rowmeta + (i - wnd - lane)));
