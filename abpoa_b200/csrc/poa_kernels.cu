@@ -1116,15 +1116,18 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
         { const int k = max(min(pb + lane, npred_tot - 1), 0); raw_pred = ldb(jv.pred + k); if (has_ps) raw_ps = ldb(jv.predscore + k); }
     }
     int nx_y = n_rows > 3 ? ldb(&jv.rowmeta[2].y) : 0;          /* packed (remain, residue) of row i+1 */
+    constexpr int LP = 4;                                     /* LEAN: up to LP predecessors per row on the straight-line path (> 2: 14 % of the rows at 10 kbp x 50) */
+    int lp_c[LP];                                             /* the coming row's first LP predecessors, broadcast off the row-to-row chain */
+#pragma unroll
+    for (int k = 0; k < LP; ++k) lp_c[k] = LEAN ? __shfl_sync(FULL, lane < pe - pb ? raw_pred : -1, k) : -1;
     KP_DECL
     for (int i = 1; i < n_rows - 1 && !stop; ++i) {
         KP(5)
         const int np = pe - pb;
         const int mypred = lane < np ? raw_pred : -1, myps = lane < np ? raw_ps : 0;
-        constexpr int LP = 4;                                 /* LEAN: up to LP predecessors per row on the straight-line path (> 2: 14 % of the rows at 10 kbp x 50) */
-        int lp[LP];                                           /* the row's first LP predecessors, known to every lane */
+        int lp[LP];                                           /* the row's first LP predecessors, known to every lane (broadcast at the end of the previous iteration) */
 #pragma unroll
-        for (int k = 0; k < LP; ++k) lp[k] = LEAN ? __shfl_sync(FULL, mypred, k) : -1;
+        for (int k = 0; k < LP; ++k) lp[k] = lp_c[k];
         /* unconditional: rowmeta has n_rows + 1 entries and i + 2 <= n_rows; the predecessor index is clamped (a predicated
          * load would need a select on its result, which the compiler schedules right behind the load) */
         int2 m2;                                              /* two 32-bit loads: a 64-bit one ties up an aligned register pair that ptxas frees by
@@ -1486,17 +1489,15 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
             /* row maximum with first / last arg-max; masked cells hold NEGP and never win against a real cell */
             {
                 const int lmax = active ? lane_max8(H) : NEGP;
+                /* one bit per cell that equals the LANE's maximum: where the row maximum sits inside the lanes that hold it,
+                 * computed while the warp-wide reduction is in flight */
+                unsigned eq = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { eq |= (unsigned)(lo16(H[k]) == lmax) << (2 * k); eq |= (unsigned)(hi16(H[k]) == lmax) << (2 * k + 1); }
+                const int lfirst = g * 8 + __ffs(eq) - 1, llast = g * 8 + 31 - __clz(eq);
                 const int pm = __reduce_max_sync(FULL, lmax);
                 const unsigned bm = __ballot_sync(FULL, lmax == pm && pm > NEGP);
                 if (bm) {
-                    int lfirst = -1, llast = -1;
-                    if (lmax == pm) {
-                        /* one bit per cell that equals the row maximum */
-                        unsigned eq = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { eq |= (unsigned)(lo16(H[k]) == pm) << (2 * k); eq |= (unsigned)(hi16(H[k]) == pm) << (2 * k + 1); }
-                        lfirst = g * 8 + __ffs(eq) - 1; llast = g * 8 + 31 - __clz(eq);
-                    }
                     const int pl = __shfl_sync(FULL, lfirst, __ffs(bm) - 1);
                     const int pr = __shfl_sync(FULL, llast, 31 - __clz(bm));
                     if (pm > row_max) { row_max = pm; row_left = pl; row_right = pr; }
@@ -1539,6 +1540,8 @@ __device__ __forceinline__ void p16_run_job(const PoaJobDesc &jd, const PoaParam
          * row's volatile shared-memory stores, a whole row later. */
         asm volatile("" : "+r"(m2.x), "+r"(m2.y), "+r"(n_raw_pred), "+r"(n_raw_ps));
         pb = pe; pe = m2.x; rbase = n_rbase; rem = n_rem; nx_y = m2.y; raw_pred = n_raw_pred; raw_ps = n_raw_ps;
+#pragma unroll
+        for (int k = 0; k < LP; ++k) lp_c[k] = LEAN ? __shfl_sync(FULL, lane < pe - pb ? raw_pred : -1, k) : -1;
     }
     cursor = cur32;
     KP_OUT(res)
