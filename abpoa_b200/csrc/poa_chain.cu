@@ -237,7 +237,15 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         extern char **environ;
         for (char **v = environ; v && *v; ++v)
             if (!strncmp(*v, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*v, "NV_NSIGHT_INJECTION", 19) || !strncmp(*v, "NV_COMPUTE_PROFILER", 19) ||
-                !strncmp(*v, "NV_SANITIZER_INJECTION", 22)) return false;
+                !strncmp(*v, "NV_SANITIZER_INJECTION", 22) || !strncmp(*v, "NV_TPS_LAUNCH_", 14)) return false;
+        /* ... or whose injection library is already mapped into this process */
+        if (FILE *mp = fopen("/proc/self/maps", "r")) {
+            char line[512]; bool hit = false;
+            while (!hit && fgets(line, sizeof line, mp))
+                hit = strstr(line, "InjectionTarget") || strstr(line, "cuda-injection") || strstr(line, "libsanitizer-collection") || strstr(line, "TreeLauncherTarget");
+            fclose(mp);
+            if (hit) return false;
+        }
         return true;
     }();
     const double pool_margin = 1.15;

@@ -438,7 +438,8 @@ def main():
                              if used_chain else "replay of all captured alignment jobs from HBM, CUDA events"),
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
                 "reads_per_s": tot_reads / elapsed, "per_gpu": e2e_gcups / world, "host_threads_per_gpu": workers,
-                "engine": "device-resident chain (align + fuse kernels per round, host only for upload / final consensus)" if used_chain
+                "engine": (("device-resident chain, free-running (one persistent alignment kernel + one persistent fuse kernel per wave" if st["chain_free_running"]
+                            else "device-resident chain, round schedule (align + fuse kernels per round") + "; host only for upload / final consensus)") if used_chain
                           else "launch engine: pipelined launches, one per half-chunk round, host graph fusion"},
         "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "chain": chain, "distributed_check": dist_check,
