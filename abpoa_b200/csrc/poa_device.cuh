@@ -4,6 +4,7 @@
 #define POA_DEVICE_CUH
 
 #include <stdint.h>
+#include <stddef.h>
 
 #define POA_GROUP 8                 /* DP cells handled by one lane per pass (one 16 B int16 vector) */
 #define POA_MAX_M 32                /* largest alphabet held in shared memory                         */
@@ -76,6 +77,12 @@ typedef struct __attribute__((aligned(16))) PoaBtRec {
     uint32_t off;                       /* start of the row's planes in the job's slab (8-cell units), as PoaRowOff.off */
     uint8_t bits[POA_BTREC_GROUPS];
 } PoaBtRec;
+#ifdef __cplusplus
+/* the kernels read the header as one uint4 (c0, p0, base | valid << 8 | ngrp << 16, off) and the bitmap as words at +16 */
+static_assert(sizeof(PoaBtRec) == POA_BTREC_BYTES && offsetof(PoaBtRec, p0) == 4 && offsetof(PoaBtRec, base) == 8 && offsetof(PoaBtRec, valid) == 9 &&
+              offsetof(PoaBtRec, ngrp) == 10 && offsetof(PoaBtRec, off) == 12 && offsetof(PoaBtRec, bits) == 16 && POA_BTREC_GROUPS % 4 == 0,
+              "PoaBtRec layout is hard-wired in poa_kernels.cu (forward writer and poa_backtrack)");
+#endif
 
 /* device pointers of one job */
 typedef struct PoaJobDesc {
