@@ -14,7 +14,9 @@
  *
  * Two engines sit behind abpoa_gpu_msa_batch.  The device-resident CHAIN engine keeps
  * the graph of every group in HBM and runs align -> fuse -> re-order -> flatten entirely on the GPU (global,
- * banded, consensus output); reads go up once, final graphs come back once.  Everything else -- local /
+ * banded, consensus output): two persistent kernels per batch -- one resident warp per group running its
+ * alignments back to back, one fuse CTA per SM serving a task queue -- so every group advances at its own
+ * pace; reads go up once, consensus bytes come back once.  Everything else -- local /
  * extend mode, RC-MSA, -s, -G, quality weights, groups that outgrow their device slot -- runs on the
  * LAUNCH engine: worker threads flatten and fuse on the host and launch one kernel grid per round, each
  * worker keeping ABPOA_GPU_PIPE_DEPTH sub-chunks in flight.  Same results either way.
