@@ -167,3 +167,19 @@ def test_device_graph_capacity_flags(emul, product_lib):
         drive(emul, product_lib, PoaConfig(), reads, K=2)
     with pytest.raises(AssertionError, match="gave up"):
         drive(emul, product_lib, PoaConfig(), reads, n_cap=330)
+
+
+def test_device_graph_code_ragged_lengths(emul, product_lib):
+    """Reads of very different lengths in one group (short reads fused into a long backbone and the other way round)."""
+    from abpoa_b200 import synth
+    rng = np.random.default_rng(11)
+    base = synth.make_group(3300, 14, 600, 0.08)
+    reads = [np.ascontiguousarray(r[: int(rng.integers(20, len(r)))]) if i % 3 == 1 else r for i, r in enumerate(base)]
+    drive(emul, product_lib, PoaConfig(), reads)
+
+
+def test_device_graph_code_high_error_amino_acid(emul, product_lib):
+    """27-letter alphabet, BLOSUM62, 20 % error: aligned sets of up to 26 members, many mismatch siblings per column."""
+    from abpoa_b200 import synth
+    cfg = synth.WORKLOADS["aa_blosum62_2k"].cfg
+    drive(emul, product_lib, cfg, synth.make_group(3400, 16, 250, 0.20, m=27), K=32)
