@@ -234,6 +234,7 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
         if (e && *e) return *e != '1';
         /* two kernels that wait for each other need to run CONCURRENTLY: under a tool that injects into the CUDA driver and
          * serialises kernel launches (ncu, compute-sanitizer) use the round schedule */
+        { const char *lb = getenv("CUDA_LAUNCH_BLOCKING"); if (lb && *lb == '1') return false; }     /* the second kernel would never be launched */
         extern char **environ;
         for (char **v = environ; v && *v; ++v)
             if (!strncmp(*v, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*v, "NV_NSIGHT_INJECTION", 19) || !strncmp(*v, "NV_COMPUTE_PROFILER", 19) ||
