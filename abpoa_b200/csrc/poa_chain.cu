@@ -229,25 +229,28 @@ int poa_chain_run(int dev, poa_arena *arena, abpoa_para_t *abpt, int n_workers, 
     if (n_cohorts > 16) n_cohorts = 16;
     /* free-running (default): every group advances at its own pace (PoaChainSync); ABPOA_GPU_CHAIN_ROUNDS=1: lock-step rounds,
      * two kernels per round and cohort */
-    const bool free_run = [] {
-        const char *e = getenv("ABPOA_GPU_CHAIN_ROUNDS");
-        if (e && *e) return *e != '1';
-        /* two kernels that wait for each other need to run CONCURRENTLY: under a tool that injects into the CUDA driver and
-         * serialises kernel launches (ncu, compute-sanitizer) use the round schedule */
-        { const char *lb = getenv("CUDA_LAUNCH_BLOCKING"); if (lb && *lb == '1') return false; }     /* the second kernel would never be launched */
+    /* two kernels that wait for each other need to run CONCURRENTLY: under a tool that injects into the CUDA driver and
+     * serialises kernel launches (ncu, compute-sanitizer), or with blocking launches, use the round schedule.  Looked up once. */
+    static const bool serialised_launches = [] {
+        { const char *lb = getenv("CUDA_LAUNCH_BLOCKING"); if (lb && *lb == '1') return true; }      /* the second kernel would never be launched */
         extern char **environ;
         for (char **v = environ; v && *v; ++v)
             if (!strncmp(*v, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*v, "NV_NSIGHT_INJECTION", 19) || !strncmp(*v, "NV_COMPUTE_PROFILER", 19) ||
-                !strncmp(*v, "NV_SANITIZER_INJECTION", 22) || !strncmp(*v, "NV_TPS_LAUNCH_", 14)) return false;
+                !strncmp(*v, "NV_SANITIZER_INJECTION", 22) || !strncmp(*v, "NV_TPS_LAUNCH_", 14)) return true;
         /* ... or whose injection library is already mapped into this process */
         if (FILE *mp = fopen("/proc/self/maps", "r")) {
             char line[512]; bool hit = false;
             while (!hit && fgets(line, sizeof line, mp))
                 hit = strstr(line, "InjectionTarget") || strstr(line, "cuda-injection") || strstr(line, "libsanitizer-collection") || strstr(line, "TreeLauncherTarget");
             fclose(mp);
-            if (hit) return false;
+            if (hit) return true;
         }
-        return true;
+        return false;
+    }();
+    const bool free_run = [] {
+        const char *e = getenv("ABPOA_GPU_CHAIN_ROUNDS");        /* per call: the tests switch schedules inside one process */
+        if (e && *e) return *e != '1';
+        return !serialised_launches;
     }();
     const double pool_margin = 1.15;
 
